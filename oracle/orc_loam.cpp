@@ -313,3 +313,32 @@ extern "C" int orc_loam_align(const float* src, size_t ns, size_t sstride, const
   if (converged) *converged = conv ? 1 : 0;
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// test hooks for the dense linear algebra restatements (tests/test_oracle_linalg.py)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int orc_test_cpqr5x3(const double* A /*5x3 row-major*/, const double* b, double* x) {
+  double a[5][3], bb[5], xx[3];
+  for (int i = 0; i < 5; i++) { for (int j = 0; j < 3; j++) a[i][j] = A[i * 3 + j]; bb[i] = b[i]; }
+  int r = cpqr_solve3<5>(a, bb, xx);
+  for (int j = 0; j < 3; j++) x[j] = xx[j];
+  return r;
+}
+extern "C" void orc_test_ldlt6(const double* A, const double* b, double* x) {
+  double a[6][6], bb[6], xx[6];
+  for (int i = 0; i < 6; i++) { for (int j = 0; j < 6; j++) a[i][j] = A[i * 6 + j]; bb[i] = b[i]; }
+  ldlt_solve<6>(a, bb, xx);
+  for (int j = 0; j < 6; j++) x[j] = xx[j];
+}
+extern "C" void orc_test_svd6(const double* A, const double* b, double* x) {
+  double a[6][6], bb[6], xx[6];
+  for (int i = 0; i < 6; i++) { for (int j = 0; j < 6; j++) a[i][j] = A[i * 6 + j]; bb[i] = b[i]; }
+  svd_solve<6>(a, bb, xx);
+  for (int j = 0; j < 6; j++) x[j] = xx[j];
+}
+extern "C" void orc_test_eig3(const double* A, double* w, double* V) {
+  double a[3][3], ww[3], vv[3][3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a[i][j] = A[i * 3 + j];
+  eig_sym3(a, ww, vv);
+  for (int i = 0; i < 3; i++) { w[i] = ww[i]; for (int j = 0; j < 3; j++) V[i * 3 + j] = vv[i][j]; }
+}

@@ -1,0 +1,778 @@
+// C ABI of the PCR CUDA library (include/pcr_cuda.h). No exceptions cross this boundary: every entry point maps
+// failures to an error code + pcr_last_error() text (SURVEY.md §8b "Errors").
+#include "../../include/pcr_cuda.h"
+#include "common.cuh"
+#include "voxel.cuh"
+#include "loam.cuh"
+#include "ndt.cuh"
+#include "vgicp.cuh"
+#include "host_math.hpp"
+#include <cfloat>
+#include <string>
+
+using namespace pcr;
+
+struct pcr_ctx {
+  pcr_params prm{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool profiling = false;
+  pcr_stats stats{};
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+
+  // staging
+  DevBuf<unsigned char> raw_src, raw_dst;
+  DevBuf<float4> src, dst, ds_in;
+  DevBuf<unsigned char> ds_out;
+  PinBuf<unsigned char> pin;
+  KeySort ks, ks_ds;
+  BBoxWork bw;
+  // downsample introspection
+  GridSpec ds_grid{};
+  size_t ds_n = 0, ds_m = 0;
+  bool ds_overflow = false;
+
+  // target state
+  bool has_target = false;
+  size_t n_target = 0;
+  CellGrid loam_grid;
+  NdtTarget ndt;
+  VgicpTarget vg;
+
+  // drivers
+  LoamDriver loam;
+  NdtDriver ndtd;
+  VgicpDriver vgd;
+
+  // VGICP: last registration (for getFitnessScore)
+  size_t last_ns = 0;
+  double last_T[16];
+  bool has_last = false;
+};
+
+static thread_local std::string g_create_error;
+
+static LoamParams loam_params(const pcr_params& p) {
+  LoamParams lp;
+  lp.max_knn_d2 = double(p.loam_max_knn_d2);
+  lp.plane_thresh = double(p.loam_plane_thresh);
+  lp.point_thresh = double(p.loam_point_thresh);
+  lp.pos_conv = double(p.loam_pos_converge);
+  lp.rot_conv = double(p.loam_rot_converge);
+  lp.max_iters = p.loam_max_iters;
+  return lp;
+}
+
+#define PCR_API_BEGIN(c)                                   \
+  if (!(c)) return PCR_ERR_INVALID;                        \
+  try {                                                    \
+    PCR_CUDA_CHECK(cudaSetDevice((c)->device));
+#define PCR_API_END(c)                                     \
+  }                                                        \
+  catch (const CudaError& e) {                             \
+    (c)->err = e.what();                                   \
+    cudaGetLastError();                                    \
+    return PCR_ERR_CUDA;                                   \
+  }                                                        \
+  catch (const std::exception& e) {                        \
+    (c)->err = e.what();                                   \
+    return PCR_ERR_INVALID;                                \
+  }
+
+static int fail(pcr_ctx* c, int code, const char* msg) {
+  c->err = msg;
+  return code;
+}
+
+extern "C" void pcr_default_params(int32_t method, pcr_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->method = method;
+  p->device = 0;
+  p->cores = 4;  // config/params.json:5
+  p->loam_max_iters = 8;
+  p->loam_max_knn_d2 = 1.0f;
+  p->loam_plane_thresh = 0.2f;
+  p->loam_point_thresh = 0.1f;
+  p->loam_pos_converge = 5e-3f;
+  p->loam_rot_converge = 5e-3f;
+  p->ndt_resolution = 1.0f;
+  p->ndt_search = PCR_NDT_DIRECT7;
+  p->ndt_max_iters = 35;
+  p->ndt_step_size = 0.1;
+  p->ndt_outlier_ratio = 0.55;
+  p->ndt_trans_eps = 0.1;
+  p->ndt_min_points = 6;
+  p->ndt_eig_mult = 0.01;
+  p->vgicp_resolution = 1.0;
+  p->vgicp_k = 20;
+  p->vgicp_max_iters = 64;
+  p->vgicp_optimizer = PCR_LSQ_LM;
+  p->vgicp_lm_max_iters = 10;
+  p->vgicp_rot_eps = 2e-3;
+  p->vgicp_trans_eps = 5e-4;
+  p->vgicp_lm_init_lambda = 1e-9;
+}
+
+extern "C" int pcr_create(const pcr_params* p, pcr_ctx** out) {
+  if (!p || !out) return PCR_ERR_INVALID;
+  *out = nullptr;
+  if (p->method < PCR_LOAM || p->method > PCR_VGICP) { g_create_error = "unknown method (expected loam|ndt|vgicp)"; return PCR_ERR_INVALID; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+    return PCR_ERR_NO_DEVICE;
+  }
+  if (p->device < 0 || p->device >= ndev) { g_create_error = "device ordinal out of range"; return PCR_ERR_NO_DEVICE; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess || prop.major < 10) {
+    g_create_error = "device is not sm_100-class (B200); kernels are built for sm_100a only";
+    return PCR_ERR_NO_DEVICE;
+  }
+  pcr_ctx* c = new pcr_ctx();
+  c->prm = *p;
+  c->device = p->device;
+  try {
+    PCR_CUDA_CHECK(cudaSetDevice(c->device));
+    PCR_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    PCR_CUDA_CHECK(cudaEventCreate(&c->ev_a));
+    PCR_CUDA_CHECK(cudaEventCreate(&c->ev_b));
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    delete c;
+    return PCR_ERR_CUDA;
+  }
+  *out = c;
+  return PCR_OK;
+}
+
+extern "C" void pcr_destroy(pcr_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  if (c->ev_a) cudaEventDestroy(c->ev_a);
+  if (c->ev_b) cudaEventDestroy(c->ev_b);
+  delete c;
+}
+
+extern "C" const char* pcr_last_error(const pcr_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int pcr_vgicp_init_for_lc(pcr_ctx* c) {
+  if (!c) return PCR_ERR_INVALID;
+  // VgicpRegister.cpp:21-28. setMaxCorrespondenceDistance(150), EuclideanFitnessEpsilon and RANSAC are no-ops for the
+  // voxel-correspondence LSQ path.
+  c->prm.vgicp_max_iters = 100;
+  c->prm.vgicp_trans_eps = 1e-6;
+  return PCR_OK;
+}
+
+extern "C" int pcr_set_profiling(pcr_ctx* c, int enable) {
+  if (!c) return PCR_ERR_INVALID;
+  c->profiling = enable != 0;
+  return PCR_OK;
+}
+
+extern "C" int pcr_get_stats(const pcr_ctx* c, pcr_stats* s) {
+  if (!c || !s) return PCR_ERR_INVALID;
+  *s = c->stats;
+  return PCR_OK;
+}
+
+// ---- uploads -------------------------------------------------------------------------------------------------------
+static const float4* upload_points(pcr_ctx* c, const void* host, size_t n, size_t stride, DevBuf<unsigned char>& raw, DevBuf<float4>& out) {
+  out.ensure(n + 1);
+  if (n == 0) return out.p;
+  raw.ensure(n * stride);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(raw.p, host, n * stride, cudaMemcpyHostToDevice, c->stream));
+  pack_points(raw.p, n, stride, out.p, c->stream);
+  return out.p;
+}
+static const float4* adopt_points(pcr_ctx* c, const void* dev, size_t n, size_t stride, DevBuf<float4>& out) {
+  out.ensure(n + 1);
+  if (n) pack_points(dev, n, stride, out.p, c->stream);
+  return out.p;
+}
+
+static int build_target(pcr_ctx* c, const float4* pts, size_t n) {
+  c->has_target = false;
+  c->n_target = n;
+  c->has_last = false;
+  int rc = 0;
+  switch (c->prm.method) {
+    case PCR_LOAM:
+      // the gate radius is sqrt(max_knn_d2): cells at least that wide make the 27-cell gather exact
+      rc = build_cell_grid(pts, n, std::max(1.0f, std::sqrt(c->prm.loam_max_knn_d2) * 1.00001f), c->loam_grid, c->ks, c->bw, c->stream);
+      break;
+    case PCR_NDT:
+      rc = ndt_build_target(pts, n, c->prm, c->ndt, c->ks, c->bw, c->stream);
+      break;
+    case PCR_VGICP:
+      rc = vgicp_build_target(pts, n, c->prm, c->vg, c->ks, c->bw, c->stream);
+      break;
+  }
+  if (rc == PCR_ERR_GRID_TOO_LARGE) return fail(c, rc, "target bounding box needs a cell table larger than the dense-table budget");
+  if (rc) return fail(c, rc, "target build failed");
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  PCR_CUDA_CHECK(cudaGetLastError());
+  c->has_target = true;
+  return PCR_OK;
+}
+
+extern "C" int pcr_set_target(pcr_ctx* c, const void* pts, size_t n, size_t stride) {
+  PCR_API_BEGIN(c)
+  if ((n && !pts) || stride < 12 || stride % 4) return fail(c, PCR_ERR_INVALID, "bad target cloud");
+  const float4* d = upload_points(c, pts, n, stride, c->raw_dst, c->dst);
+  return build_target(c, d, n);
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_set_target_device(pcr_ctx* c, const void* dev_pts, size_t n, size_t stride) {
+  PCR_API_BEGIN(c)
+  if ((n && !dev_pts) || stride < 12 || stride % 4) return fail(c, PCR_ERR_INVALID, "bad target cloud");
+  const float4* d = adopt_points(c, dev_pts, n, stride, c->dst);
+  return build_target(c, d, n);
+  PCR_API_END(c)
+}
+
+// ---- align ---------------------------------------------------------------------------------------------------------
+static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_t n_scans, double* T, int32_t* converged) {
+  if (!c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no target set");
+  pcr_stats& st = c->stats;
+  memset(&st, 0, sizeof(st));
+  st.n_source = int64_t(offs[n_scans] - offs[0]);
+  st.n_target = int64_t(c->n_target);
+  PCR_CUDA_CHECK(cudaEventRecord(c->ev_a, c->stream));
+  int rc = 0;
+  std::vector<int32_t> conv(n_scans, 0), iters(n_scans, 0);
+  switch (c->prm.method) {
+    case PCR_LOAM: {
+      std::vector<int64_t> nl(n_scans, 0);
+      rc = c->loam.align(src, offs, n_scans, c->loam_grid, loam_params(c->prm), T, conv.data(), iters.data(), nl.data(), c->profiling,
+                         c->stream);
+      st.iterations = iters[0];
+      st.evaluations = 0;
+      for (size_t i = 0; i < n_scans; i++) st.evaluations += iters[i];
+      st.n_residuals = nl[0];
+      st.kernel_launches = c->loam.launches;
+      st.ms_hot_kernel = c->loam.hot_ms;
+      st.hot_kernel_launches = c->loam.hot_launches;
+      break;
+    }
+    case PCR_NDT: {
+      std::vector<double> tp(n_scans, 0.0);
+      rc = c->ndtd.align(src, offs, n_scans, c->ndt, c->prm, T, conv.data(), iters.data(), tp.data(), c->profiling, c->stream);
+      st.iterations = iters[0];
+      st.evaluations = c->ndtd.total_evals;
+      st.hessian_evals = c->ndtd.total_hess;
+      st.score = tp[0];
+      st.kernel_launches = c->ndtd.launches;
+      st.ms_hot_kernel = c->ndtd.hot_ms;
+      st.hot_kernel_launches = c->ndtd.hot_launches;
+      break;
+    }
+    case PCR_VGICP: {
+      c->vgd.launches = 0;
+      float hot = 0.f;
+      int hotl = 0, evals = 0;
+      for (size_t i = 0; i < n_scans && rc == 0; i++) {  // independent scans, processed one after the other
+        const size_t ns = offs[i + 1] - offs[i];
+        const float4* sp = src + (offs[i] - offs[0]);
+        rc = c->vgd.compute_source_covs(sp, ns, c->prm.vgicp_k, c->ks, c->bw, c->stream);
+        if (rc) break;
+        rc = c->vgd.align(sp, ns, c->vg, c->prm, T + i * 16, &conv[i], &iters[i], c->profiling, c->stream);
+        hot += c->vgd.hot_ms;
+        hotl += c->vgd.hot_launches;
+        evals += c->vgd.n_linearize + c->vgd.n_error;
+      }
+      st.iterations = iters[0];
+      st.evaluations = evals;
+      st.n_residuals = c->vgd.last_corr;
+      st.score = c->vgd.last_cost;
+      st.kernel_launches = c->vgd.launches;
+      st.ms_hot_kernel = hot;
+      st.hot_kernel_launches = hotl;
+      // remember the last scan for getFitnessScore (pcl keeps input_ + final_transformation_)
+      c->last_ns = offs[n_scans] - offs[n_scans - 1];
+      memcpy(c->last_T, T + (n_scans - 1) * 16, sizeof(double) * 16);
+      c->has_last = true;
+      break;
+    }
+  }
+  if (rc == PCR_ERR_UNSUPPORTED) return fail(c, rc, "unsupported option (NDT KDTREE neighbourhood is not built yet)");
+  if (rc) return fail(c, rc, "align failed");
+  PCR_CUDA_CHECK(cudaEventRecord(c->ev_b, c->stream));
+  PCR_CUDA_CHECK(cudaEventSynchronize(c->ev_b));
+  PCR_CUDA_CHECK(cudaEventElapsedTime(&st.ms_total, c->ev_a, c->ev_b));
+  st.converged = conv[0];
+  if (converged)
+    for (size_t i = 0; i < n_scans; i++) converged[i] = conv[i];
+  return PCR_OK;
+}
+
+extern "C" int pcr_align(pcr_ctx* c, const void* src, size_t n, size_t stride, double T[16], int32_t* converged) {
+  PCR_API_BEGIN(c)
+  if ((n && !src) || !T || stride < 12 || stride % 4) return fail(c, PCR_ERR_INVALID, "bad source cloud");
+  const float4* d = upload_points(c, src, n, stride, c->raw_src, c->src);
+  size_t offs[2] = {0, n};
+  return align_packed(c, d, offs, 1, T, converged);
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_align_device(pcr_ctx* c, const void* dev_src, size_t n, size_t stride, double T[16], int32_t* converged) {
+  PCR_API_BEGIN(c)
+  if ((n && !dev_src) || !T || stride < 12 || stride % 4) return fail(c, PCR_ERR_INVALID, "bad source cloud");
+  const float4* d = adopt_points(c, dev_src, n, stride, c->src);
+  size_t offs[2] = {0, n};
+  return align_packed(c, d, offs, 1, T, converged);
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_scan2map(pcr_ctx* c, const void* src, size_t ns, size_t sstride, const void* dst, size_t nm, size_t dstride,
+                            double T[16], int32_t* converged) {
+  int rc = pcr_set_target(c, dst, nm, dstride);
+  if (rc) return rc;
+  return pcr_align(c, src, ns, sstride, T, converged);
+}
+
+extern "C" int pcr_batch_align(pcr_ctx* c, const void* src, const size_t* offsets, size_t n_scans, size_t stride, double* T,
+                               int32_t* converged) {
+  PCR_API_BEGIN(c)
+  if (!offsets || !T || stride < 12 || stride % 4) return fail(c, PCR_ERR_INVALID, "bad batch");
+  if (n_scans == 0) return PCR_OK;
+  const size_t n = offsets[n_scans] - offsets[0];
+  const unsigned char* base = static_cast<const unsigned char*>(src) + offsets[0] * stride;
+  const float4* d = upload_points(c, base, n, stride, c->raw_src, c->src);
+  return align_packed(c, d, offsets, n_scans, T, converged);
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_batch_align_device(pcr_ctx* c, const void* dev_src, const size_t* offsets, size_t n_scans, size_t stride, double* T,
+                                      int32_t* converged) {
+  PCR_API_BEGIN(c)
+  if (!offsets || !T || stride < 12 || stride % 4) return fail(c, PCR_ERR_INVALID, "bad batch");
+  if (n_scans == 0) return PCR_OK;
+  const size_t n = offsets[n_scans] - offsets[0];
+  const unsigned char* base = static_cast<const unsigned char*>(dev_src) + offsets[0] * stride;
+  const float4* d = adopt_points(c, base, n, stride, c->src);
+  return align_packed(c, d, offsets, n_scans, T, converged);
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_fitness(pcr_ctx* c, double* score) {
+  PCR_API_BEGIN(c)
+  if (!score) return PCR_ERR_INVALID;
+  *score = 0.0;  // PointCloudRegister::getFitnessScore() base implementation returns 0
+  if (c->prm.method != PCR_VGICP) return PCR_OK;
+  if (!c->has_target || !c->has_last) return fail(c, PCR_ERR_NO_TARGET, "getFitnessScore before scan2Map");
+  // the last source scan is still resident at the tail of c->src
+  const float4* sp = c->src.p + (size_t(c->stats.n_source) - c->last_ns);
+  return c->vgd.fitness(sp, c->last_ns, c->vg, c->last_T, DBL_MAX, score, c->stream);
+  PCR_API_END(c)
+}
+
+// ---- voxel downsample ----------------------------------------------------------------------------------------------
+static int downsample_packed(pcr_ctx* c, const float4* pts, size_t n, float leaf, void* dev_out32, size_t cap, size_t* m) {
+  c->ds_n = n;
+  c->ds_m = 0;
+  c->ds_overflow = false;
+  if (n == 0) { *m = 0; return PCR_OK; }
+  float mn[3], mx[3];
+  bbox_blocking(pts, n, mn, mx, c->bw, c->stream);
+  if (!make_grid_spec(mn, mx, leaf, c->ds_grid)) {
+    // PCL: "Leaf size is too small for the input dataset" -> the input is returned unchanged
+    c->ds_overflow = true;
+    if (cap < n) return fail(c, PCR_ERR_INVALID, "output capacity too small");
+    write_xyzi32(pts, n, dev_out32, c->stream);
+    *m = n;
+    c->ds_m = n;
+    return PCR_OK;
+  }
+  c->ks_ds.sort(pts, n, c->ds_grid, c->stream);
+  c->ks_ds.segment(c->stream);
+  if (c->ks_ds.nseg > cap) return fail(c, PCR_ERR_INVALID, "output capacity too small");
+  voxel_centroids(pts, c->ks_ds, dev_out32, c->stream);
+  *m = c->ks_ds.nseg;
+  c->ds_m = *m;
+  return PCR_OK;
+}
+
+extern "C" int pcr_voxel_downsample(pcr_ctx* c, const void* pts, size_t n, size_t stride, float leaf, void* out, size_t cap, size_t* m) {
+  PCR_API_BEGIN(c)
+  if ((n && !pts) || !m || !(leaf > 0.f) || stride < 12 || stride % 4) return fail(c, PCR_ERR_INVALID, "bad arguments");
+  const float4* d = upload_points(c, pts, n, stride, c->raw_src, c->ds_in);
+  c->ds_out.ensure(std::max<size_t>(n, 1) * 32);
+  int rc = downsample_packed(c, d, n, leaf, c->ds_out.p, std::min(cap, n), m);
+  if (rc) return rc;
+  if (*m) PCR_CUDA_CHECK(cudaMemcpyAsync(out, c->ds_out.p, *m * 32, cudaMemcpyDeviceToHost, c->stream));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  PCR_CUDA_CHECK(cudaGetLastError());
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_voxel_downsample_device(pcr_ctx* c, const void* dev_pts, size_t n, size_t stride, float leaf, void* dev_out, size_t cap,
+                                           size_t* m) {
+  PCR_API_BEGIN(c)
+  if ((n && !dev_pts) || !m || !(leaf > 0.f) || stride < 12 || stride % 4) return fail(c, PCR_ERR_INVALID, "bad arguments");
+  const float4* d = adopt_points(c, dev_pts, n, stride, c->ds_in);
+  int rc = downsample_packed(c, d, n, leaf, dev_out, cap, m);
+  if (rc) return rc;
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  PCR_CUDA_CHECK(cudaGetLastError());
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+__global__ void seg_info_kernel(const uint32_t* keys, const uint32_t* seg_start, size_t nseg, int32_t* okeys, int32_t* ocounts) {
+  size_t v = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (v >= nseg) return;
+  okeys[v] = int32_t(keys[seg_start[v]]);
+  ocounts[v] = int32_t(seg_start[v + 1] - seg_start[v]);
+}
+
+extern "C" int pcr_debug_voxel(pcr_ctx* c, int32_t* keys, int32_t* out_keys, int32_t* out_counts, int32_t grid[9]) {
+  PCR_API_BEGIN(c)
+  if (grid)
+    for (int a = 0; a < 3; a++) { grid[a] = c->ds_grid.min_b[a]; grid[3 + a] = c->ds_grid.div_b[a]; grid[6 + a] = c->ds_grid.mul[a]; }
+  if (c->ds_n == 0) return PCR_OK;
+  if (c->ds_overflow) {
+    if (keys) for (size_t i = 0; i < c->ds_n; i++) keys[i] = -1;
+    return PCR_OK;
+  }
+  if (keys) PCR_CUDA_CHECK(cudaMemcpy(keys, c->ks_ds.keys_unsorted, c->ds_n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if ((out_keys || out_counts) && c->ds_m) {
+    DevBuf<int32_t> tmp;
+    tmp.ensure(c->ds_m * 2);
+    seg_info_kernel<<<unsigned((c->ds_m + 127) / 128), 128, 0, c->stream>>>(c->ks_ds.keys, c->ks_ds.seg_start.p, c->ds_m, tmp.p, tmp.p + c->ds_m);
+    PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (out_keys) PCR_CUDA_CHECK(cudaMemcpy(out_keys, tmp.p, c->ds_m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (out_counts) PCR_CUDA_CHECK(cudaMemcpy(out_counts, tmp.p + c->ds_m, c->ds_m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+// ---- target blob (multi-GPU broadcast) ----------------------------------------------------------------------------
+namespace {
+struct BlobHeader {
+  uint64_t magic;
+  int32_t method;
+  int32_t pad;
+  uint64_t n_target;
+  uint64_t sizes[8];  // byte sizes of the sections that follow (each 256-byte aligned)
+  GridSpec g;
+  double d[4];
+  int32_t i[8];
+};
+constexpr uint64_t kMagic = 0x50435242323030ull;  // "PCRB200"
+size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct Section { const void* src; void* dst_holder; size_t bytes; };
+
+// describes the device arrays making up the built target of ctx c
+int collect_sections(pcr_ctx* c, BlobHeader& h, const void* ptrs[8]) {
+  memset(&h, 0, sizeof(h));
+  h.magic = kMagic;
+  h.method = c->prm.method;
+  h.n_target = c->n_target;
+  for (int k = 0; k < 8; k++) ptrs[k] = nullptr;
+  switch (c->prm.method) {
+    case PCR_LOAM:
+      h.g = c->loam_grid.g;
+      h.i[0] = c->loam_grid.built ? 1 : 0;
+      if (c->loam_grid.built) {
+        ptrs[0] = c->loam_grid.pts.p; h.sizes[0] = c->loam_grid.n * sizeof(float4);
+        ptrs[1] = c->loam_grid.range.p; h.sizes[1] = size_t(c->loam_grid.g.ncell) * sizeof(int2);
+      }
+      break;
+    case PCR_NDT:
+      h.g = c->ndt.g;
+      h.i[0] = c->ndt.overflow ? 1 : 0;
+      h.i[1] = int32_t(c->ndt.nleaves);
+      h.d[0] = c->ndt.d1; h.d[1] = c->ndt.d2; h.d[2] = c->ndt.d3; h.d[3] = c->ndt.resolution;
+      if (!c->ndt.overflow && c->ndt.nleaves) {
+        const size_t L = c->ndt.nleaves;
+        ptrs[0] = c->ndt.recs.p; h.sizes[0] = L * sizeof(NdtLeafRec);
+        ptrs[1] = c->ndt.table.p; h.sizes[1] = size_t(c->ndt.g.ncell) * sizeof(int32_t);
+        ptrs[2] = c->ndt.mean.p; h.sizes[2] = L * 3 * sizeof(double);
+        ptrs[3] = c->ndt.icov.p; h.sizes[3] = L * 9 * sizeof(double);
+        ptrs[4] = c->ndt.cov.p; h.sizes[4] = L * 9 * sizeof(double);
+        ptrs[5] = c->ndt.keys.p; h.sizes[5] = L * sizeof(int32_t);
+        ptrs[6] = c->ndt.npts.p; h.sizes[6] = L * sizeof(int32_t);
+      }
+      break;
+    default:
+      return PCR_ERR_UNSUPPORTED;
+  }
+  return PCR_OK;
+}
+}  // namespace
+
+extern "C" int pcr_target_blob_size(pcr_ctx* c, size_t* bytes) {
+  PCR_API_BEGIN(c)
+  if (!bytes) return PCR_ERR_INVALID;
+  if (!c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no target set");
+  BlobHeader h;
+  const void* ptrs[8];
+  int rc = collect_sections(c, h, ptrs);
+  if (rc) return fail(c, rc, "target export is implemented for loam and ndt");
+  size_t total = align256(sizeof(BlobHeader));
+  for (int k = 0; k < 8; k++) total += align256(h.sizes[k]);
+  *bytes = total;
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_target_export(pcr_ctx* c, void* dev_blob, size_t cap) {
+  PCR_API_BEGIN(c)
+  if (!c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no target set");
+  BlobHeader h;
+  const void* ptrs[8];
+  int rc = collect_sections(c, h, ptrs);
+  if (rc) return fail(c, rc, "target export is implemented for loam and ndt");
+  size_t off = align256(sizeof(BlobHeader));
+  unsigned char* base = static_cast<unsigned char*>(dev_blob);
+  for (int k = 0; k < 8; k++) {
+    if (off + align256(h.sizes[k]) > cap) return fail(c, PCR_ERR_INVALID, "blob capacity too small");
+    if (h.sizes[k]) PCR_CUDA_CHECK(cudaMemcpyAsync(base + off, ptrs[k], h.sizes[k], cudaMemcpyDeviceToDevice, c->stream));
+    off += align256(h.sizes[k]);
+  }
+  PCR_CUDA_CHECK(cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes) {
+  PCR_API_BEGIN(c)
+  if (!dev_blob || bytes < sizeof(BlobHeader)) return fail(c, PCR_ERR_INVALID, "bad blob");
+  BlobHeader h;
+  PCR_CUDA_CHECK(cudaMemcpy(&h, dev_blob, sizeof(h), cudaMemcpyDeviceToHost));
+  if (h.magic != kMagic || h.method != c->prm.method) return fail(c, PCR_ERR_INVALID, "blob does not match this context's method");
+  const unsigned char* base = static_cast<const unsigned char*>(dev_blob);
+  size_t off = align256(sizeof(BlobHeader));
+  auto take = [&](void* dst, int k) {
+    if (h.sizes[k]) PCR_CUDA_CHECK(cudaMemcpyAsync(dst, base + off, h.sizes[k], cudaMemcpyDeviceToDevice, c->stream));
+    off += align256(h.sizes[k]);
+  };
+  c->has_target = false;
+  c->n_target = h.n_target;
+  if (h.method == PCR_LOAM) {
+    c->loam_grid.g = h.g;
+    c->loam_grid.n = h.sizes[0] / sizeof(float4);
+    c->loam_grid.built = h.i[0] != 0;
+    if (c->loam_grid.built) {
+      c->loam_grid.pts.ensure(c->loam_grid.n);
+      c->loam_grid.range.ensure(size_t(h.g.ncell));
+      take(c->loam_grid.pts.p, 0);
+      take(c->loam_grid.range.p, 1);
+    }
+  } else if (h.method == PCR_NDT) {
+    NdtTarget& t = c->ndt;
+    t.g = h.g;
+    t.overflow = h.i[0] != 0;
+    t.nleaves = size_t(h.i[1]);
+    t.d1 = h.d[0]; t.d2 = h.d[1]; t.d3 = h.d[2]; t.resolution = float(h.d[3]);
+    if (!t.overflow && t.nleaves) {
+      const size_t L = t.nleaves;
+      t.recs.ensure(L); t.table.ensure(size_t(h.g.ncell)); t.mean.ensure(L * 3); t.icov.ensure(L * 9); t.cov.ensure(L * 9);
+      t.keys.ensure(L); t.npts.ensure(L);
+      take(t.recs.p, 0); take(t.table.p, 1); take(t.mean.p, 2); take(t.icov.p, 3); take(t.cov.p, 4); take(t.keys.p, 5); take(t.npts.p, 6);
+    }
+    t.built = true;
+  } else {
+    return fail(c, PCR_ERR_UNSUPPORTED, "target import is implemented for loam and ndt");
+  }
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->has_target = true;
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+// ---- parity / introspection ---------------------------------------------------------------------------------------
+extern "C" int pcr_loam_linearize(pcr_ctx* c, const void* src, size_t ns, size_t stride, const double T[16], int32_t* knn_idx,
+                                  int32_t* status, double JtJ[36], double JtE[6], int64_t* n_acc) {
+  PCR_API_BEGIN(c)
+  if (c->prm.method != PCR_LOAM) return fail(c, PCR_ERR_INVALID, "not a LOAM context");
+  if (!c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no target set");
+  const float4* d = upload_points(c, src, ns, stride, c->raw_src, c->src);
+  return c->loam.linearize(d, ns, c->loam_grid, loam_params(c->prm), T, knn_idx, status, JtJ, JtE, n_acc, c->stream);
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_loam_get_logs(pcr_ctx* c, pcr_loam_iter_log* logs, int32_t cap, int32_t* n) {
+  if (!c || !n) return PCR_ERR_INVALID;
+  int cnt = std::min(c->loam.last_log_count, cap);
+  if (logs && c->loam.h_logs.p)
+    for (int i = 0; i < cnt; i++) logs[i] = c->loam.h_logs.p[i];
+  *n = cnt;
+  return PCR_OK;
+}
+
+extern "C" int pcr_ndt_num_leaves(pcr_ctx* c, size_t* n, int32_t grid[9]) {
+  if (!c || !n) return PCR_ERR_INVALID;
+  if (c->prm.method != PCR_NDT || !c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no NDT target");
+  *n = c->ndt.overflow ? 0 : c->ndt.nleaves;
+  if (grid)
+    for (int a = 0; a < 3; a++) { grid[a] = c->ndt.g.min_b[a]; grid[3 + a] = c->ndt.g.max_b[a]; grid[6 + a] = c->ndt.g.div_b[a]; }
+  return PCR_OK;
+}
+
+extern "C" int pcr_ndt_get_leaves(pcr_ctx* c, int32_t* keys, int32_t* npts, double* mean, double* cov, double* icov) {
+  PCR_API_BEGIN(c)
+  if (c->prm.method != PCR_NDT || !c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no NDT target");
+  const size_t L = c->ndt.overflow ? 0 : c->ndt.nleaves;
+  if (!L) return PCR_OK;
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  if (keys) PCR_CUDA_CHECK(cudaMemcpy(keys, c->ndt.keys.p, L * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (npts) PCR_CUDA_CHECK(cudaMemcpy(npts, c->ndt.npts.p, L * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (mean) PCR_CUDA_CHECK(cudaMemcpy(mean, c->ndt.mean.p, L * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (cov) PCR_CUDA_CHECK(cudaMemcpy(cov, c->ndt.cov.p, L * 9 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (icov) PCR_CUDA_CHECK(cudaMemcpy(icov, c->ndt.icov.p, L * 9 * sizeof(double), cudaMemcpyDeviceToHost));
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+static int ndt_eval_one(pcr_ctx* c, const void* src, size_t ns, size_t stride, const double p[6], const float* Tf, int kind, int hess,
+                        NdtEvalResult& out) {
+  if (c->prm.method != PCR_NDT || !c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no NDT target");
+  if (c->prm.ndt_search == PCR_NDT_KDTREE) return fail(c, PCR_ERR_UNSUPPORTED, "NDT KDTREE neighbourhood is not built yet");
+  const float4* d = upload_points(c, src, ns, stride, c->raw_src, c->src);
+  uint32_t* ho = c->ndtd.h_offsets.ensure(2);
+  ho[0] = 0; ho[1] = uint32_t(ns);
+  c->ndtd.offsets.ensure(2);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(c->ndtd.offsets.p, ho, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  NdtEvalParams* ep = c->ndtd.h_params.ensure(1);
+  float Tm[16];
+  if (Tf) memcpy(Tm, Tf, sizeof(Tm)); else hm::ndt_pose_matrix_f32(p, Tm);
+  memcpy(ep->Tf, Tm, sizeof(Tm));
+  hm::ndt_angle_tables(p, ep->j_ang, ep->h_ang, ep->j_ang_d, ep->h_ang_d);
+  ep->compute_hessian = hess; ep->kind = kind; ep->scan = 0; ep->pad = 0;
+  c->ndtd.evaluate(d, c->ndtd.offsets.p, ns, c->ndt, c->prm.ndt_search, 1, false, c->stream);
+  out = c->ndtd.h_results.p[0];
+  return PCR_OK;
+}
+
+extern "C" int pcr_ndt_derivatives(pcr_ctx* c, const void* src, size_t ns, size_t stride, const double p[6], const float* Tf,
+                                   int32_t compute_hessian, double* score, double g[6], double H[36]) {
+  PCR_API_BEGIN(c)
+  NdtEvalResult r;
+  int rc = ndt_eval_one(c, src, ns, stride, p, Tf, 0, compute_hessian ? 1 : 0, r);
+  if (rc) return rc;
+  if (score) *score = r.v[0];
+  if (g) for (int i = 0; i < 6; i++) g[i] = r.v[1 + i];
+  if (H) {
+    int k = 7;
+    for (int a = 0; a < 6; a++)
+      for (int b = a; b < 6; b++) { H[a * 6 + b] = compute_hessian ? r.v[k] : 0.0; H[b * 6 + a] = H[a * 6 + b]; k++; }
+  }
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_ndt_hessian(pcr_ctx* c, const void* src, size_t ns, size_t stride, const double p[6], double H[36]) {
+  PCR_API_BEGIN(c)
+  NdtEvalResult r;
+  int rc = ndt_eval_one(c, src, ns, stride, p, nullptr, 1, 1, r);
+  if (rc) return rc;
+  int k = 7;
+  for (int a = 0; a < 6; a++)
+    for (int b = a; b < 6; b++) { H[a * 6 + b] = r.v[k]; H[b * 6 + a] = r.v[k]; k++; }
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_gicp_covariances(pcr_ctx* c, const void* pts, size_t n, size_t stride, int32_t k, double* covs, int32_t* knn_idx) {
+  PCR_API_BEGIN(c)
+  if (k < 1 || k > 32) return fail(c, PCR_ERR_INVALID, "k must be in [1, 32]");
+  if (n == 0) return PCR_OK;
+  const float4* d = upload_points(c, pts, n, stride, c->raw_src, c->src);
+  CellGrid& grid = c->vgd.src_grid;
+  int rc = build_cell_grid(d, n, 0.5f, grid, c->ks, c->bw, c->stream);
+  if (rc) return fail(c, rc, "grid too large");
+  c->vgd.src_covs.ensure(n * 6);
+  int32_t* dk = knn_idx ? c->vgd.knn_dbg.ensure(n * size_t(k)) : nullptr;
+  gicp_covariances(d, n, grid, k, c->vgd.src_covs.p, dk, c->stream);
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  PCR_CUDA_CHECK(cudaGetLastError());
+  if (covs) {
+    std::vector<double> h(n * 6);
+    PCR_CUDA_CHECK(cudaMemcpy(h.data(), c->vgd.src_covs.p, n * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) {
+      const double* s = &h[i * 6];
+      double* o = covs + i * 9;
+      o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[1]; o[4] = s[3]; o[5] = s[4]; o[6] = s[2]; o[7] = s[4]; o[8] = s[5];
+    }
+  }
+  if (knn_idx) PCR_CUDA_CHECK(cudaMemcpy(knn_idx, dk, n * size_t(k) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_vgicp_num_voxels(pcr_ctx* c, size_t* n) {
+  if (!c || !n) return PCR_ERR_INVALID;
+  if (c->prm.method != PCR_VGICP || !c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no VGICP target");
+  *n = c->vg.nvox;
+  return PCR_OK;
+}
+
+extern "C" int pcr_vgicp_get_voxels(pcr_ctx* c, int32_t* coords, int32_t* npts, double* mean, double* cov) {
+  PCR_API_BEGIN(c)
+  if (c->prm.method != PCR_VGICP || !c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no VGICP target");
+  const size_t V = c->vg.nvox;
+  if (!V) return PCR_OK;
+  std::vector<VoxelRec> h(V);
+  std::vector<int32_t> keys(V);
+  PCR_CUDA_CHECK(cudaMemcpy(h.data(), c->vg.vox.p, V * sizeof(VoxelRec), cudaMemcpyDeviceToHost));
+  PCR_CUDA_CHECK(cudaMemcpy(keys.data(), c->vg.vox_key.p, V * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (size_t v = 0; v < V; v++) {
+    if (coords) {
+      long long k = keys[v];
+      coords[v * 3] = int32_t(k % c->vg.cdim[0]) + c->vg.cmin[0];
+      coords[v * 3 + 1] = int32_t((k / c->vg.cdim[0]) % c->vg.cdim[1]) + c->vg.cmin[1];
+      coords[v * 3 + 2] = int32_t(k / ((long long)c->vg.cdim[0] * c->vg.cdim[1])) + c->vg.cmin[2];
+    }
+    if (npts) npts[v] = int32_t(h[v].n + 0.5);
+    if (mean) for (int a = 0; a < 3; a++) mean[v * 3 + a] = h[v].mean[a];
+    if (cov) {
+      const double* s = h[v].cov;
+      double* o = cov + v * 9;
+      o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[1]; o[4] = s[3]; o[5] = s[4]; o[6] = s[2]; o[7] = s[4]; o[8] = s[5];
+    }
+  }
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_vgicp_evaluate(pcr_ctx* c, const void* src, size_t ns, size_t stride, const double T0[16], const double Ti[16],
+                                  double* cost, double H[36], double b[6], int64_t* n_corr) {
+  PCR_API_BEGIN(c)
+  if (c->prm.method != PCR_VGICP || !c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no VGICP target");
+  const float4* d = upload_points(c, src, ns, stride, c->raw_src, c->src);
+  int rc = c->vgd.compute_source_covs(d, ns, c->prm.vgicp_k, c->ks, c->bw, c->stream);
+  if (rc) return fail(c, rc, "source covariance build failed");
+  uint32_t* ho = c->vgd.h_offsets.ensure(2);
+  ho[0] = 0; ho[1] = uint32_t(ns);
+  c->vgd.offsets.ensure(2);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(c->vgd.offsets.p, ho, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  VgicpEvalParams* ep = c->vgd.h_params.ensure(1);
+  memcpy(ep->T0, T0, sizeof(double) * 16);
+  memcpy(ep->Ti, Ti, sizeof(double) * 16);
+  ep->want_hb = (H || b) ? 1 : 0;
+  ep->scan = 0;
+  ep->pad[0] = ep->pad[1] = 0;
+  c->vgd.evaluate(d, c->vgd.src_covs.p, c->vgd.offsets.p, ns, c->vg, 1, false, c->stream);
+  const VgicpEvalResult& r = c->vgd.h_results.p[0];
+  if (cost) *cost = r.v[0];
+  if (H) {
+    int k = 1;
+    for (int a = 0; a < 6; a++)
+      for (int q = a; q < 6; q++) { H[a * 6 + q] = r.v[k]; H[q * 6 + a] = r.v[k]; k++; }
+  }
+  if (b) for (int a = 0; a < 6; a++) b[a] = r.v[22 + a];
+  if (n_corr) *n_corr = int64_t(r.v[28] + 0.5);
+  return PCR_OK;
+  PCR_API_END(c)
+}

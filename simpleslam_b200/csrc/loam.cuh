@@ -1,0 +1,46 @@
+// LOAM-style point-to-plane scan-to-map registration on the GPU.
+#pragma once
+#include "common.cuh"
+#include "voxel.cuh"
+#include "../../include/pcr_cuda.h"
+
+namespace pcr {
+
+struct LoamParams {
+  double max_knn_d2, plane_thresh, point_thresh, pos_conv, rot_conv;
+  int max_iters;
+};
+
+struct LoamState {  // one per scan, device resident
+  double T[16];
+  int done, converged, iters, n_last;
+  unsigned ticket;
+  int pad[3];
+};
+
+struct LoamDriver {
+  DevBuf<LoamState> states;
+  DevBuf<double> partials;
+  DevBuf<pcr_loam_iter_log> logs;
+  DevBuf<uint32_t> offsets;
+  DevBuf<int32_t> dbg_knn, dbg_status;
+  PinBuf<LoamState> h_states;
+  PinBuf<uint32_t> h_offsets;
+  PinBuf<pcr_loam_iter_log> h_logs;
+  int last_log_count = 0;
+  long long launches = 0;
+  float hot_ms = 0.f;
+  int hot_launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  ~LoamDriver();
+  // src: device float4 points of all scans, concatenated; offs: host offsets [n_scans+1].
+  // T: host, 16*n_scans doubles (column-major) in/out. Returns 0.
+  int align(const float4* src, const size_t* offs, size_t n_scans, const CellGrid& grid, const LoamParams& prm, double* T,
+            int32_t* converged, int32_t* iters_out, int64_t* n_last_out, bool profile, cudaStream_t s);
+  // one linearisation at pose T for a single scan; outputs are host pointers (nullable)
+  int linearize(const float4* src, size_t ns, const CellGrid& grid, const LoamParams& prm, const double* T, int32_t* knn_idx,
+                int32_t* status, double* JtJ, double* JtE, int64_t* n_acc, cudaStream_t s);
+};
+
+}  // namespace pcr

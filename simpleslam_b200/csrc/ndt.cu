@@ -1,0 +1,649 @@
+// pclomp NDT on the GPU. Reference: third_parties/pclomp/src/ndt_omp_impl.hpp, voxel_grid_covariance_omp_impl.hpp.
+#include "ndt.cuh"
+#include "dev_linalg.cuh"
+#include "host_math.hpp"
+#include <cfloat>
+
+namespace pcr {
+
+constexpr int kNdtBlock = 128;
+constexpr int kNdtNV = 28;
+
+// ================================================================================================================
+// N1. target voxel grid: per-leaf FP64 moments (ascending original index, like the reference's serial pass),
+// covariance, eigenvalue inflation, inverse — VoxelGridCovariance::applyFilter (voxel_grid_covariance_omp_impl.hpp:209-367)
+// ================================================================================================================
+__global__ void __launch_bounds__(128)
+ndt_leaf_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                const uint32_t* __restrict__ seg_start, size_t nseg, int min_points, double eig_mult,
+                NdtLeafRec* __restrict__ recs, int32_t* __restrict__ okeys, int32_t* __restrict__ onpts,
+                double* __restrict__ omean, double* __restrict__ ocov, double* __restrict__ oicov, int32_t* __restrict__ table,
+                float4* __restrict__ centroids) {
+  size_t l = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (l >= nseg) return;
+  const uint32_t b = seg_start[l], e = seg_start[l + 1];
+  const int n = int(e - b);
+  const uint32_t key = keys[b];
+  double sx = 0, sy = 0, sz = 0;
+  // Leaf() starts cov_ at Identity (pclomp/voxel_grid_covariance_omp.h:107) and `cov_ += pt pt^T` (impl :237)
+  double cxx = 1, cxy = 0, cxz = 0, cyy = 1, cyz = 0, czz = 1;
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+  for (uint32_t j = b; j < e; j++) {
+    const float4 p = __ldg(pts + vals[j]);
+    const double x = p.x, y = p.y, z = p.z;
+    sx += x; sy += y; sz += z;
+    cxx += x * x; cxy += x * y; cxz += x * z; cyy += y * y; cyz += y * z; czz += z * z;  // exact products
+    fx = __fadd_rn(fx, p.x); fy = __fadd_rn(fy, p.y); fz = __fadd_rn(fz, p.z);
+  }
+  const double dn = double(n);
+  double mean[3] = {sx / dn, sy / dn, sz / dn};
+  const double sum[3] = {sx, sy, sz};
+  double cov[3][3] = {{cxx, cxy, cxz}, {cxy, cyy, cyz}, {cxz, cyz, czz}};
+  double icov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  int npts = n;
+  bool in_cloud = false;
+  if (n >= min_points) {
+    in_cloud = true;
+    double c2[3][3];
+    for (int r = 0; r < 3; r++)
+      for (int q = 0; q < 3; q++) c2[r][q] = (cov[r][q] - 2 * (sum[r] * mean[q])) / dn + mean[r] * mean[q];  // :329
+    const double f = (dn - 1.0) / dn;
+    for (int r = 0; r < 3; r++)
+      for (int q = 0; q < 3; q++) cov[r][q] = c2[r][q] * f;  // :330
+    double w[3], V[3][3];
+    eig_sym3(cov, w, V);
+    if (w[0] < 0 || w[1] < 0 || w[2] <= 0) {
+      npts = -1;  // :337-341
+    } else {
+      const double mn = eig_mult * w[2];
+      if (w[0] < mn) {
+        w[0] = mn;
+        if (w[1] < mn) w[1] = mn;
+        double Vi[3][3];
+        inv3(V, Vi);
+        for (int r = 0; r < 3; r++)
+          for (int q = 0; q < 3; q++) {
+            double v = 0;
+            for (int k = 0; k < 3; k++) v += (V[r][k] * w[k]) * Vi[k][q];
+            cov[r][q] = v;  // :355 cov = evecs * diag * evecs^-1
+          }
+      }
+      inv3(cov, icov);
+      double mx = -DBL_MAX, mi = DBL_MAX;
+      for (int r = 0; r < 3; r++)
+        for (int q = 0; q < 3; q++) { mx = fmax(mx, icov[r][q]); mi = fmin(mi, icov[r][q]); }
+      if (mx == INFINITY || mi == -INFINITY) npts = -1;  // :360-364
+    }
+  } else {
+    for (int r = 0; r < 3; r++)
+      for (int q = 0; q < 3; q++) cov[r][q] = (r == q) ? 1.0 : 0.0;
+  }
+  NdtLeafRec rec;
+  for (int r = 0; r < 3; r++) {
+    rec.mean[r] = mean[r];
+    omean[l * 3 + r] = mean[r];
+    for (int q = 0; q < 3; q++) {
+      rec.icov[r * 3 + q] = float(icov[r][q]);
+      ocov[l * 9 + r * 3 + q] = cov[r][q];
+      oicov[l * 9 + r * 3 + q] = icov[r][q];
+    }
+  }
+  rec.npts = npts;
+  recs[l] = rec;
+  okeys[l] = int32_t(key);
+  onpts[l] = npts;
+  if (npts >= min_points) table[key] = int32_t(l);
+  const float fn = float(n);
+  centroids[l] = make_float4(__fdiv_rn(fx, fn), __fdiv_rn(fy, fn), __fdiv_rn(fz, fn), in_cloud ? 1.f : 0.f);
+}
+
+static void gauss_params(double resolution, double outlier_ratio, double& d1, double& d2, double& d3) {
+  // ndt_omp_impl.hpp:86-93
+  const double c1 = 10 * (1 - outlier_ratio);
+  const double c2 = outlier_ratio / std::pow(resolution, 3);
+  d3 = -std::log(c2);
+  d1 = -std::log(c1 + c2) - d3;
+  d2 = -2 * std::log((-std::log(c1 * std::exp(-0.5) + c2) - d3) / d1);
+}
+
+int ndt_build_target(const float4* pts, size_t n, const pcr_params& prm, NdtTarget& tgt, KeySort& ks, BBoxWork& bw, cudaStream_t s) {
+  tgt.built = false;
+  tgt.overflow = false;
+  tgt.nleaves = 0;
+  tgt.resolution = prm.ndt_resolution;
+  gauss_params(double(prm.ndt_resolution), prm.ndt_outlier_ratio, tgt.d1, tgt.d2, tgt.d3);
+  if (n == 0) { tgt.overflow = true; tgt.built = true; return 0; }
+  float mn[3], mx[3];
+  bbox_blocking(pts, n, mn, mx, bw, s);
+  if (!make_grid_spec(mn, mx, prm.ndt_resolution, tgt.g)) {  // :79-84 leaf size too small -> no leaves
+    tgt.overflow = true;
+    tgt.built = true;
+    return 0;
+  }
+  if (tgt.g.ncell > (1ll << 29)) return PCR_ERR_GRID_TOO_LARGE;
+  ks.sort(pts, n, tgt.g, s);
+  ks.segment(s);
+  const size_t L = ks.nseg;
+  tgt.nleaves = L;
+  tgt.recs.ensure(L); tgt.keys.ensure(L); tgt.npts.ensure(L);
+  tgt.mean.ensure(L * 3); tgt.cov.ensure(L * 9); tgt.icov.ensure(L * 9);
+  tgt.centroids.ensure(L);
+  tgt.table.ensure(size_t(tgt.g.ncell));
+  PCR_CUDA_CHECK(cudaMemsetAsync(tgt.table.p, 0xff, size_t(tgt.g.ncell) * sizeof(int32_t), s));
+  ndt_leaf_kernel<<<unsigned((L + 127) / 128), 128, 0, s>>>(pts, ks.keys, ks.vals, ks.seg_start.p, L, prm.ndt_min_points, prm.ndt_eig_mult,
+                                                           tgt.recs.p, tgt.keys.p, tgt.npts.p, tgt.mean.p, tgt.cov.p, tgt.icov.p,
+                                                           tgt.table.p, tgt.centroids.p);
+  PCR_CUDA_CHECK(cudaGetLastError());
+  tgt.built = true;
+  return 0;
+}
+
+// ================================================================================================================
+// N2 + N3 + N4. One thread per source point: float transform, DIRECT{7,1,26} voxel lookup, per-(point, leaf) FP32
+// score / gradient / Hessian terms accumulated in FP64, deterministic block + last-block reduction.
+// ================================================================================================================
+struct NdtTargetView {
+  const NdtLeafRec* recs;
+  const double* mean;
+  const double* icov;
+  const int32_t* table;
+  GridSpec g;
+  float d2f;
+  double d1, d2;
+};
+
+__constant__ int c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+
+__device__ __forceinline__ void nb_offset(int search, int ni, int& ox, int& oy, int& oz) {
+  if (search == PCR_NDT_DIRECT26) {
+    // the 26 non-centre cells, x-major
+    int k = ni >= 13 ? ni + 1 : ni;
+    ox = k / 9 - 1; oy = (k / 3) % 3 - 1; oz = k % 3 - 1;
+  } else {
+    ox = c_off7[ni][0]; oy = c_off7[ni][1]; oz = c_off7[ni][2];
+  }
+}
+
+__global__ void __launch_bounds__(kNdtBlock)
+ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, NdtTargetView tgt, int search,
+                const NdtEvalParams* __restrict__ params, NdtEvalResult* __restrict__ results, double* __restrict__ partials,
+                unsigned* __restrict__ tickets, int max_blocks) {
+  const int req = blockIdx.y;
+  __shared__ NdtEvalParams sp;
+  __shared__ double sred[kNdtNV * (kNdtBlock / 32)];
+  __shared__ int s_last;
+  {
+    const int nwords = sizeof(NdtEvalParams) / 4;
+    const int* gp = reinterpret_cast<const int*>(params + req);
+    int* spw = reinterpret_cast<int*>(&sp);
+    for (int k = threadIdx.x; k < nwords; k += kNdtBlock) spw[k] = gp[k];
+  }
+  __syncthreads();
+  const uint32_t begin = offs[sp.scan], end = offs[sp.scan + 1];
+  const int nb = int((end - begin + kNdtBlock - 1) / kNdtBlock);
+  if (int(blockIdx.x) >= nb) return;
+
+  double acc[kNdtNV];
+#pragma unroll
+  for (int k = 0; k < kNdtNV; k++) acc[k] = 0.0;
+
+  const uint32_t i = begin + blockIdx.x * kNdtBlock + threadIdx.x;
+  if (i < end) {
+    const float4 po = __ldg(src + i);
+    // pcl::transformPointCloud (float): ((m00 x + m01 y) + m02 z) + m03
+    float pt[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      pt[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(sp.Tf[r], po.x), __fmul_rn(sp.Tf[4 + r], po.y)), __fmul_rn(sp.Tf[8 + r], po.z)),
+                        sp.Tf[12 + r]);
+    // voxel of the transformed point: floor(p / leaf)  (voxel_grid_covariance_omp_impl.hpp:379-381)
+    const GridSpec& g = tgt.g;
+    float fi[3];
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      fi[a] = floorf(__fdiv_rn(pt[a], g.leaf[a]));
+      if (!(fabsf(fi[a]) < 1.0e9f)) ok = false;
+    }
+    if (ok) {
+      const int ijk[3] = {int(fi[0]), int(fi[1]), int(fi[2])};
+      const int nnb = (search == PCR_NDT_DIRECT7) ? 7 : (search == PCR_NDT_DIRECT1 ? 1 : 26);
+      if (sp.kind == 0) {
+        // ---------------- float path: computePointDerivatives (:399-440) + updateDerivatives (:485-537) ----------------
+        const bool hess = sp.compute_hessian != 0;
+        float xj[8], xh[15];
+#pragma unroll
+        for (int r = 0; r < 8; r++) xj[r] = (sp.j_ang[r][0] * po.x + sp.j_ang[r][1] * po.y) + sp.j_ang[r][2] * po.z;
+        if (hess) {
+#pragma unroll
+          for (int r = 0; r < 15; r++) xh[r] = (sp.h_ang[r][0] * po.x + sp.h_ang[r][1] * po.y) + sp.h_ang[r][2] * po.z;
+        }
+        for (int ni = 0; ni < nnb; ni++) {
+          int ox, oy, oz;
+          nb_offset(search, ni, ox, oy, oz);
+          const int cx = ijk[0] + ox, cy = ijk[1] + oy, cz = ijk[2] + oz;
+          if (cx < g.min_b[0] || cx > g.max_b[0] || cy < g.min_b[1] || cy > g.max_b[1] || cz < g.min_b[2] || cz > g.max_b[2]) continue;
+          const long long key = (long long)(cx - g.min_b[0]) * g.mul[0] + (long long)(cy - g.min_b[1]) * g.mul[1] +
+                                (long long)(cz - g.min_b[2]) * g.mul[2];
+          const int id = __ldg(tgt.table + key);
+          if (id < 0) continue;
+          const float4* rp = reinterpret_cast<const float4*>(tgt.recs + id);
+          const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
+          const double m0 = __hiloint2double(__float_as_int(r0.y), __float_as_int(r0.x));
+          const double m1 = __hiloint2double(__float_as_int(r0.w), __float_as_int(r0.z));
+          const double m2 = __hiloint2double(__float_as_int(r1.y), __float_as_int(r1.x));
+          const float C[3][3] = {{r1.z, r1.w, r2.x}, {r2.y, r2.z, r2.w}, {r3.x, r3.y, r3.z}};
+          const float xt[3] = {float(double(pt[0]) - m0), float(double(pt[1]) - m1), float(double(pt[2]) - m2)};
+          float xC[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) xC[c] = (xt[0] * C[0][c] + xt[1] * C[1][c]) + xt[2] * C[2][c];
+          const float q = (xt[0] * xC[0] + xt[1] * xC[1]) + xt[2] * xC[2];
+          float e = expf(-tgt.d2f * q * 0.5f);
+          const float score_inc = float(-tgt.d1 * double(e));
+          e = tgt.d2f * e;
+          if (e > 1.f || e < 0.f || e != e) continue;  // :506-507 contributes nothing, not even score
+          e = float(double(e) * tgt.d1);
+          // CJ = C * J, J = [I | Jang]
+          float CJ[3][6];
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            CJ[r][0] = C[r][0]; CJ[r][1] = C[r][1]; CJ[r][2] = C[r][2];
+            CJ[r][3] = C[r][1] * xj[0] + C[r][2] * xj[1];
+            CJ[r][4] = (C[r][0] * xj[2] + C[r][1] * xj[3]) + C[r][2] * xj[4];
+            CJ[r][5] = (C[r][0] * xj[5] + C[r][1] * xj[6]) + C[r][2] * xj[7];
+          }
+          float xCJ[6];
+#pragma unroll
+          for (int c = 0; c < 6; c++) xCJ[c] = (xt[0] * CJ[0][c] + xt[1] * CJ[1][c]) + xt[2] * CJ[2][c];
+          acc[0] += double(score_inc);
+#pragma unroll
+          for (int c = 0; c < 6; c++) acc[1 + c] += double(e * xCJ[c]);
+          if (hess) {
+            // J^T C J rows for the angular columns (rows 0..2 of J^T C J are CJ itself)
+            float JCJ[6][6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+              JCJ[0][c] = CJ[0][c]; JCJ[1][c] = CJ[1][c]; JCJ[2][c] = CJ[2][c];
+              JCJ[3][c] = xj[0] * CJ[1][c] + xj[1] * CJ[2][c];
+              JCJ[4][c] = (xj[2] * CJ[0][c] + xj[3] * CJ[1][c]) + xj[4] * CJ[2][c];
+              JCJ[5][c] = (xj[5] * CJ[0][c] + xj[6] * CJ[1][c]) + xj[7] * CJ[2][c];
+            }
+            // x^T C H_E blocks (only i, j >= 3 are nonzero): a b c / b d e / c e f
+            const float ha = xC[1] * xh[0] + xC[2] * xh[1];
+            const float hb = xC[1] * xh[2] + xC[2] * xh[3];
+            const float hc = xC[1] * xh[4] + xC[2] * xh[5];
+            const float hd = (xC[0] * xh[6] + xC[1] * xh[7]) + xC[2] * xh[8];
+            const float he = (xC[0] * xh[9] + xC[1] * xh[10]) + xC[2] * xh[11];
+            const float hf = (xC[0] * xh[12] + xC[1] * xh[13]) + xC[2] * xh[14];
+            const float xH[3][3] = {{ha, hb, hc}, {hb, hd, he}, {hc, he, hf}};
+            int k = 7;
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+              for (int c = r; c < 6; c++) {
+                const float hx = (r >= 3) ? xH[r - 3][c - 3] : 0.f;
+                acc[k++] += double(e * (-tgt.d2f * xCJ[r] * xCJ[c] + hx + JCJ[c][r]));
+              }
+          }
+        }
+      } else {
+        // ---------------- double path: computeHessian / updateHessian (:541-645) ----------------
+        const double x[3] = {double(po.x), double(po.y), double(po.z)};
+        double xj[8], xh[15];
+#pragma unroll
+        for (int r = 0; r < 8; r++) xj[r] = x[0] * sp.j_ang_d[r][0] + x[1] * sp.j_ang_d[r][1] + x[2] * sp.j_ang_d[r][2];
+#pragma unroll
+        for (int r = 0; r < 15; r++) xh[r] = x[0] * sp.h_ang_d[r][0] + x[1] * sp.h_ang_d[r][1] + x[2] * sp.h_ang_d[r][2];
+        // J columns (3-vectors)
+        const double Jc[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, xj[0], xj[1]}, {xj[2], xj[3], xj[4]}, {xj[5], xj[6], xj[7]}};
+        for (int ni = 0; ni < nnb; ni++) {
+          int ox, oy, oz;
+          nb_offset(search, ni, ox, oy, oz);
+          const int cx = ijk[0] + ox, cy = ijk[1] + oy, cz = ijk[2] + oz;
+          if (cx < g.min_b[0] || cx > g.max_b[0] || cy < g.min_b[1] || cy > g.max_b[1] || cz < g.min_b[2] || cz > g.max_b[2]) continue;
+          const long long key = (long long)(cx - g.min_b[0]) * g.mul[0] + (long long)(cy - g.min_b[1]) * g.mul[1] +
+                                (long long)(cz - g.min_b[2]) * g.mul[2];
+          const int id = __ldg(tgt.table + key);
+          if (id < 0) continue;
+          double C[3][3], xt[3];
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            xt[r] = double(pt[r]) - __ldg(tgt.mean + size_t(id) * 3 + r);
+#pragma unroll
+            for (int c = 0; c < 3; c++) C[r][c] = __ldg(tgt.icov + size_t(id) * 9 + r * 3 + c);
+          }
+          double Cx[3];
+#pragma unroll
+          for (int r = 0; r < 3; r++) Cx[r] = C[r][0] * xt[0] + C[r][1] * xt[1] + C[r][2] * xt[2];
+          double e = tgt.d2 * exp(-tgt.d2 * (xt[0] * Cx[0] + xt[1] * Cx[1] + xt[2] * Cx[2]) / 2);
+          if (e > 1 || e < 0 || e != e) continue;
+          e *= tgt.d1;
+          double CJ[6][3], xCJ[6];  // C * J_i and x^T C J_i
+#pragma unroll
+          for (int c = 0; c < 6; c++) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) CJ[c][r] = C[r][0] * Jc[c][0] + C[r][1] * Jc[c][1] + C[r][2] * Jc[c][2];
+            xCJ[c] = xt[0] * CJ[c][0] + xt[1] * CJ[c][1] + xt[2] * CJ[c][2];
+          }
+          // x^T C h_ij for i,j >= 3
+          auto xCh = [&](double h0, double h1, double h2) {
+            return xt[0] * (C[0][0] * h0 + C[0][1] * h1 + C[0][2] * h2) + xt[1] * (C[1][0] * h0 + C[1][1] * h1 + C[1][2] * h2) +
+                   xt[2] * (C[2][0] * h0 + C[2][1] * h1 + C[2][2] * h2);
+          };
+          const double ha = xCh(0, xh[0], xh[1]), hb = xCh(0, xh[2], xh[3]), hc = xCh(0, xh[4], xh[5]);
+          const double hd = xCh(xh[6], xh[7], xh[8]), he = xCh(xh[9], xh[10], xh[11]), hf = xCh(xh[12], xh[13], xh[14]);
+          const double xH[3][3] = {{ha, hb, hc}, {hb, hd, he}, {hc, he, hf}};
+          int k = 7;
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = r; c < 6; c++) {
+              const double hx = (r >= 3) ? xH[r - 3][c - 3] : 0.0;
+              const double jd = Jc[c][0] * CJ[r][0] + Jc[c][1] * CJ[r][1] + Jc[c][2] * CJ[r][2];
+              acc[k++] += e * (-tgt.d2 * xCJ[r] * xCJ[c] + hx + jd);
+            }
+        }
+      }
+    }
+  }
+
+  double r = block_reduce_vec<kNdtNV, kNdtBlock>(acc, sred);
+  double* my = partials + (size_t(req) * max_blocks + blockIdx.x) * kNdtNV;
+  if (threadIdx.x < kNdtNV) my[threadIdx.x] = r;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(tickets + req, 1u);
+    s_last = (t == unsigned(nb - 1));
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < kNdtNV) {
+    const double* base = partials + size_t(req) * max_blocks * kNdtNV + threadIdx.x;
+    double tsum = 0.0;
+    for (int b = 0; b < nb; b++) tsum += __ldcg(base + size_t(b) * kNdtNV);
+    results[req].v[threadIdx.x] = tsum;
+  }
+  if (threadIdx.x == 0) tickets[req] = 0;
+}
+
+NdtDriver::~NdtDriver() {
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+}
+
+void NdtDriver::evaluate(const float4* src, const uint32_t* d_offs, size_t max_pts, const NdtTarget& tgt, int search, int count,
+                         bool profile, cudaStream_t s) {
+  if (count == 0) return;
+  int max_blocks = int((max_pts + kNdtBlock - 1) / kNdtBlock);
+  if (max_blocks < 1) max_blocks = 1;
+  d_params.ensure(count);
+  d_results.ensure(count);
+  partials.ensure(size_t(count) * max_blocks * kNdtNV);
+  if (tickets.cap < size_t(count)) {
+    tickets.ensure(count);
+    PCR_CUDA_CHECK(cudaMemsetAsync(tickets.p, 0, tickets.cap * sizeof(unsigned), s));
+  }
+  PCR_CUDA_CHECK(cudaMemcpyAsync(d_params.p, h_params.p, size_t(count) * sizeof(NdtEvalParams), cudaMemcpyHostToDevice, s));
+  PCR_CUDA_CHECK(cudaMemsetAsync(d_results.p, 0, size_t(count) * sizeof(NdtEvalResult), s));
+  if (!tgt.overflow && tgt.nleaves > 0 && max_pts > 0) {
+    NdtTargetView v;
+    v.recs = tgt.recs.p; v.mean = tgt.mean.p; v.icov = tgt.icov.p; v.table = tgt.table.p; v.g = tgt.g;
+    v.d1 = tgt.d1; v.d2 = tgt.d2; v.d2f = float(tgt.d2);
+    if (profile) {
+      if (!ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
+      PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
+    }
+    ndt_eval_kernel<<<dim3(max_blocks, count), kNdtBlock, 0, s>>>(src, d_offs, v, search, d_params.p, d_results.p, partials.p, tickets.p,
+                                                                  max_blocks);
+    if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev1, s));
+    launches++;
+    hot_launches++;
+  }
+  h_results.ensure(count);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(h_results.p, d_results.p, size_t(count) * sizeof(NdtEvalResult), cudaMemcpyDeviceToHost, s));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(s));
+  PCR_CUDA_CHECK(cudaGetLastError());
+  if (profile && !tgt.overflow && tgt.nleaves > 0 && max_pts > 0) {
+    float ms = 0.f;
+    PCR_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+    hot_ms += ms;
+  }
+}
+
+// ================================================================================================================
+// N5. Newton + More-Thuente driver (ndt_omp_impl.hpp:81-171, 773-932) as a per-scan state machine, so that a batch
+// of independent scans advances in lock-step with ONE kernel launch per round.
+// ================================================================================================================
+namespace {
+struct ScanState {
+  enum Phase { INIT_EVAL, LS_FIRST, LS_LOOP, LS_HESSIAN, FINISHED } phase = INIT_EVAL;
+  double p[6];
+  double score = 0;
+  double g[6];
+  double H[36];
+  float final_T[16];
+  float eval_T[16];
+  double eval_p[6];
+  int eval_kind = 0, eval_hess = 1;
+  int nr_iterations = 0;
+  bool converged = false;
+  // line search
+  double step_dir[6], phi_0, d_phi_0, a_l, f_l, g_l, a_u, f_u, g_u, a_t, x_t[6], phi_t, d_phi_t, psi_t, d_psi_t;
+  bool interval_converged, open_interval;
+  int step_iterations;
+  int n_evals = 0, n_hess = 0;
+};
+
+struct NdtLogic {
+  const pcr_params& prm;
+  static constexpr double mu = 1.e-4, nu = 0.9;
+  static constexpr int max_step_iterations = 10;
+
+  void request_deriv(ScanState& st, const float* T, const double* p, bool hess) {
+    std::memcpy(st.eval_T, T, sizeof(float) * 16);
+    std::memcpy(st.eval_p, p, sizeof(double) * 6);
+    st.eval_kind = 0;
+    st.eval_hess = hess ? 1 : 0;
+  }
+  void start(ScanState& st, const double* Tguess) {
+    float guess[16];
+    bool ident = true;
+    for (int i = 0; i < 16; i++) {
+      guess[i] = static_cast<float>(Tguess[i]);  // NdtRegister.cpp:27 res.matrix().cast<float>()
+      if (guess[i] != ((i % 5 == 0) ? 1.f : 0.f)) ident = false;
+    }
+    for (int i = 0; i < 16; i++) st.final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
+    if (!ident) std::memcpy(st.final_T, guess, sizeof(guess));  // ndt_omp_impl.hpp:95-101
+    float Rm[9], eul[3];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) Rm[r * 3 + c] = st.final_T[c * 4 + r];
+    hm::euler_xyz_f32(Rm, eul);  // :103-111
+    st.p[0] = st.final_T[12]; st.p[1] = st.final_T[13]; st.p[2] = st.final_T[14];
+    st.p[3] = eul[0]; st.p[4] = eul[1]; st.p[5] = eul[2];
+    st.nr_iterations = 0;
+    st.converged = false;
+    st.phase = ScanState::INIT_EVAL;
+    request_deriv(st, st.final_T, st.p, true);
+  }
+  void take(ScanState& st, const NdtEvalResult& r, bool with_hessian) {
+    st.score = r.v[0];
+    for (int i = 0; i < 6; i++) st.g[i] = r.v[1 + i];
+    int k = 7;
+    for (int a = 0; a < 6; a++)
+      for (int b = a; b < 6; b++) { st.H[a * 6 + b] = with_hessian ? r.v[k] : 0.0; st.H[b * 6 + a] = st.H[a * 6 + b]; k++; }
+  }
+  void set_trial(ScanState& st) {
+    st.a_t = std::min(st.a_t, prm.ndt_step_size);
+    st.a_t = std::max(st.a_t, prm.ndt_trans_eps / 2);
+    for (int i = 0; i < 6; i++) st.x_t[i] = st.p[i] + st.step_dir[i] * st.a_t;
+    hm::ndt_pose_matrix_f32(st.x_t, st.final_T);
+  }
+  void begin_outer(ScanState& st) {
+    double b[6], delta_p[6];
+    for (int i = 0; i < 6; i++) b[i] = -st.g[i];
+    hm::svd6_solve(st.H, b, delta_p);  // :127-129
+    double nrm = 0;
+    for (int i = 0; i < 6; i++) nrm += delta_p[i] * delta_p[i];
+    nrm = std::sqrt(nrm);
+    if (nrm == 0 || nrm != nrm) {  // :134-139
+      st.converged = nrm == nrm;
+      st.phase = ScanState::FINISHED;
+      return;
+    }
+    for (int i = 0; i < 6; i++) st.step_dir[i] = delta_p[i] / nrm;
+    // computeStepLengthMT :773-
+    st.phi_0 = -st.score;
+    double d = 0;
+    for (int i = 0; i < 6; i++) d += st.g[i] * st.step_dir[i];
+    st.d_phi_0 = -d;
+    if (st.d_phi_0 >= 0) {
+      if (st.d_phi_0 == 0) { end_outer(st, 0.0); return; }
+      st.d_phi_0 *= -1;
+      for (int i = 0; i < 6; i++) st.step_dir[i] *= -1;
+    }
+    st.step_iterations = 0;
+    st.a_l = 0; st.a_u = 0;
+    st.f_l = hm::mt_psi(st.a_l, st.phi_0, st.phi_0, st.d_phi_0, mu);
+    st.g_l = hm::mt_dpsi(st.d_phi_0, st.d_phi_0, mu);
+    st.f_u = hm::mt_psi(st.a_u, st.phi_0, st.phi_0, st.d_phi_0, mu);
+    st.g_u = hm::mt_dpsi(st.d_phi_0, st.d_phi_0, mu);
+    st.interval_converged = (prm.ndt_step_size - prm.ndt_trans_eps / 2) < 0;
+    st.open_interval = true;
+    st.a_t = nrm;
+    set_trial(st);
+    st.phase = ScanState::LS_FIRST;
+    request_deriv(st, st.final_T, st.x_t, true);
+  }
+  void after_eval(ScanState& st) {
+    st.phi_t = -st.score;
+    double d = 0;
+    for (int i = 0; i < 6; i++) d += st.g[i] * st.step_dir[i];
+    st.d_phi_t = -d;
+    st.psi_t = hm::mt_psi(st.a_t, st.phi_t, st.phi_0, st.d_phi_0, mu);
+    st.d_psi_t = hm::mt_dpsi(st.d_phi_t, st.d_phi_0, mu);
+  }
+  void ls_continue(ScanState& st) {
+    if (!st.interval_converged && st.step_iterations < max_step_iterations && !(st.psi_t <= 0 && st.d_phi_t <= -nu * st.d_phi_0)) {
+      if (st.open_interval) st.a_t = hm::mt_trial_value(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, st.psi_t, st.d_psi_t);
+      else st.a_t = hm::mt_trial_value(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, st.phi_t, st.d_phi_t);
+      set_trial(st);
+      st.phase = ScanState::LS_LOOP;
+      request_deriv(st, st.final_T, st.x_t, false);
+      return;
+    }
+    if (st.step_iterations) {  // :928-929 computeHessian
+      st.phase = ScanState::LS_HESSIAN;
+      std::memcpy(st.eval_T, st.final_T, sizeof(float) * 16);
+      std::memcpy(st.eval_p, st.x_t, sizeof(double) * 6);
+      st.eval_kind = 1;
+      st.eval_hess = 1;
+      return;
+    }
+    end_outer(st, st.a_t);
+  }
+  void end_outer(ScanState& st, double a) {
+    for (int i = 0; i < 6; i++) st.p[i] += st.step_dir[i] * a;
+    if (st.nr_iterations > prm.ndt_max_iters || (st.nr_iterations && (std::fabs(a) < prm.ndt_trans_eps))) st.converged = true;  // :158-162
+    st.nr_iterations++;
+    if (st.converged) { st.phase = ScanState::FINISHED; return; }
+    begin_outer(st);
+  }
+  void on_result(ScanState& st, const NdtEvalResult& r) {
+    switch (st.phase) {
+      case ScanState::INIT_EVAL:
+        st.n_evals++;
+        take(st, r, true);
+        begin_outer(st);
+        break;
+      case ScanState::LS_FIRST:
+        st.n_evals++;
+        take(st, r, true);
+        after_eval(st);
+        ls_continue(st);
+        break;
+      case ScanState::LS_LOOP: {
+        st.n_evals++;
+        take(st, r, false);
+        after_eval(st);
+        if (st.open_interval && (st.psi_t <= 0 && st.d_psi_t >= 0)) {
+          st.open_interval = false;
+          st.f_l = st.f_l + st.phi_0 - mu * st.d_phi_0 * st.a_l;
+          st.g_l = st.g_l + mu * st.d_phi_0;
+          st.f_u = st.f_u + st.phi_0 - mu * st.d_phi_0 * st.a_u;
+          st.g_u = st.g_u + mu * st.d_phi_0;
+        }
+        if (st.open_interval)
+          st.interval_converged = hm::mt_update_interval(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, st.psi_t, st.d_psi_t);
+        else
+          st.interval_converged = hm::mt_update_interval(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, st.phi_t, st.d_phi_t);
+        st.step_iterations++;
+        ls_continue(st);
+        break;
+      }
+      case ScanState::LS_HESSIAN: {
+        st.n_hess++;
+        int k = 7;
+        for (int a = 0; a < 6; a++)
+          for (int b = a; b < 6; b++) { st.H[a * 6 + b] = r.v[k]; st.H[b * 6 + a] = r.v[k]; k++; }
+        end_outer(st, st.a_t);
+        break;
+      }
+      default: break;
+    }
+  }
+};
+}  // namespace
+
+static void fill_params(NdtEvalParams& ep, const float* T, const double* p, int kind, int hess, int scan) {
+  std::memcpy(ep.Tf, T, sizeof(float) * 16);
+  hm::ndt_angle_tables(p, ep.j_ang, ep.h_ang, ep.j_ang_d, ep.h_ang_d);
+  ep.compute_hessian = hess;
+  ep.kind = kind;
+  ep.scan = scan;
+  ep.pad = 0;
+}
+
+int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, const NdtTarget& tgt, const pcr_params& prm, double* T,
+                     int32_t* converged, int32_t* iters, double* trans_prob, bool profile, cudaStream_t s) {
+  launches = 0; hot_ms = 0.f; hot_launches = 0; total_evals = 0; total_hess = 0;
+  if (n_scans == 0) return 0;
+  if (prm.ndt_search == PCR_NDT_KDTREE) return PCR_ERR_UNSUPPORTED;
+  uint32_t* ho = h_offsets.ensure(n_scans + 1);
+  size_t max_pts = 0;
+  for (size_t i = 0; i <= n_scans; i++) ho[i] = uint32_t(offs[i] - offs[0]);
+  for (size_t i = 0; i < n_scans; i++) max_pts = std::max(max_pts, size_t(offs[i + 1] - offs[i]));
+  offsets.ensure(n_scans + 1);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(offsets.p, ho, (n_scans + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  std::vector<ScanState> st(n_scans);
+  NdtLogic logic{prm};
+  for (size_t i = 0; i < n_scans; i++) logic.start(st[i], T + i * 16);
+  h_params.ensure(n_scans);
+  std::vector<int> active;
+  active.reserve(n_scans);
+  for (;;) {
+    active.clear();
+    for (size_t i = 0; i < n_scans; i++)
+      if (st[i].phase != ScanState::FINISHED) active.push_back(int(i));
+    if (active.empty()) break;
+    for (size_t k = 0; k < active.size(); k++) {
+      ScanState& ss = st[active[k]];
+      fill_params(h_params.p[k], ss.eval_T, ss.eval_p, ss.eval_kind, ss.eval_hess, active[k]);
+    }
+    evaluate(src, offsets.p, max_pts, tgt, prm.ndt_search, int(active.size()), profile, s);
+    for (size_t k = 0; k < active.size(); k++) logic.on_result(st[active[k]], h_results.p[k]);
+  }
+  for (size_t i = 0; i < n_scans; i++) {
+    for (int q = 0; q < 16; q++) T[i * 16 + q] = double(st[i].final_T[q]);  // NdtRegister.cpp:28
+    if (converged) converged[i] = st[i].converged ? 1 : 0;
+    if (iters) iters[i] = st[i].nr_iterations;
+    const size_t ns = offs[i + 1] - offs[i];
+    if (trans_prob) trans_prob[i] = st[i].score / double(ns);
+    total_evals += st[i].n_evals;
+    total_hess += st[i].n_hess;
+  }
+  return 0;
+}
+
+}  // namespace pcr

@@ -1,0 +1,551 @@
+// FastVGICP on the GPU. Reference: third_parties/pclomp/src/fast_gicp_impl.hpp, fast_vgicp_impl.hpp,
+// pclomp/fast_vgicp_voxel.hpp, lsq_registration_impl.hpp, so3/so3.hpp.
+#include "vgicp.cuh"
+#include "dev_linalg.cuh"
+#include "host_math.hpp"
+#include <cfloat>
+
+namespace pcr {
+
+constexpr int kVgBlock = 128;
+constexpr int kVgNV = 29;  // cost, 21 H, 6 b, count
+constexpr int kMaxK = 32;
+
+// ================================================================================================================
+// exact k-NN on the uniform grid with Chebyshev ring expansion. Float metric of FLANN L2_Simple<float>
+// (float diff, float square, float accumulate x->y->z), ties broken by (d2, original index).
+// Terminates when the k-th distance is provably smaller than the distance to every unvisited cell.
+// ================================================================================================================
+__device__ __forceinline__ float dist2_f32(float qx, float qy, float qz, const float4& m) {
+  const float dx = __fsub_rn(qx, m.x), dy = __fsub_rn(qy, m.y), dz = __fsub_rn(qz, m.z);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ int knn_ring_f32(const CellGridView& grid, float qx, float qy, float qz, int k, float* bd, int* bi, double slack_cells) {
+  const GridSpec& g = grid.g;
+  int cnt = 0;
+  const float q[3] = {qx, qy, qz};
+  int c[3];
+  double margin = 1e30;
+  for (int a = 0; a < 3; a++) {
+    const float s = __fmul_rn(q[a], g.inv_leaf[a]);
+    float fc = __fsub_rn(floorf(s), float(g.min_b[a]));
+    fc = fminf(fmaxf(fc, -1.0e9f), 1.0e9f);
+    c[a] = int(fc);
+    const double fr = double(s) - floor(double(s));
+    margin = fmin(margin, fmin(fr, 1.0 - fr));
+  }
+  margin -= slack_cells;
+  int rstart = 0, rmax = 0;
+  for (int a = 0; a < 3; a++) {
+    rstart = max(rstart, max(-c[a], c[a] - (g.div_b[a] - 1)));
+    rmax = max(rmax, max(c[a], g.div_b[a] - 1 - c[a]));
+  }
+  const double leaf = double(g.leaf[0]);
+  for (int r = rstart; r <= rmax; r++) {
+    const int zlo = max(c[2] - r, 0), zhi = min(c[2] + r, g.div_b[2] - 1);
+    const int ylo = max(c[1] - r, 0), yhi = min(c[1] + r, g.div_b[1] - 1);
+    for (int z = zlo; z <= zhi; z++) {
+      const bool zedge = (z == c[2] - r) || (z == c[2] + r);
+      for (int y = ylo; y <= yhi; y++) {
+        const bool edge = zedge || (y == c[1] - r) || (y == c[1] + r);
+        const long long rowbase = (long long)y * g.mul[1] + (long long)z * g.mul[2];
+        const int xstep = (edge || r == 0) ? 1 : 2 * r;
+        for (int x = c[0] - r; x <= c[0] + r; x += xstep) {
+          if (x < 0 || x >= g.div_b[0]) continue;
+          const int2 rg = __ldg(grid.range + rowbase + x);
+          for (int j = rg.x; j < rg.y; j++) {
+            const float4 m = __ldg(grid.pts + j);
+            const float d2 = dist2_f32(qx, qy, qz, m);
+            const int idx = __float_as_int(m.w);
+            if (cnt == k && !(d2 < bd[k - 1] || (d2 == bd[k - 1] && idx < bi[k - 1]))) continue;
+            int p = (cnt < k) ? cnt : k - 1;
+            while (p > 0 && (bd[p - 1] > d2 || (bd[p - 1] == d2 && bi[p - 1] > idx))) {
+              bd[p] = bd[p - 1]; bi[p] = bi[p - 1]; p--;
+            }
+            bd[p] = d2; bi[p] = idx;
+            if (cnt < k) cnt++;
+          }
+        }
+      }
+    }
+    if (cnt == k) {
+      const double reach = (double(r) + margin) * leaf;
+      if (reach > 0.0 && double(bd[k - 1]) < reach * reach * (1.0 - 1e-6)) break;
+    }
+  }
+  return cnt;
+}
+
+static double grid_slack_cells(const GridSpec& g) {
+  // float rounding of x*inv_leaf moves a point by at most ~|cell index| * 2^-23 cells across a cell face
+  double m = 1.0;
+  for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs(double(g.min_b[a])), std::fabs(double(g.max_b[a]))));
+  return std::max(1e-3, m * 4.8e-7);
+}
+
+// ================================================================================================================
+// V1. FastGICP::calculate_covariances (fast_gicp_impl.hpp:241-298): k-NN (self included), cov = N N^T / k of the
+// mean-centred neighbours (FP64), PLANE regularisation U diag(1,1,1e-3) V^T.
+// ================================================================================================================
+__global__ void __launch_bounds__(128)
+gicp_cov_kernel(const float4* __restrict__ pts, size_t n, CellGridView grid, int k, double slack, double* __restrict__ covs,
+                int32_t* __restrict__ knn_idx) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float bd[kMaxK];
+  int bi[kMaxK];
+  const float4 q = __ldg(pts + i);
+  const int found = knn_ring_f32(grid, q.x, q.y, q.z, k, bd, bi, slack);
+  if (knn_idx)
+    for (int j = 0; j < k; j++) knn_idx[i * k + j] = j < found ? bi[j] : -1;
+  double mean[3] = {0, 0, 0};
+  for (int j = 0; j < found; j++) {
+    const float4 p = __ldg(pts + bi[j]);
+    mean[0] += double(p.x); mean[1] += double(p.y); mean[2] += double(p.z);
+  }
+  const double dk = double(k);
+  mean[0] /= dk; mean[1] /= dk; mean[2] /= dk;
+  double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int j = 0; j < found; j++) {
+    const float4 p = __ldg(pts + bi[j]);
+    const double d[3] = {double(p.x) - mean[0], double(p.y) - mean[1], double(p.z) - mean[2]};
+    for (int r = 0; r < 3; r++)
+      for (int c = r; c < 3; c++) cov[r][c] += d[r] * d[c];
+  }
+  for (int r = 0; r < 3; r++)
+    for (int c = r; c < 3; c++) { cov[r][c] /= dk; cov[c][r] = cov[r][c]; }
+  double w[3], V[3][3];
+  eig_sym3(cov, w, V);  // ascending; the SVD's descending singular values get (1, 1, 1e-3)
+  const double vals[3] = {1e-3, 1.0, 1.0};
+  double* o = covs + i * 6;
+  int t = 0;
+  for (int r = 0; r < 3; r++)
+    for (int c = r; c < 3; c++) {
+      double v = 0;
+      for (int e = 2; e >= 0; e--) v += (V[r][e] * vals[e]) * V[c][e];
+      o[t++] = v;
+    }
+}
+
+void gicp_covariances(const float4* pts, size_t n, const CellGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s) {
+  if (n == 0) return;
+  gicp_cov_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(pts, n, view_of(grid), k, grid_slack_cells(grid.g), covs, knn_idx);
+}
+
+// ================================================================================================================
+// V2. GaussianVoxelMap::create_voxelmap, ADDITIVE (fast_vgicp_voxel.hpp:105-174): coord = floor(x / res - 0.5) in FP64
+// ================================================================================================================
+__device__ __forceinline__ int vg_coord(double x, double res) { return int(floor(__dsub_rn(__ddiv_rn(x, res), 0.5))); }
+
+__global__ void __launch_bounds__(256)
+vg_key_kernel(const float4* __restrict__ pts, size_t n, double res, int c0, int c1, int c2, int d0, int d1, uint32_t* __restrict__ keys) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(pts + i);
+  const int x = vg_coord(double(p.x), res) - c0, y = vg_coord(double(p.y), res) - c1, z = vg_coord(double(p.z), res) - c2;
+  keys[i] = uint32_t(x) + uint32_t(d0) * (uint32_t(y) + uint32_t(d1) * uint32_t(z));
+}
+
+__global__ void __launch_bounds__(128)
+vg_voxel_kernel(const float4* __restrict__ pts, const double* __restrict__ covs, const uint32_t* __restrict__ keys,
+                const uint32_t* __restrict__ vals, const uint32_t* __restrict__ seg_start, size_t nseg, VoxelRec* __restrict__ vox,
+                int32_t* __restrict__ vox_key, int32_t* __restrict__ table) {
+  size_t v = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (v >= nseg) return;
+  const uint32_t b = seg_start[v], e = seg_start[v + 1];
+  double m[3] = {0, 0, 0}, c[6] = {0, 0, 0, 0, 0, 0};
+  for (uint32_t j = b; j < e; j++) {  // ascending original index == the reference's serial append order
+    const uint32_t idx = vals[j];
+    const float4 p = __ldg(pts + idx);
+    m[0] += double(p.x); m[1] += double(p.y); m[2] += double(p.z);
+    const double* cp = covs + size_t(idx) * 6;
+#pragma unroll
+    for (int t = 0; t < 6; t++) c[t] += cp[t];
+  }
+  const double dn = double(e - b);
+  VoxelRec r;
+  for (int t = 0; t < 3; t++) r.mean[t] = m[t] / dn;
+  for (int t = 0; t < 6; t++) r.cov[t] = c[t] / dn;
+  r.n = dn;
+  vox[v] = r;
+  const uint32_t key = keys[b];
+  vox_key[v] = int32_t(key);
+  table[key] = int32_t(v);
+}
+
+int vgicp_build_target(const float4* pts, size_t n, const pcr_params& prm, VgicpTarget& tgt, KeySort& ks, BBoxWork& bw, cudaStream_t s) {
+  tgt.built = false;
+  tgt.n = n;
+  tgt.nvox = 0;
+  tgt.resolution = prm.vgicp_resolution;
+  if (n == 0) { tgt.built = true; return 0; }
+  if (prm.vgicp_k > kMaxK || prm.vgicp_k < 1) return PCR_ERR_INVALID;
+  // kNN grid (0.5 m cells) + per-point covariances
+  int rc = build_cell_grid(pts, n, 0.5f, tgt.grid, ks, bw, s);
+  if (rc) return rc;
+  tgt.covs.ensure(n * 6);
+  gicp_covariances(pts, n, tgt.grid, prm.vgicp_k, tgt.covs.p, nullptr, s);
+  // voxel map
+  float mn[3], mx[3];
+  bbox_blocking(pts, n, mn, mx, bw, s);
+  long long ncell = 1;
+  for (int a = 0; a < 3; a++) {
+    tgt.cmin[a] = int(std::floor(double(mn[a]) / tgt.resolution - 0.5));
+    const int cmax = int(std::floor(double(mx[a]) / tgt.resolution - 0.5));
+    tgt.cdim[a] = cmax - tgt.cmin[a] + 1;
+    ncell *= tgt.cdim[a];
+    if (ncell > (1ll << 29)) return PCR_ERR_GRID_TOO_LARGE;
+  }
+  tgt.ncell = ncell;
+  ks.k0.ensure(n);
+  vg_key_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(pts, n, tgt.resolution, tgt.cmin[0], tgt.cmin[1], tgt.cmin[2], tgt.cdim[0],
+                                                         tgt.cdim[1], ks.k0.p);
+  ks.sort_keys_in_k0(n, ncell, s);
+  ks.segment(s);
+  tgt.nvox = ks.nseg;
+  tgt.vox.ensure(tgt.nvox);
+  tgt.vox_key.ensure(tgt.nvox);
+  tgt.table.ensure(size_t(ncell));
+  PCR_CUDA_CHECK(cudaMemsetAsync(tgt.table.p, 0xff, size_t(ncell) * sizeof(int32_t), s));
+  vg_voxel_kernel<<<unsigned((tgt.nvox + 127) / 128), 128, 0, s>>>(pts, tgt.covs.p, ks.keys, ks.vals, ks.seg_start.p, tgt.nvox, tgt.vox.p,
+                                                                  tgt.vox_key.p, tgt.table.p);
+  PCR_CUDA_CHECK(cudaGetLastError());
+  tgt.built = true;
+  return 0;
+}
+
+// ================================================================================================================
+// V3 + V4. update_correspondences (DIRECT1) + linearize / compute_error fused: one thread per source point.
+// Correspondence and Mahalanobis matrix come from T0 (the linearisation point, fast_vgicp_impl.hpp:73-116);
+// the error is evaluated at Ti (Ti = T0 for linearize, Ti = delta*T0 for compute_error, :183-204).
+// ================================================================================================================
+struct VgTargetView {
+  const VoxelRec* vox;
+  const int32_t* table;
+  double res;
+  int cmin[3], cdim[3];
+};
+
+__device__ __forceinline__ void xform_exact(const double* T, double x, double y, double z, double* o) {
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+    o[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[r], x), __dmul_rn(T[4 + r], y)), __dmul_rn(T[8 + r], z)), T[12 + r]);
+}
+
+__global__ void __launch_bounds__(kVgBlock)
+vgicp_eval_kernel(const float4* __restrict__ src, const double* __restrict__ src_covs, const uint32_t* __restrict__ offs, VgTargetView tgt,
+                  const VgicpEvalParams* __restrict__ params, VgicpEvalResult* __restrict__ results, double* __restrict__ partials,
+                  unsigned* __restrict__ tickets, int max_blocks) {
+  const int req = blockIdx.y;
+  __shared__ VgicpEvalParams sp;
+  __shared__ double sred[kVgNV * (kVgBlock / 32)];
+  __shared__ int s_last;
+  {
+    const int nwords = sizeof(VgicpEvalParams) / 4;
+    const int* gp = reinterpret_cast<const int*>(params + req);
+    int* spw = reinterpret_cast<int*>(&sp);
+    for (int k = threadIdx.x; k < nwords; k += kVgBlock) spw[k] = gp[k];
+  }
+  __syncthreads();
+  const uint32_t begin = offs[sp.scan], end = offs[sp.scan + 1];
+  const int nb = int((end - begin + kVgBlock - 1) / kVgBlock);
+  if (int(blockIdx.x) >= nb) return;
+
+  double acc[kVgNV];
+#pragma unroll
+  for (int k = 0; k < kVgNV; k++) acc[k] = 0.0;
+  const uint32_t i = begin + blockIdx.x * kVgBlock + threadIdx.x;
+  if (i < end) {
+    const float4 p = __ldg(src + i);
+    const double px = double(p.x), py = double(p.y), pz = double(p.z);
+    double t0[3];
+    xform_exact(sp.T0, px, py, pz, t0);
+    const int cx = vg_coord(t0[0], tgt.res) - tgt.cmin[0], cy = vg_coord(t0[1], tgt.res) - tgt.cmin[1],
+              cz = vg_coord(t0[2], tgt.res) - tgt.cmin[2];
+    if (cx >= 0 && cx < tgt.cdim[0] && cy >= 0 && cy < tgt.cdim[1] && cz >= 0 && cz < tgt.cdim[2]) {
+      const long long key = cx + (long long)tgt.cdim[0] * (cy + (long long)tgt.cdim[1] * cz);
+      const int vid = __ldg(tgt.table + key);
+      if (vid >= 0) {
+        const double2* vp = reinterpret_cast<const double2*>(tgt.vox + vid);
+        const double2 v0 = __ldg(vp), v1 = __ldg(vp + 1), v2 = __ldg(vp + 2), v3 = __ldg(vp + 3), v4 = __ldg(vp + 4);
+        const double mB[3] = {v0.x, v0.y, v1.x};
+        const double cB[6] = {v1.y, v2.x, v2.y, v3.x, v3.y, v4.x};
+        const double wgt = sqrt(v4.y);
+        const double* ca = src_covs + size_t(i) * 6;
+        const double A[3][3] = {{ca[0], ca[1], ca[2]}, {ca[1], ca[3], ca[4]}, {ca[2], ca[4], ca[5]}};
+        // RCR = C_B + R C_A R^T (upper 3x3 of the reference's 4x4; the (3,3)=1 row/col decouples)
+        double RC[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) RC[r][c] = (sp.T0[r] * A[0][c] + sp.T0[4 + r] * A[1][c]) + sp.T0[8 + r] * A[2][c];
+        double S[3][3];
+        S[0][0] = cB[0] + ((RC[0][0] * sp.T0[0] + RC[0][1] * sp.T0[4]) + RC[0][2] * sp.T0[8]);
+        S[0][1] = cB[1] + ((RC[0][0] * sp.T0[1] + RC[0][1] * sp.T0[5]) + RC[0][2] * sp.T0[9]);
+        S[0][2] = cB[2] + ((RC[0][0] * sp.T0[2] + RC[0][1] * sp.T0[6]) + RC[0][2] * sp.T0[10]);
+        S[1][1] = cB[3] + ((RC[1][0] * sp.T0[1] + RC[1][1] * sp.T0[5]) + RC[1][2] * sp.T0[9]);
+        S[1][2] = cB[4] + ((RC[1][0] * sp.T0[2] + RC[1][1] * sp.T0[6]) + RC[1][2] * sp.T0[10]);
+        S[2][2] = cB[5] + ((RC[2][0] * sp.T0[2] + RC[2][1] * sp.T0[6]) + RC[2][2] * sp.T0[10]);
+        S[1][0] = S[0][1]; S[2][0] = S[0][2]; S[2][1] = S[1][2];
+        double M[3][3];
+        inv3(S, M);
+        double tA[3];
+        xform_exact(sp.Ti, px, py, pz, tA);
+        const double e[3] = {mB[0] - tA[0], mB[1] - tA[1], mB[2] - tA[2]};
+        double Me[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) Me[r] = (M[r][0] * e[0] + M[r][1] * e[1]) + M[r][2] * e[2];
+        acc[0] = wgt * ((e[0] * Me[0] + e[1] * Me[1]) + e[2] * Me[2]);
+        acc[28] = 1.0;
+        if (sp.want_hb) {
+          // J = [ skew(T p) | -I ] : columns
+          const double J[6][3] = {{0.0, tA[2], -tA[1]}, {-tA[2], 0.0, tA[0]}, {tA[1], -tA[0], 0.0}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}};
+          double MJ[6][3];
+#pragma unroll
+          for (int c = 0; c < 6; c++)
+#pragma unroll
+            for (int r = 0; r < 3; r++) MJ[c][r] = (M[r][0] * J[c][0] + M[r][1] * J[c][1]) + M[r][2] * J[c][2];
+          int k = 1;
+#pragma unroll
+          for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = r; c < 6; c++) acc[k++] = wgt * ((J[r][0] * MJ[c][0] + J[r][1] * MJ[c][1]) + J[r][2] * MJ[c][2]);
+#pragma unroll
+          for (int r = 0; r < 6; r++) acc[22 + r] = wgt * ((J[r][0] * Me[0] + J[r][1] * Me[1]) + J[r][2] * Me[2]);
+        }
+      }
+    }
+  }
+  double r = block_reduce_vec<kVgNV, kVgBlock>(acc, sred);
+  double* my = partials + (size_t(req) * max_blocks + blockIdx.x) * kVgNV;
+  if (threadIdx.x < kVgNV) my[threadIdx.x] = r;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(tickets + req, 1u);
+    s_last = (t == unsigned(nb - 1));
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < kVgNV) {
+    const double* base = partials + size_t(req) * max_blocks * kVgNV + threadIdx.x;
+    double tsum = 0.0;
+    for (int b = 0; b < nb; b++) tsum += __ldcg(base + size_t(b) * kVgNV);
+    results[req].v[threadIdx.x] = tsum;
+  }
+  if (threadIdx.x == 0) tickets[req] = 0;
+}
+
+VgicpDriver::~VgicpDriver() {
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+}
+
+void VgicpDriver::evaluate(const float4* src, const double* covs, const uint32_t* d_offs, size_t max_pts, const VgicpTarget& tgt, int count,
+                           bool profile, cudaStream_t s) {
+  if (count == 0) return;
+  int max_blocks = int((max_pts + kVgBlock - 1) / kVgBlock);
+  if (max_blocks < 1) max_blocks = 1;
+  d_params.ensure(count);
+  d_results.ensure(count);
+  partials.ensure(size_t(count) * max_blocks * kVgNV);
+  if (tickets.cap < size_t(count)) {
+    tickets.ensure(count);
+    PCR_CUDA_CHECK(cudaMemsetAsync(tickets.p, 0, tickets.cap * sizeof(unsigned), s));
+  }
+  PCR_CUDA_CHECK(cudaMemcpyAsync(d_params.p, h_params.p, size_t(count) * sizeof(VgicpEvalParams), cudaMemcpyHostToDevice, s));
+  PCR_CUDA_CHECK(cudaMemsetAsync(d_results.p, 0, size_t(count) * sizeof(VgicpEvalResult), s));
+  const bool run = tgt.nvox > 0 && max_pts > 0;
+  if (run) {
+    VgTargetView v;
+    v.vox = tgt.vox.p; v.table = tgt.table.p; v.res = tgt.resolution;
+    for (int a = 0; a < 3; a++) { v.cmin[a] = tgt.cmin[a]; v.cdim[a] = tgt.cdim[a]; }
+    if (profile) {
+      if (!ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
+      PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
+    }
+    vgicp_eval_kernel<<<dim3(max_blocks, count), kVgBlock, 0, s>>>(src, covs, d_offs, v, d_params.p, d_results.p, partials.p, tickets.p,
+                                                                   max_blocks);
+    if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev1, s));
+    launches++;
+    hot_launches++;
+  }
+  h_results.ensure(count);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(h_results.p, d_results.p, size_t(count) * sizeof(VgicpEvalResult), cudaMemcpyDeviceToHost, s));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(s));
+  PCR_CUDA_CHECK(cudaGetLastError());
+  if (profile && run) {
+    float ms = 0.f;
+    PCR_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+    hot_ms += ms;
+  }
+}
+
+int VgicpDriver::compute_source_covs(const float4* src, size_t ns, int k, KeySort& ks, BBoxWork& bw, cudaStream_t s) {
+  if (ns == 0) return 0;
+  if (k > kMaxK || k < 1) return PCR_ERR_INVALID;
+  int rc = build_cell_grid(src, ns, 0.5f, src_grid, ks, bw, s);
+  if (rc) return rc;
+  src_covs.ensure(ns * 6);
+  gicp_covariances(src, ns, src_grid, k, src_covs.p, nullptr, s);
+  launches += 3;
+  return 0;
+}
+
+// ================================================================================================================
+// V5. LsqRegistration::computeTransformation / step_lm / step_gn / is_converged (lsq_registration_impl.hpp:53-172)
+// ================================================================================================================
+namespace {
+void make_delta(const double* d, double* D) {  // delta.linear = so3_exp(d[0:3]), delta.translation = d[3:6]; column-major
+  double R[9];
+  hm::so3_exp_matrix(d, R);
+  for (int i = 0; i < 16; i++) D[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) D[c * 4 + r] = R[r * 3 + c];
+    D[12 + r] = d[3 + r];
+  }
+}
+bool lsq_converged(const double* D, double rot_eps, double trans_eps) {
+  double m = 0;
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) m = std::max(m, 1.0 / rot_eps * std::fabs(D[c * 4 + r] - (r == c ? 1.0 : 0.0)));
+    m = std::max(m, 1.0 / trans_eps * std::fabs(D[12 + r]));
+  }
+  return m < 1;
+}
+void unpack(const VgicpEvalResult& r, double* H, double* b) {
+  int k = 1;
+  for (int a = 0; a < 6; a++)
+    for (int c = a; c < 6; c++) { H[a * 6 + c] = r.v[k]; H[c * 6 + a] = r.v[k]; k++; }
+  for (int a = 0; a < 6; a++) b[a] = r.v[22 + a];
+}
+}  // namespace
+
+int VgicpDriver::align(const float4* src, size_t ns, const VgicpTarget& tgt, const pcr_params& prm, double* T, int32_t* converged,
+                       int32_t* iters, bool profile, cudaStream_t s) {
+  hot_ms = 0.f; hot_launches = 0; n_linearize = 0; n_error = 0;
+  uint32_t* ho = h_offsets.ensure(2);
+  ho[0] = 0; ho[1] = uint32_t(ns);
+  offsets.ensure(2);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(offsets.p, ho, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  h_params.ensure(1);
+  double x0[16];
+  for (int i = 0; i < 16; i++) x0[i] = double(static_cast<float>(T[i]));  // VgicpRegister.cpp:36 cast<float>, lsq :54 cast<double>
+  double lm_lambda = -1.0;
+  bool conv = false;
+  int nr_iterations = 0;
+  auto eval = [&](const double* T0, const double* Ti, bool want) -> const VgicpEvalResult& {
+    VgicpEvalParams& ep = h_params.p[0];
+    std::memcpy(ep.T0, T0, sizeof(double) * 16);
+    std::memcpy(ep.Ti, Ti, sizeof(double) * 16);
+    ep.want_hb = want ? 1 : 0;
+    ep.scan = 0;
+    ep.pad[0] = ep.pad[1] = 0;
+    evaluate(src, src_covs.p, offsets.p, ns, tgt, 1, profile, s);
+    return h_results.p[0];
+  };
+  for (int it = 0; it < prm.vgicp_max_iters && !conv; it++) {
+    nr_iterations = it;
+    double H[36], b[6], delta[16];
+    const VgicpEvalResult& r0 = eval(x0, x0, true);
+    n_linearize++;
+    const double y0 = r0.v[0];
+    last_cost = y0;
+    last_corr = int64_t(r0.v[28] + 0.5);
+    unpack(r0, H, b);
+    bool ok = false;
+    if (prm.vgicp_optimizer == PCR_LSQ_GN) {
+      double nb[6], d[6];
+      for (int a = 0; a < 6; a++) nb[a] = -b[a];
+      ldlt6_solve(H, nb, d);
+      make_delta(d, delta);
+      mat4_mul(delta, x0, x0);
+      ok = true;
+    } else {
+      if (lm_lambda < 0.0) {
+        double mx = 0;
+        for (int a = 0; a < 6; a++) mx = std::max(mx, std::fabs(H[a * 6 + a]));
+        lm_lambda = prm.vgicp_lm_init_lambda * mx;
+      }
+      double nu = 2.0;
+      for (int li = 0; li < prm.vgicp_lm_max_iters; li++) {
+        double A[36], nb[6], d[6], xi[16];
+        for (int a = 0; a < 36; a++) A[a] = H[a];
+        for (int a = 0; a < 6; a++) { A[a * 6 + a] += lm_lambda; nb[a] = -b[a]; }
+        ldlt6_solve(A, nb, d);
+        make_delta(d, delta);
+        mat4_mul(delta, x0, xi);
+        const double yi = eval(x0, xi, false).v[0];
+        n_error++;
+        double den = 0;
+        for (int a = 0; a < 6; a++) den += d[a] * (lm_lambda * d[a] - b[a]);
+        const double rho = (y0 - yi) / den;
+        if (rho < 0) {
+          if (lsq_converged(delta, prm.vgicp_rot_eps, prm.vgicp_trans_eps)) { ok = true; break; }
+          lm_lambda = nu * lm_lambda;
+          nu = 2 * nu;
+          continue;
+        }
+        std::memcpy(x0, xi, sizeof(xi));
+        lm_lambda = lm_lambda * std::max(1.0 / 3.0, 1 - std::pow(2 * rho - 1, 3));
+        ok = true;
+        break;
+      }
+    }
+    if (!ok) break;  // "lm not converged!!" (lsq_registration_impl.hpp:69-72)
+    conv = lsq_converged(delta, prm.vgicp_rot_eps, prm.vgicp_trans_eps);
+  }
+  for (int i = 0; i < 16; i++) T[i] = double(static_cast<float>(x0[i]));  // final_transformation_ = x0.cast<float>()
+  if (converged) *converged = conv ? 1 : 0;
+  if (iters) *iters = nr_iterations;
+  return 0;
+}
+
+// ================================================================================================================
+// V6. pcl::Registration::getFitnessScore: float transform, exact 1-NN (float metric), mean of d2 <= max_range (FP64)
+// ================================================================================================================
+__global__ void __launch_bounds__(128)
+fitness_kernel(const float4* __restrict__ src, size_t ns, CellGridView grid, double slack, const float* __restrict__ Tf, double max_range,
+               double* __restrict__ partials) {
+  __shared__ double sred[2 * 4];
+  double acc[2] = {0.0, 0.0};
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < ns) {
+    const float4 p = __ldg(src + i);
+    float q[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+      q[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tf[r], p.x), __fmul_rn(Tf[4 + r], p.y)), __fmul_rn(Tf[8 + r], p.z)), Tf[12 + r]);
+    float bd[1];
+    int bi[1];
+    if (knn_ring_f32(grid, q[0], q[1], q[2], 1, bd, bi, slack) == 1 && double(bd[0]) <= max_range) { acc[0] = double(bd[0]); acc[1] = 1.0; }
+  }
+  double r = block_reduce_vec<2, 128>(acc, sred);
+  if (threadIdx.x < 2) partials[size_t(blockIdx.x) * 2 + threadIdx.x] = r;
+}
+
+int VgicpDriver::fitness(const float4* src, size_t ns, const VgicpTarget& tgt, const double* T, double max_range, double* score,
+                         cudaStream_t s) {
+  *score = DBL_MAX;
+  if (ns == 0 || tgt.n == 0 || !tgt.grid.built) return 0;
+  const unsigned blocks = unsigned((ns + 127) / 128);
+  fit_partials.ensure(size_t(blocks) * 2 + 16);
+  float* dTf = reinterpret_cast<float*>(fit_partials.p + size_t(blocks) * 2);
+  float hT[16];
+  for (int i = 0; i < 16; i++) hT[i] = static_cast<float>(T[i]);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(dTf, hT, sizeof(hT), cudaMemcpyHostToDevice, s));
+  fitness_kernel<<<blocks, 128, 0, s>>>(src, ns, view_of(tgt.grid), grid_slack_cells(tgt.grid.g), dTf, max_range, fit_partials.p);
+  launches++;
+  double* h = h_fit.ensure(size_t(blocks) * 2);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(h, fit_partials.p, size_t(blocks) * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(s));
+  PCR_CUDA_CHECK(cudaGetLastError());
+  double sum = 0, cnt = 0;
+  for (unsigned b = 0; b < blocks; b++) { sum += h[b * 2]; cnt += h[b * 2 + 1]; }
+  if (cnt > 0) *score = sum / cnt;
+  return 0;
+}
+
+}  // namespace pcr

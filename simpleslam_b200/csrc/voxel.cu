@@ -1,0 +1,262 @@
+// Voxel keys / stable sort / segments / downsample / uniform cell grid.
+// Reference behaviour restated: pcl::VoxelGrid as reached from common/pcp/pcp.hpp:15-28 (key math written out in-tree
+// at pcp.hpp:191-210), and the integer grid of pclomp::VoxelGridCovariance (voxel_grid_covariance_omp_impl.hpp:67-103).
+#include "voxel.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cmath>
+#include <limits>
+
+namespace pcr {
+
+// ------------------------------------------------------------------------------------------------------------
+// AoS records -> float4
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_kernel(const unsigned char* __restrict__ raw, size_t n, size_t stride, int mode,
+                                                   float4* __restrict__ out) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float4 o;
+  if (mode == 32) {  // pcl::PointXYZI, 16-byte aligned
+    const float4* r = reinterpret_cast<const float4*>(raw) + i * 2;
+    float4 a = __ldg(r), b = __ldg(r + 1);
+    o = make_float4(a.x, a.y, a.z, b.x);
+  } else if (mode == 16) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(raw) + i);
+    o = make_float4(a.x, a.y, a.z, 0.f);
+  } else {
+    const float* r = reinterpret_cast<const float*>(raw + i * stride);
+    o = make_float4(r[0], r[1], r[2], stride >= 20 ? r[4] : 0.f);
+  }
+  out[i] = o;
+}
+
+void pack_points(const void* dev_raw, size_t n, size_t stride, float4* out, cudaStream_t s) {
+  if (n == 0) return;
+  int mode = 0;
+  if ((reinterpret_cast<uintptr_t>(dev_raw) & 15) == 0) {
+    if (stride == 32) mode = 32;
+    else if (stride == 16) mode = 16;
+  }
+  unsigned blocks = unsigned((n + 255) / 256);
+  pack_kernel<<<blocks, 256, 0, s>>>(static_cast<const unsigned char*>(dev_raw), n, stride, mode, out);
+}
+
+__global__ void __launch_bounds__(256) write_xyzi32_kernel(const float4* __restrict__ pts, size_t n, float4* __restrict__ out) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  out[2 * i] = make_float4(p.x, p.y, p.z, 1.0f);
+  out[2 * i + 1] = make_float4(p.w, 0.f, 0.f, 0.f);
+}
+void write_xyzi32(const float4* pts, size_t n, void* dev_out32, cudaStream_t s) {
+  if (n == 0) return;
+  write_xyzi32_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(pts, n, static_cast<float4*>(dev_out32));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// bounding box
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ pts, size_t n, unsigned* __restrict__ out) {
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    float4 p = __ldg(pts + i);
+    mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+    mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+    mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_down_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_down_sync(0xffffffffu, mx[a], o));
+    }
+  }
+  __shared__ float smn[8][3], smx[8][3];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int a = 0; a < 3; a++) { smn[warp][a] = mn[a]; smx[warp][a] = mx[a]; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    int a = threadIdx.x;
+    float lo = smn[0][a], hi = smx[0][a];
+    for (int w = 1; w < 8; w++) { lo = fminf(lo, smn[w][a]); hi = fmaxf(hi, smx[w][a]); }
+    atomicMin(out + a, enc_f32(lo));
+    atomicMax(out + 3 + a, enc_f32(hi));
+  }
+}
+
+void bbox_blocking(const float4* pts, size_t n, float mn[3], float mx[3], BBoxWork& w, cudaStream_t s) {
+  unsigned* d = w.d.ensure(6);
+  unsigned* h = w.h.ensure(6);
+  h[0] = h[1] = h[2] = 0xffffffffu;
+  h[3] = h[4] = h[5] = 0u;
+  PCR_CUDA_CHECK(cudaMemcpyAsync(d, h, 6 * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+  unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, size_t(kNumSMs) * 8));
+  bbox_kernel<<<blocks, 256, 0, s>>>(pts, n, d);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(h, d, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int a = 0; a < 3; a++) { mn[a] = dec_f32(h[a]); mx[a] = dec_f32(h[3 + a]); }
+}
+
+bool make_grid_spec(const float mn[3], const float mx[3], float leaf, GridSpec& g) {
+  const float inv = 1.0f / leaf;
+  long long d[3];
+  for (int a = 0; a < 3; a++) {
+    g.leaf[a] = leaf;
+    g.inv_leaf[a] = inv;
+    volatile float span = (mx[a] - mn[a]);
+    volatile float scaled = span * inv;
+    d[a] = static_cast<long long>(scaled) + 1;
+    volatile float lo = mn[a] * inv, hi = mx[a] * inv;
+    g.min_b[a] = static_cast<int>(std::floor(lo));
+    g.max_b[a] = static_cast<int>(std::floor(hi));
+    g.div_b[a] = g.max_b[a] - g.min_b[a] + 1;
+  }
+  g.mul[0] = 1;
+  g.mul[1] = g.div_b[0];
+  g.mul[2] = g.div_b[0] * g.div_b[1];
+  g.ncell = (long long)g.div_b[0] * g.div_b[1] * g.div_b[2];
+  return !((d[0] * d[1] * d[2]) > (long long)std::numeric_limits<int32_t>::max());
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// keys + sort + segments
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) voxel_key_kernel(const float4* __restrict__ pts, size_t n, GridSpec g,
+                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float4 p = __ldg(pts + i);
+  int i0 = voxel_axis(p.x, g.inv_leaf[0], g.min_b[0]);
+  int i1 = voxel_axis(p.y, g.inv_leaf[1], g.min_b[1]);
+  int i2 = voxel_axis(p.z, g.inv_leaf[2], g.min_b[2]);
+  keys[i] = static_cast<uint32_t>(i0 * g.mul[0] + i1 * g.mul[1] + i2 * g.mul[2]);
+  vals[i] = static_cast<uint32_t>(i);
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t* v, size_t n) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < n) v[i] = uint32_t(i);
+}
+
+static int bits_for(long long ncell) {
+  int b = 1;
+  while (b < 32 && (1ll << b) < ncell) b++;
+  return b;
+}
+
+void KeySort::sort_keys_in_k0(size_t n_, long long ncell, cudaStream_t s) {
+  n = n_;
+  k1.ensure(n); v0.ensure(n); v1.ensure(n);
+  iota_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(v0.p, n);
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0.p, k1.p, v0.p, v1.p, int(n), 0, bits_for(ncell), s);
+  tmp.ensure(bytes);
+  PCR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, k0.p, k1.p, v0.p, v1.p, int(n), 0, bits_for(ncell), s));
+  keys_unsorted = k0.p;
+  keys = k1.p;
+  vals = v1.p;
+  nseg = 0;
+}
+
+void KeySort::sort(const float4* pts, size_t n_, const GridSpec& g, cudaStream_t s) {
+  n = n_;
+  k0.ensure(n); k1.ensure(n); v0.ensure(n); v1.ensure(n);
+  voxel_key_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(pts, n, g, k0.p, v0.p);
+  size_t bytes = 0;
+  int bits = bits_for(g.ncell);
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, k0.p, k1.p, v0.p, v1.p, int(n), 0, bits, s);
+  tmp.ensure(bytes);
+  PCR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, k0.p, k1.p, v0.p, v1.p, int(n), 0, bits, s));
+  keys_unsorted = k0.p;
+  keys = k1.p;
+  vals = v1.p;
+  nseg = 0;
+}
+
+struct HeadPred {
+  const uint32_t* keys;
+  __device__ __forceinline__ bool operator()(const uint32_t& i) const { return i == 0 || keys[i] != keys[i - 1]; }
+};
+
+__global__ void set_tail_kernel(uint32_t* seg_start, const unsigned* count, uint32_t n) { seg_start[*count] = n; }
+
+void KeySort::segment(cudaStream_t s) {
+  seg_start.ensure(n + 1);
+  unsigned* dc = d_count.ensure(1);
+  unsigned* hc = h_count.ensure(1);
+  cub::CountingInputIterator<uint32_t> it(0);
+  HeadPred pred{keys};
+  size_t bytes = 0;
+  cub::DeviceSelect::If(nullptr, bytes, it, seg_start.p, dc, int(n), pred, s);
+  tmp.ensure(bytes);
+  PCR_CUDA_CHECK(cub::DeviceSelect::If(tmp.p, bytes, it, seg_start.p, dc, int(n), pred, s));
+  set_tail_kernel<<<1, 1, 0, s>>>(seg_start.p, dc, uint32_t(n));
+  PCR_CUDA_CHECK(cudaMemcpyAsync(hc, dc, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(s));
+  nseg = *hc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pcl::VoxelGrid centroid: one thread per voxel, float32 running sums in ascending original index
+// (pcl::CentroidPoint<PointXYZI>: xyz and intensity accumulators are float).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) centroid_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ vals,
+                                                       const uint32_t* __restrict__ seg_start, size_t nseg,
+                                                       float4* __restrict__ out) {
+  size_t v = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (v >= nseg) return;
+  uint32_t b = seg_start[v], e = seg_start[v + 1];
+  float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+  for (uint32_t j = b; j < e; j++) {
+    float4 p = __ldg(pts + vals[j]);
+    sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+  }
+  float cnt = static_cast<float>(e - b);
+  out[2 * v] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 1.0f);
+  out[2 * v + 1] = make_float4(__fdiv_rn(si, cnt), 0.f, 0.f, 0.f);
+}
+
+void voxel_centroids(const float4* pts, const KeySort& ks, void* dev_out32, cudaStream_t s) {
+  if (ks.nseg == 0) return;
+  centroid_kernel<<<unsigned((ks.nseg + 127) / 128), 128, 0, s>>>(pts, ks.vals, ks.seg_start.p, ks.nseg,
+                                                                 static_cast<float4*>(dev_out32));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// uniform cell grid: cell-sorted points (w = original index) + dense per-cell [start,end)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) grid_scatter_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ keys,
+                                                           const uint32_t* __restrict__ vals, size_t n,
+                                                           float4* __restrict__ sorted, int2* __restrict__ range) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k = keys[i], v = vals[i];
+  float4 p = __ldg(pts + v);
+  p.w = __int_as_float(int(v));
+  sorted[i] = p;
+  if (i == 0 || keys[i - 1] != k) range[k].x = int(i);
+  if (i == n - 1 || keys[i + 1] != k) range[k].y = int(i + 1);
+}
+
+int build_cell_grid(const float4* pts, size_t n, float cell, CellGrid& grid, KeySort& ks, BBoxWork& bw, cudaStream_t s) {
+  grid.built = false;
+  grid.n = n;
+  if (n == 0) return 0;
+  float mn[3], mx[3];
+  bbox_blocking(pts, n, mn, mx, bw, s);
+  bool ok = make_grid_spec(mn, mx, cell, grid.g);
+  if (!ok || grid.g.ncell > (1ll << 28)) return -5;
+  ks.sort(pts, n, grid.g, s);
+  grid.pts.ensure(n);
+  grid.range.ensure(size_t(grid.g.ncell));
+  PCR_CUDA_CHECK(cudaMemsetAsync(grid.range.p, 0, size_t(grid.g.ncell) * sizeof(int2), s));
+  grid_scatter_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(pts, ks.keys, ks.vals, n, grid.pts.p, grid.range.p);
+  grid.built = true;
+  return 0;
+}
+
+}  // namespace pcr

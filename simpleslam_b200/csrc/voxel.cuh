@@ -1,0 +1,66 @@
+// Voxel keys, stable key sort, segments, PCL-VoxelGrid downsample and the uniform cell grid used by the kNN kernels.
+#pragma once
+#include "common.cuh"
+
+namespace pcr {
+
+// float4 point: (x, y, z, intensity). In cell-sorted arrays w carries the ORIGINAL index (int bits).
+void pack_points(const void* dev_raw, size_t n, size_t stride, float4* out, cudaStream_t s);
+void write_xyzi32(const float4* pts, size_t n, void* dev_out32, cudaStream_t s);
+
+// Bounding box (blocking: returns host values). n must be > 0.
+struct BBoxWork { DevBuf<unsigned> d; PinBuf<unsigned> h; };
+void bbox_blocking(const float4* pts, size_t n, float mn[3], float mx[3], BBoxWork& w, cudaStream_t s);
+
+// PCL VoxelGrid grid parameters from a bounding box (pcp.hpp:191-200; voxel_grid_covariance_omp_impl.hpp:75-103).
+// Returns false when dx*dy*dz overflows int32 (PCL's "leaf size too small").
+bool make_grid_spec(const float mn[3], const float mx[3], float leaf, GridSpec& g);
+
+// (key, original index) pairs sorted by key, stable => ascending original index inside a voxel.
+struct KeySort {
+  DevBuf<uint32_t> k0, k1, v0, v1, seg_start;
+  DevBuf<unsigned char> tmp;
+  DevBuf<unsigned> d_count;
+  PinBuf<unsigned> h_count;
+  uint32_t* keys_unsorted = nullptr;  // per input point
+  uint32_t* keys = nullptr;           // sorted
+  uint32_t* vals = nullptr;           // original indices, sorted by key
+  size_t n = 0;
+  size_t nseg = 0;                    // valid after segment()
+  // keys -> sort
+  void sort(const float4* pts, size_t n, const GridSpec& g, cudaStream_t s);
+  // generic: sort precomputed keys living in k0 (vals are generated)
+  void sort_keys_in_k0(size_t n, long long ncell, cudaStream_t s);
+  // run starts of equal keys -> seg_start[0..nseg] (seg_start[nseg] = n). Blocking (reads nseg back).
+  void segment(cudaStream_t s);
+};
+
+// pcl::VoxelGrid centroid per segment: float32 sums in ascending original index, / count.
+// out32: 32-byte PointXYZI records.
+void voxel_centroids(const float4* pts, const KeySort& ks, void* dev_out32, cudaStream_t s);
+
+// Uniform grid over a cloud for neighbour search.
+struct CellGrid {
+  GridSpec g{};
+  DevBuf<float4> pts;      // cell-sorted, w = original index bits
+  DevBuf<int2> range;      // per cell [start, end)
+  size_t n = 0;
+  bool built = false;
+};
+// Kernel-side view of a CellGrid.
+struct CellGridView {
+  const float4* pts;
+  const int2* range;
+  GridSpec g;
+};
+inline CellGridView view_of(const CellGrid& grid) {
+  CellGridView v;
+  v.pts = grid.pts.p;
+  v.range = grid.range.p;
+  v.g = grid.g;
+  return v;
+}
+// Returns PCR error code (0 ok, -5 grid too large).
+int build_cell_grid(const float4* pts, size_t n, float cell, CellGrid& grid, KeySort& ks, BBoxWork& bw, cudaStream_t s);
+
+}  // namespace pcr
