@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — scan registrations/sec of the PCR hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2_ndt|c1_loam|c3_vgicp]
+
+One "step" = one scan-to-map registration of one synthetic scan against the workload's static map.
+  value      registrations/s with inputs resident in HBM (scan already on the device, map index built):
+             sum of the K per-step device times (CUDA events on the library's stream bracketing the whole align,
+             L2 flushed between steps), max over ranks.
+  e2e        the same metric through the reference-facing call pcr_scan2map(src, dst, pose) with HOST buffers:
+             target upload + index build + scan upload + align + pose read-back inside the timed region
+             (the reference rebuilds its index on every scan2Map too).
+  roofline   dominant kernel (NDT: ndt_eval_kernel; LOAM: loam_iter_kernel; VGICP: vgicp_eval_kernel): algorithmic bytes
+             per launch (SURVEY.md §8(d) formulas) / mean launch duration measured live with CUDA events.
+  cpu_baseline  the CPU oracle (restatement of the reference's OpenMP path) timed on the host cores on a bounded sample.
+--impl reference times the oracle alone (the reference's own libPCR cannot be built here: needs PCL/Eigen/FLANN).
+N > 1 (torchrun): every rank registers its own K scans against a replica of the map index that rank 0 built and
+broadcast once over NCCL (no data-path collective) -> weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+# SURVEY.md §8(d) algorithmic bytes (SoA/float4 map, minimal traffic, no cache credit)
+def algo_bytes(method, n_src, launches, pairs):
+    if method == "ndt":      # Ns*(16 + 7*8) per evaluation + 104 B per (point, leaf) pair
+        return n_src * (16 + 56) * launches + 104.0 * pairs
+    if method == "loam":     # Ns*(16 + 27*8) per iteration + 16 B per candidate map point examined
+        return n_src * (16 + 27 * 8) * launches + 16.0 * pairs
+    if method == "vgicp":    # per evaluation Ns*(16 + 48 + 8) + 84 B per correspondence
+        return n_src * (16 + 48 + 8) * launches + 84.0 * pairs
+    raise ValueError(method)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_workload(name, downsample, n_scans, seed_offset):
+    from simpleslam_b200 import workloads
+    if name == "c2_ndt":
+        return workloads.c2_ndt(downsample, n_scans, seed_offset=seed_offset)
+    if name == "c1_loam":
+        return workloads.c1_loam(downsample, n_scans, seed_offset=seed_offset)
+    if name == "c3_vgicp":
+        return workloads.c3_vgicp(n_scans, seed_offset=seed_offset)
+    raise SystemExit("unknown workload " + name)
+
+
+def oracle_register(method, src, dst, T, threads):
+    """one full scan2Map with the CPU oracle, reference structure: index rebuilt on every call"""
+    from oracle import pyoracle as orc
+    if method == "ndt":
+        return orc.Ndt(dst, 1.0).align(src, T, threads=threads)["T"]
+    if method == "loam":
+        return orc.loam_align(src, dst, T, threads=threads)["T"]
+    return orc.Vgicp(dst, 1.0, 20, threads=threads).align(src, T, threads=threads)["T"]
+
+
+def step_inputs(wl, k):
+    if wl["method"] == "vgicp":
+        p = wl["pairs"][k % len(wl["pairs"])]
+        return p["src"], p["dst"], p["T_guess"], p["T_true"]
+    n = len(wl["scans"])
+    return wl["scans"][k % n], wl["dst"], wl["guesses"][k % n], wl["truths"][k % n]
+
+
+def pose_err(Ta, Tb):
+    dt = float(np.linalg.norm(Ta[:3, 3] - Tb[:3, 3]))
+    f = np.linalg.norm(Ta[:3, :3] - Tb[:3, :3])
+    return dt, float(2.0 * np.arcsin(min(1.0, f / (2.0 * np.sqrt(2.0)))))
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle restatement; libPCR itself needs PCL/Eigen/FLANN) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as orc
+    orc.build()
+    cores = os.cpu_count() or 1
+    ds = lambda pts, leaf: orc.voxel_downsample(pts, leaf)["points"]  # noqa: E731
+    wl = build_workload(args.workload, ds, args.steps + args.warmup, 0)
+    method = wl["method"]
+    for k in range(args.warmup):
+        s, d, Tg, _ = step_inputs(wl, k)
+        oracle_register(method, s, d, Tg, cores)
+    times = []
+    for k in range(args.warmup, args.warmup + args.steps):
+        s, d, Tg, _ = step_inputs(wl, k)
+        t0 = time.perf_counter()
+        oracle_register(method, s, d, Tg, cores)
+        times.append(time.perf_counter() - t0)
+    total = float(np.sum(times))
+    val = args.steps / total
+    s0, d0, _, _ = step_inputs(wl, 0)
+    sample = "every step = one full scan2Map (index rebuilt per call, as the reference does) on the full workload"
+    out = {
+        "impl": "reference", "metric": "scan registrations/sec (%s)" % method.upper(), "value": val, "unit": "registrations/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "p50_align_ms": 1e3 * float(np.median(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": wl["name"], "n_source": int(len(s0)), "n_target": int(len(d0))},
+        "cpu_baseline": {"value": val, "unit": "registrations/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference libPCR needs PCL+Eigen+FLANN (absent, no network): this arm times oracle/ (CPU restatement, OpenMP, all host cores)",
+    }
+    print(json.dumps(out))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from simpleslam_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    method_id = {"c2_ndt": capi.PCR_NDT, "c1_loam": capi.PCR_LOAM, "c3_vgicp": capi.PCR_VGICP}[args.workload]
+    ctx = capi.Context(method_id, device=local_rank)
+    ds = lambda pts, leaf: ctx.voxel_downsample(pts, leaf)  # noqa: E731
+    n_items = args.steps + args.warmup
+    t_gen = time.perf_counter()
+    wl = build_workload(args.workload, ds, n_items, rank)
+    t_gen = time.perf_counter() - t_gen
+    method = wl["method"]
+
+    # ---- static map: rank 0 builds the index, broadcasts it once over NCCL; the others import it
+    setup = {}
+    if method != "vgicp":
+        t0 = time.perf_counter()
+        if rank == 0 or dist is None:
+            ctx.set_target(wl["dst"])
+        setup["index_build_ms"] = 1e3 * (time.perf_counter() - t0)
+        if dist is not None:
+            nbytes = torch.zeros(1, dtype=torch.int64, device="cuda")
+            if rank == 0:
+                nbytes[0] = ctx.target_blob_size()
+            dist.broadcast(nbytes, 0)
+            blob = torch.empty(int(nbytes.item()), dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                ctx.target_export(blob.data_ptr(), blob.numel())
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            dist.broadcast(blob, 0)
+            torch.cuda.synchronize()
+            setup["index_broadcast_ms"] = 1e3 * (time.perf_counter() - t0)
+            setup["index_bytes"] = int(blob.numel())
+            if rank != 0:
+                ctx.target_import(blob.data_ptr(), blob.numel())
+            del blob
+
+    # device-resident copies of the scans for the HBM-resident measurement
+    dev_scans = []
+    for k in range(n_items):
+        s, d, Tg, _ = step_inputs(wl, k)
+        dev_scans.append(torch.from_numpy(np.ascontiguousarray(s)).cuda())
+    dev_dst = None
+    if method == "vgicp":
+        dev_dst = [torch.from_numpy(np.ascontiguousarray(p["dst"])).cuda() for p in wl["pairs"]]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def resident_step(k):
+        s, d, Tg, Tt = step_inputs(wl, k)
+        if method == "vgicp":
+            dd = dev_dst[k % len(dev_dst)]
+            ctx.set_target_device(dd.data_ptr(), dd.shape[0], 32)  # VGICP target = the other scan: part of every registration
+        T, conv = ctx.align_device(dev_scans[k].data_ptr(), dev_scans[k].shape[0], 32, Tg)
+        return T, conv, Tt
+
+    ctx.set_profiling(True)
+    for k in range(args.warmup):
+        resident_step(k)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    wall0 = time.perf_counter()
+    ms, hot_ms, hot_launches, launches, pairs, nsrc_total, errs, target_ms = [], 0.0, 0, 0, 0, 0, [], []
+    for k in range(args.warmup, n_items):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        T, conv, Tt = resident_step(k)
+        wall_step = 1e3 * (time.perf_counter() - t0)
+        st = ctx.stats()
+        # device time of the step: CUDA events on the library stream around the whole align (+ target build for VGICP, wall)
+        ms.append(wall_step if method == "vgicp" else st["ms_total"])
+        hot_ms += st["ms_hot_kernel"]
+        hot_launches += st["hot_kernel_launches"]
+        launches += st["kernel_launches"]
+        pairs += st["n_pairs"]
+        nsrc_total += st["n_source"] * st["hot_kernel_launches"]
+        errs.append(pose_err(T, Tt))
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall_total = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    t_resident = float(np.sum(ms)) / 1e3
+
+    # ---- e2e: the reference-facing call with HOST buffers (target upload + index build + align per call)
+    ctx.set_profiling(False)
+    e2e_steps = args.steps
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    e2e_t, e2e_cached_t, h2d, d2h = [], [], 0, 0
+    host_dst = pin(wl["dst"]) if method != "vgicp" else None
+    for k in range(args.warmup, args.warmup + e2e_steps):
+        s, d, Tg, _ = step_inputs(wl, k)
+        hs = pin(s)
+        hd = host_dst if host_dst is not None else pin(d)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.scan2map(hs, hd, Tg)
+        e2e_t.append(time.perf_counter() - t0)
+        h2d = hs.nbytes + hd.nbytes
+        d2h = 16 * 8 + 4
+        if method != "vgicp":  # static-map (loc.cpp) variant: target stays registered, only the scan crosses PCIe
+            t0 = time.perf_counter()
+            ctx.align(hs, Tg)
+            e2e_cached_t.append(time.perf_counter() - t0)
+    t_e2e = float(np.sum(e2e_t))
+
+    # ---- max over ranks
+    if dist is not None:
+        tt = torch.tensor([t_resident, t_e2e, wall_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_resident, t_e2e, wall_total = [float(x) for x in tt.tolist()]
+        cnt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        launches = int(cnt.item())
+    value = world * args.steps / t_resident
+    e2e_value = world * e2e_steps / t_e2e
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ab = algo_bytes(method, nsrc_total / max(hot_launches, 1), hot_launches, pairs)
+        achieved = ab / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else None
+        roof = {"bound": "hbm", "kernel": {"ndt": "ndt_eval_kernel", "loam": "loam_iter_kernel", "vgicp": "vgicp_eval_kernel"}[method],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "launches": hot_launches, "avg_launch_us": 1e3 * hot_ms / max(hot_launches, 1), "algorithmic_bytes_per_launch": ab / max(hot_launches, 1),
+                "kernel_share_of_step": hot_ms / (1e3 * t_resident) if t_resident > 0 else None,
+                "note": "working set (scan + leaf/cell tables) is L2-resident at this size: the step is launch/latency bound (SURVEY §8d caveat)"}
+        # ---- CPU baseline: the oracle on the host cores, bounded sample
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import pyoracle as orc
+            orc.build()
+            cores = os.cpu_count() or 1
+            n_cpu = 3 if method != "vgicp" else 1
+            tc = []
+            for k in range(n_cpu):
+                s, d, Tg, _ = step_inputs(wl, args.warmup + k)
+                t0 = time.perf_counter()
+                oracle_register(method, s, d, Tg, cores)
+                tc.append(time.perf_counter() - t0)
+            cpu = {"value": n_cpu / float(np.sum(tc)), "unit": "registrations/s", "cores": cores, "kind": "port",
+                   "sample": "%d full scan2Map calls (index rebuilt per call) of the same workload with the CPU oracle, OpenMP %d threads" % (n_cpu, cores),
+                   "ms_per_registration": 1e3 * float(np.mean(tc))}
+        s0, d0, _, _ = step_inputs(wl, 0)
+        errs = np.array(errs)
+        out = {
+            "metric": "scan registrations/sec (%s)" % method.upper(), "value": value, "unit": "registrations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_resident / args.steps, "p50_align_ms": float(np.median(ms)),
+            "p95_align_ms": float(np.percentile(ms, 95)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"ndt": "f32 pair math, f64 accumulate", "loam": "f64", "vgicp": "f64"}[method], "data": "synthetic",
+            "config": {"workload": wl["name"], "n_source": int(len(s0)), "n_target": int(len(d0)), "l2": "flushed between timed steps (256 MiB memset)",
+                       "timing": "sum over steps of CUDA-event time on the library stream around the whole align; max over ranks",
+                       "parallelism": "replicas: %d rank(s), map index broadcast once (NCCL), no per-iteration collective" % world},
+            "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * t_e2e / e2e_steps, "what": "pcr_scan2map(src, dst, pose) with host buffers: target upload + index build + align",
+                    "static_map_ms_per_step": (1e3 * float(np.mean(e2e_cached_t))) if e2e_cached_t else None},
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "setup": dict(setup, data_generation_s=t_gen), "wall_s_timed_region": wall_total,
+            "pose_error_vs_truth": {"median_m": float(np.median(errs[:, 0])), "median_rad": float(np.median(errs[:, 1]))},
+        }
+        print(json.dumps(out))
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_ndt", choices=["c2_ndt", "c1_loam", "c3_vgicp"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

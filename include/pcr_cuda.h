@@ -83,6 +83,8 @@ typedef struct pcr_stats {
   int64_t n_target;
   int64_t n_residuals;       /* LOAM: accepted residuals of the last linearisation; VGICP: correspondences */
   int64_t kernel_launches;   /* hand-written kernels launched by the last align/scan2map call */
+  int64_t n_pairs;           /* LOAM: map points examined by the 27-cell gather (sum over iterations and scans); NDT: (point, leaf)
+                                pairs evaluated (sum over evaluations); VGICP: correspondences (sum over evaluations) */
   double score;              /* NDT trans_probability; VGICP last cost */
   float ms_total;            /* device time of the last align call (CUDA events on the context's stream) */
   float ms_hot_kernel;       /* summed device time of the dominant correspondence/accumulation kernel */

@@ -274,13 +274,15 @@ class Vgicp:
     def error(self, src, src_covs, T0, Ti, threads=8):
         s, ns, ss = _pts(src)
         sc = np.ascontiguousarray(src_covs, dtype=np.float64)
-        return lib().orc_vgicp_error(self.h, _p(s), ctypes.c_size_t(ns), ctypes.c_size_t(ss), _p(sc), _p(_T(T0)), _p(_T(Ti)), threads)
+        t0, ti = _T(T0), _T(Ti)  # keep the buffers alive across the call
+        return lib().orc_vgicp_error(self.h, _p(s), ctypes.c_size_t(ns), ctypes.c_size_t(ss), _p(sc), _p(t0), _p(ti), threads)
 
     def align(self, src, T, src_covs=None, threads=8, optimizer="LM", max_iterations=64, rot_eps=2e-3, trans_eps=5e-4):
         s, ns, ss = _pts(src)
         sc = np.ascontiguousarray(src_covs, dtype=np.float64) if src_covs is not None else None
         res = VgicpResult()
-        lib().orc_vgicp_align(self.h, _p(s), ctypes.c_size_t(ns), ctypes.c_size_t(ss), _p(sc), _p(_T(T)), threads, 0 if optimizer == "LM" else 1,
+        tg = _T(T)
+        lib().orc_vgicp_align(self.h, _p(s), ctypes.c_size_t(ns), ctypes.c_size_t(ss), _p(sc), _p(tg), threads, 0 if optimizer == "LM" else 1,
                               max_iterations, ctypes.c_double(rot_eps), ctypes.c_double(trans_eps), ctypes.byref(res))
         return dict(T=_Tback(res.T), converged=bool(res.converged), nr_iterations=res.nr_iterations, n_linearize=res.n_linearize,
                     n_error_evals=res.n_error_evals)
@@ -290,5 +292,6 @@ def fitness(src, dst, T, max_range=float("inf"), threads=8):
     s, ns, ss = _pts(src)
     d, nm, ds = _pts(dst)
     mr = 1.7976931348623157e308 if max_range == float("inf") else max_range
-    return lib().orc_fitness(_p(s), ctypes.c_size_t(ns), ctypes.c_size_t(ss), _p(d), ctypes.c_size_t(nm), ctypes.c_size_t(ds), _p(_T(T)),
+    tt = _T(T)
+    return lib().orc_fitness(_p(s), ctypes.c_size_t(ns), ctypes.c_size_t(ss), _p(d), ctypes.c_size_t(nm), ctypes.c_size_t(ds), _p(tt),
                              ctypes.c_double(mr), threads)

@@ -255,7 +255,8 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       st.evaluations = 0;
       for (size_t i = 0; i < n_scans; i++) st.evaluations += iters[i];
       st.n_residuals = nl[0];
-      st.kernel_launches = c->loam.launches;
+      st.kernel_launches = c->loam.launches + 1;  // + pack kernel
+      st.n_pairs = c->loam.cand_total;
       st.ms_hot_kernel = c->loam.hot_ms;
       st.hot_kernel_launches = c->loam.hot_launches;
       break;
@@ -267,7 +268,8 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       st.evaluations = c->ndtd.total_evals;
       st.hessian_evals = c->ndtd.total_hess;
       st.score = tp[0];
-      st.kernel_launches = c->ndtd.launches;
+      st.kernel_launches = c->ndtd.launches + 1;
+      st.n_pairs = c->ndtd.total_pairs;
       st.ms_hot_kernel = c->ndtd.hot_ms;
       st.hot_kernel_launches = c->ndtd.hot_launches;
       break;
@@ -276,6 +278,7 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       c->vgd.launches = 0;
       float hot = 0.f;
       int hotl = 0, evals = 0;
+      long long corr = 0;
       for (size_t i = 0; i < n_scans && rc == 0; i++) {  // independent scans, processed one after the other
         const size_t ns = offs[i + 1] - offs[i];
         const float4* sp = src + (offs[i] - offs[0]);
@@ -285,12 +288,14 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
         hot += c->vgd.hot_ms;
         hotl += c->vgd.hot_launches;
         evals += c->vgd.n_linearize + c->vgd.n_error;
+        corr += c->vgd.total_corr;
       }
       st.iterations = iters[0];
       st.evaluations = evals;
       st.n_residuals = c->vgd.last_corr;
       st.score = c->vgd.last_cost;
-      st.kernel_launches = c->vgd.launches;
+      st.kernel_launches = c->vgd.launches + 1;
+      st.n_pairs = corr;
       st.ms_hot_kernel = hot;
       st.hot_kernel_launches = hotl;
       // remember the last scan for getFitnessScore (pcl keeps input_ + final_transformation_)

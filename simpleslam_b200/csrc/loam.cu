@@ -11,7 +11,7 @@
 namespace pcr {
 
 constexpr int kLoamBlock = 128;
-constexpr int kNV = 28;  // 21 upper JtJ + 6 JtE + count
+constexpr int kNV = 29;  // 21 upper JtJ + 6 JtE + count + candidates examined
 
 using GridView = CellGridView;
 
@@ -61,6 +61,7 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
 #pragma unroll
     for (int k = 0; k < 5; k++) { bd[k] = DBL_MAX; bi[k] = 0x7fffffff; bx[k] = by[k] = bz[k] = 0.f; }
     int status = 0;
+    int ncand = 0;
     // cell of the query (same key math as the build); clamp in float first so the int conversion cannot overflow
     const GridSpec& g = grid.g;
     float fc[3];
@@ -85,6 +86,7 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
           const long long rowbase = (long long)y * g.mul[1] + (long long)z * g.mul[2];
           for (int x = x0; x <= x1; x++) {
             const int2 rg = __ldg(grid.range + rowbase + x);
+            ncand += rg.y - rg.x;
             for (int j = rg.x; j < rg.y; j++) {
               const float4 m = __ldg(grid.pts + j);
               const double dx = q0 - double(m.x), dyy = q1 - double(m.y), dzz = q2 - double(m.z);
@@ -154,6 +156,7 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
         }
       }
     }
+    acc[28] = double(ncand);
     if (DEBUG && dbg_status) dbg_status[i] = status;
   }
 
@@ -195,6 +198,7 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     }
     st->iters = it + 1;
     st->n_last = int(n);
+    st->cand_total += (long long)(stot[28] + 0.5);
     if (n < 6) {  // LoamRegister.cpp:173-176
       st->done = 1;
     } else {
@@ -238,7 +242,7 @@ static GridView make_view(const CellGrid& grid) { return view_of(grid); }
 
 int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, const CellGrid& grid, const LoamParams& prm,
                       double* T, int32_t* converged, int32_t* iters_out, int64_t* n_last_out, bool profile, cudaStream_t s) {
-  launches = 0; hot_ms = 0.f; hot_launches = 0;
+  launches = 0; cand_total = 0; hot_ms = 0.f; hot_launches = 0;
   if (n_scans == 0) return 0;
   LoamState* hs = h_states.ensure(n_scans);
   uint32_t* ho = h_offsets.ensure(n_scans + 1);
@@ -287,6 +291,7 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     if (converged) converged[i] = hs[i].converged;
     if (iters_out) iters_out[i] = hs[i].iters;
     if (n_last_out) n_last_out[i] = hs[i].n_last;
+    cand_total += hs[i].cand_total;
   }
   last_log_count = hs[0].iters;
   return 0;

@@ -15,7 +15,8 @@ struct LoamState {  // one per scan, device resident
   double T[16];
   int done, converged, iters, n_last;
   unsigned ticket;
-  int pad[3];
+  int pad;
+  long long cand_total;  // map points examined by the 27-cell gather, summed over iterations
 };
 
 struct LoamDriver {
@@ -29,6 +30,7 @@ struct LoamDriver {
   PinBuf<pcr_loam_iter_log> h_logs;
   int last_log_count = 0;
   long long launches = 0;
+  long long cand_total = 0;
   float hot_ms = 0.f;
   int hot_launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

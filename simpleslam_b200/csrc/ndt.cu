@@ -7,7 +7,7 @@
 namespace pcr {
 
 constexpr int kNdtBlock = 128;
-constexpr int kNdtNV = 28;
+constexpr int kNdtNV = 29;  // score, g[6], H upper 21, (point, leaf) pairs
 
 // ================================================================================================================
 // N1. target voxel grid: per-leaf FP64 moments (ascending original index, like the reference's serial pass),
@@ -256,6 +256,7 @@ ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ off
 #pragma unroll
           for (int c = 0; c < 6; c++) xCJ[c] = (xt[0] * CJ[0][c] + xt[1] * CJ[1][c]) + xt[2] * CJ[2][c];
           acc[0] += double(score_inc);
+          acc[28] += 1.0;
 #pragma unroll
           for (int c = 0; c < 6; c++) acc[1 + c] += double(e * xCJ[c]);
           if (hess) {
@@ -318,6 +319,7 @@ ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ off
           double e = tgt.d2 * exp(-tgt.d2 * (xt[0] * Cx[0] + xt[1] * Cx[1] + xt[2] * Cx[2]) / 2);
           if (e > 1 || e < 0 || e != e) continue;
           e *= tgt.d1;
+          acc[28] += 1.0;
           double CJ[6][3], xCJ[6];  // C * J_i and x^T C J_i
 #pragma unroll
           for (int c = 0; c < 6; c++) {
@@ -434,6 +436,7 @@ struct ScanState {
   bool interval_converged, open_interval;
   int step_iterations;
   int n_evals = 0, n_hess = 0;
+  long long n_pairs = 0;
 };
 
 struct NdtLogic {
@@ -551,6 +554,7 @@ struct NdtLogic {
     begin_outer(st);
   }
   void on_result(ScanState& st, const NdtEvalResult& r) {
+    st.n_pairs += (long long)(r.v[28] + 0.5);
     switch (st.phase) {
       case ScanState::INIT_EVAL:
         st.n_evals++;
@@ -607,7 +611,7 @@ static void fill_params(NdtEvalParams& ep, const float* T, const double* p, int 
 
 int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, const NdtTarget& tgt, const pcr_params& prm, double* T,
                      int32_t* converged, int32_t* iters, double* trans_prob, bool profile, cudaStream_t s) {
-  launches = 0; hot_ms = 0.f; hot_launches = 0; total_evals = 0; total_hess = 0;
+  launches = 0; hot_ms = 0.f; hot_launches = 0; total_evals = 0; total_hess = 0; total_pairs = 0;
   if (n_scans == 0) return 0;
   if (prm.ndt_search == PCR_NDT_KDTREE) return PCR_ERR_UNSUPPORTED;
   uint32_t* ho = h_offsets.ensure(n_scans + 1);
@@ -642,6 +646,7 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
     if (trans_prob) trans_prob[i] = st[i].score / double(ns);
     total_evals += st[i].n_evals;
     total_hess += st[i].n_hess;
+    total_pairs += st[i].n_pairs;
   }
   return 0;
 }

@@ -41,7 +41,7 @@ struct NdtEvalParams {  // per scan, per evaluation
   int pad;
 };
 
-struct NdtEvalResult { double v[28]; };  // score, g[6], H upper-triangular 21 (row-major order r<=c)
+struct NdtEvalResult { double v[30]; };  // score, g[6], H upper-triangular 21 (row-major order r<=c), pairs, pad
 
 struct NdtDriver {
   DevBuf<NdtEvalParams> d_params;
@@ -57,6 +57,7 @@ struct NdtDriver {
   float hot_ms = 0.f;
   int hot_launches = 0;
   int total_evals = 0, total_hess = 0;
+  long long total_pairs = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   ~NdtDriver();
 

@@ -425,7 +425,7 @@ void unpack(const VgicpEvalResult& r, double* H, double* b) {
 
 int VgicpDriver::align(const float4* src, size_t ns, const VgicpTarget& tgt, const pcr_params& prm, double* T, int32_t* converged,
                        int32_t* iters, bool profile, cudaStream_t s) {
-  hot_ms = 0.f; hot_launches = 0; n_linearize = 0; n_error = 0;
+  hot_ms = 0.f; hot_launches = 0; n_linearize = 0; n_error = 0; total_corr = 0;
   uint32_t* ho = h_offsets.ensure(2);
   ho[0] = 0; ho[1] = uint32_t(ns);
   offsets.ensure(2);
@@ -444,6 +444,7 @@ int VgicpDriver::align(const float4* src, size_t ns, const VgicpTarget& tgt, con
     ep.scan = 0;
     ep.pad[0] = ep.pad[1] = 0;
     evaluate(src, src_covs.p, offsets.p, ns, tgt, 1, profile, s);
+    total_corr += (long long)(h_results.p[0].v[28] + 0.5);
     return h_results.p[0];
   };
   for (int it = 0; it < prm.vgicp_max_iters && !conv; it++) {

@@ -56,6 +56,7 @@ struct VgicpDriver {
   int hot_launches = 0;
   int n_linearize = 0, n_error = 0;
   int64_t last_corr = 0;
+  long long total_corr = 0;
   double last_cost = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   ~VgicpDriver();

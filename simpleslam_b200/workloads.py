@@ -1,0 +1,85 @@
+"""Synthetic benchmark workloads of BASELINE.json, shared by bench.py and the tests.
+Bench/test utility: it only produces host arrays (scans, maps, poses); `downsample` is injected by the caller
+(the CUDA path in our arm, the CPU oracle in the reference arm — both are bit-identical, tests/test_gpu_voxel.py)."""
+import numpy as np
+from . import synth
+
+SEED = 1234
+
+
+def _loop_pose(sc, i, n, cx, cy, radius, z=2.0):
+    a = 2 * np.pi * i / n
+    return sc.free_pose_near(cx + radius * np.cos(a), cy + radius * np.sin(a), z, a + np.pi / 2)
+
+
+def _perturb(rng, max_t, max_deg):
+    t = rng.uniform(-max_t, max_t, 3) * [1.0, 1.0, 0.15]
+    r = np.deg2rad(rng.uniform(-max_deg, max_deg, 3)) * [0.2, 0.2, 1.0]
+    return synth.se3_exp(np.concatenate([t, r]))
+
+
+def c2_ndt(downsample, n_scans, n_map_scans=192, seed_offset=0):
+    """C2: 64-beam scan (~130k pts, no source downsample) vs ~2M-point static map (0.2 m downsample of 192 scans on two
+    concentric loops), NDT resolution 1.0 / DIRECT7; initial guess = truth o exp(<=0.5 m, <=3 deg)."""
+    sc = synth.Scene(seed=SEED, tiles=(2, 2))
+    clouds = []
+    for i in range(n_map_scans):
+        T = _loop_pose(sc, i, n_map_scans, 200.0, 200.0, 100.0 if i % 3 else 45.0)  # two concentric loops
+        clouds.append(synth.transform_cloud(T, sc.scan(T, "hdl64", seed=300 + i)))
+    raw = np.concatenate(clouds)
+    del clouds
+    dst = downsample(raw, 0.2)
+    rng = np.random.RandomState(17 + seed_offset)
+    scans, truths, guesses = [], [], []
+    for k in range(n_scans):
+        i = (7 + 11 * (k + seed_offset * 1009)) % n_map_scans
+        T = _loop_pose(sc, i + 0.37, n_map_scans, 200.0, 200.0, 100.0 + rng.uniform(-1.5, 1.5))
+        scans.append(sc.scan(T, "hdl64", seed=5000 + k + 100000 * seed_offset))
+        truths.append(T)
+        guesses.append(T @ _perturb(rng, 0.5, 3.0))
+    return dict(name="C2 NDT scan-to-map: 64-beam scan (~130k pts) vs ~2M-pt map, res 1.0, DIRECT7", method="ndt", dst=dst, scans=scans,
+                truths=truths, guesses=guesses, raw_map_points=len(raw))
+
+
+def c1_loam(downsample, n_scans, seed_offset=0):
+    """C1: VLP-16 scan (28.8k rays, 0.5 m downsample) vs ~200k-point local submap (0.5 m downsample of 80 scans along a
+    70 m arc), LOAM; guess = truth o exp([0.3,-0.2,0.05 m; 0.5,-0.5,2 deg]-scale perturbations)."""
+    sc = synth.Scene(seed=SEED, tiles=(1, 1))
+    clouds, poses = [], []
+    for i in range(80):
+        T = sc.free_pose_near(60 + i * 0.9, 100 + 6 * np.sin(i * 0.08), 2.0, 0.1 * np.sin(i * 0.05))
+        poses.append(T)
+        clouds.append(synth.transform_cloud(T, sc.scan(T, "vlp16", seed=100 + i)))
+    dst = downsample(np.concatenate(clouds), 0.5)
+    rng = np.random.RandomState(23 + seed_offset)
+    scans, truths, guesses = [], [], []
+    for k in range(n_scans):
+        T = poses[(5 + 7 * k) % len(poses)] @ synth.se3_exp([0.4, 0.1, 0, 0, 0, 0.01])
+        raw = sc.scan(T, "vlp16", seed=7000 + k + 100000 * seed_offset)
+        scans.append(downsample(raw, 0.5))
+        truths.append(T)
+        guesses.append(T @ _perturb(rng, 0.3, 2.0))
+    return dict(name="C1 LOAM scan2map: VLP-16 scan (0.5 m downsample) vs ~200k-pt submap", method="loam", dst=dst, scans=scans, truths=truths,
+                guesses=guesses)
+
+
+def c3_vgicp(n_pairs, seed_offset=0):
+    """C3: 128-beam scan pairs (~260k pts each) 1.5 m / 3 deg apart, VGICP resolution 1.0."""
+    sc = synth.Scene(seed=SEED, tiles=(1, 1))
+    rng = np.random.RandomState(31 + seed_offset)
+    pairs = []
+    for k in range(n_pairs):
+        Ta = sc.free_pose_near(80 + 9 * k, 100 + 3 * k, 2.0, 0.2 * k)
+        Tb = Ta @ synth.se3_exp([1.5, 0.2, 0.0, 0.0, 0.0, np.deg2rad(3.0)])
+        dst = sc.scan(Ta, "os128", seed=9000 + 2 * k)
+        src = sc.scan(Tb, "os128", seed=9001 + 2 * k)
+        T_true = np.linalg.inv(Ta) @ Tb
+        pairs.append(dict(src=src, dst=dst, T_true=T_true, T_guess=T_true @ _perturb(rng, 0.2, 1.0)))
+    return dict(name="C3 VGICP scan-to-scan: 128-beam scans (~260k pts each), res 1.0", method="vgicp", pairs=pairs)
+
+
+def shard(n_items, rank, world):
+    """contiguous block partition of n_items over `world` ranks (scans i -> contiguous blocks)"""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

@@ -73,9 +73,9 @@ def vgicp_case():
 def pose_err(Ta, Tb):
     """translation (m) and rotation (rad) distance between two 4x4 poses"""
     dt = float(np.linalg.norm(Ta[:3, 3] - Tb[:3, 3]))
-    R = Ta[:3, :3].T @ Tb[:3, :3]
-    c = np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)
-    return dt, float(np.arccos(c))
+    # chordal form: well conditioned near zero (arccos of the trace loses half the digits there)
+    f = np.linalg.norm(Ta[:3, :3] - Tb[:3, :3])
+    return dt, float(2.0 * np.arcsin(min(1.0, f / (2.0 * np.sqrt(2.0)))))
 
 
 def rel_err(a, b):
