@@ -694,11 +694,12 @@ extern "C" int pcr_gicp_covariances(pcr_ctx* c, const void* pts, size_t n, size_
   if (k < 1 || k > 32) return fail(c, PCR_ERR_INVALID, "k must be in [1, 32]");
   if (n == 0) return PCR_OK;
   const float4* d = upload_points(c, pts, n, stride, c->raw_src, c->src);
+  c->has_last = false;
   CellGrid& grid = c->vgd.src_grid;
   int rc = build_cell_grid(d, n, 0.5f, grid, c->ks, c->bw, c->stream);
   if (rc) return fail(c, rc, "grid too large");
   c->vgd.src_covs.ensure(n * 6);
-  int32_t* dk = knn_idx ? c->vgd.knn_dbg.ensure(n * size_t(k)) : nullptr;
+  int32_t* dk = c->vgd.knn_dbg.ensure(n * size_t(k));
   gicp_covariances(d, n, grid, k, c->vgd.src_covs.p, dk, c->stream);
   PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   PCR_CUDA_CHECK(cudaGetLastError());

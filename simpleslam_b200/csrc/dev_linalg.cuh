@@ -187,6 +187,83 @@ PCR_HD void ldlt6_solve(const double* A, const double* rhs, double* x) {
   for (int i = 0; i < 6; i++) x[i] = y[i];
 }
 
+#ifdef __CUDACC__
+// Warp-cooperative version of ldlt6_solve for the on-device Gauss-Newton step: the same pivoted LDL^T (Eigen::LDLT)
+// on a 6x6 matrix held in shared memory. m: 36 doubles row-major (destroyed), y: rhs in / solution out, tr: 6 ints.
+// Must be called by all 32 lanes of one warp.
+__device__ __forceinline__ void ldlt6_solve_warp(double* m, double* y, int* tr, int lane) {
+  bool zero = false;
+  for (int k = 0; k < 6; k++) {
+    int big = k;
+    double bigv = fabs(m[k * 6 + k]);
+    for (int i = k + 1; i < 6; i++) {
+      const double v = fabs(m[i * 6 + i]);
+      if (v > bigv) { bigv = v; big = i; }
+    }
+    if (lane == 0) tr[k] = big;
+    if (big != k) {  // symmetric row / column swap
+      if (lane < 6) { const double t = m[k * 6 + lane]; m[k * 6 + lane] = m[big * 6 + lane]; m[big * 6 + lane] = t; }
+      __syncwarp();
+      if (lane < 6) { const double t = m[lane * 6 + k]; m[lane * 6 + k] = m[lane * 6 + big]; m[lane * 6 + big] = t; }
+      __syncwarp();
+    }
+    double akk = m[k * 6 + k];
+    for (int j = 0; j < k; j++) akk -= m[k * 6 + j] * (m[j * 6 + j] * m[k * 6 + j]);
+    const int i = k + 1 + lane;
+    const bool act = i < 6;
+    double v = 0.0;
+    if (act) {
+      v = m[i * 6 + k];
+      for (int j = 0; j < k; j++) v -= m[i * 6 + j] * (m[j * 6 + j] * m[k * 6 + j]);
+    }
+    __syncwarp();
+    if (lane == 0) m[k * 6 + k] = akk;
+    const bool valid = fabs(akk) > 0.0;
+    if (k == 0 && !valid) { zero = true; break; }
+    if (act) {
+      if (valid) v /= akk;
+      m[i * 6 + k] = v;
+      m[k * 6 + i] = v;
+    }
+    __syncwarp();
+  }
+  if (zero) {
+    if (lane < 6) y[lane] = 0.0;
+    __syncwarp();
+    return;
+  }
+  if (lane == 0) {
+    for (int k = 0; k < 6; k++) {
+      const int t = tr[k];
+      if (t != k) { const double u = y[k]; y[k] = y[t]; y[t] = u; }
+    }
+    double Y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) Y[i] = y[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j < i; j++) Y[i] -= m[i * 6 + j] * Y[j];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const double d = m[i * 6 + i];
+      Y[i] = (fabs(d) > DBL_MIN) ? Y[i] / d : 0.0;
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; i--)
+#pragma unroll
+      for (int j = i + 1; j < 6; j++) Y[i] -= m[j * 6 + i] * Y[j];
+#pragma unroll
+    for (int i = 0; i < 6; i++) y[i] = Y[i];
+    for (int k = 5; k >= 0; k--) {
+      const int t = tr[k];
+      if (t != k) { const double u = y[k]; y[k] = y[t]; y[t] = u; }
+    }
+  }
+  __syncwarp();
+}
+#endif
+
 // ----------------------------------------------------------------------------------------------------------------
 // SE(3) exponential, ordering [rho; omega], left Jacobian V — geometry::manifolds::exp
 // (common/geometry/manifolds.hpp:33-60). E: column-major 4x4.

@@ -3,6 +3,7 @@
 #include "dev_linalg.cuh"
 #include "host_math.hpp"
 #include <cfloat>
+#include <algorithm>
 
 namespace pcr {
 
@@ -139,8 +140,11 @@ int ndt_build_target(const float4* pts, size_t n, const pcr_params& prm, NdtTarg
 }
 
 // ================================================================================================================
-// N2 + N3 + N4. One thread per source point: float transform, DIRECT{7,1,26} voxel lookup, per-(point, leaf) FP32
-// score / gradient / Hessian terms accumulated in FP64, deterministic block + last-block reduction.
+// N2 + N3 + N4. Source points are strided over the threads of a request's blocks. Per point: float transform,
+// DIRECT{7,1,26} voxel lookups (all table loads issued up front), then per valid leaf the FP32 score / gradient /
+// Hessian terms of updateDerivatives, accumulated in FP64 registers (leaf records software-prefetched one ahead).
+// Deterministic warp-shuffle + block + last-block reduction; the last block writes the 29 sums straight into
+// host-mapped pinned memory, so one kernel launch + one stream sync is the whole evaluation.
 // ================================================================================================================
 struct NdtTargetView {
   const NdtLeafRec* recs;
@@ -152,25 +156,149 @@ struct NdtTargetView {
   double d1, d2;
 };
 
-__constant__ int c_off7[7][3] = {{0, 0, 0}, {1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+template <int SEARCH>
+struct NbTraits;
+template <> struct NbTraits<PCR_NDT_DIRECT7> { static constexpr int N = 7; };
+template <> struct NbTraits<PCR_NDT_DIRECT1> { static constexpr int N = 1; };
+template <> struct NbTraits<PCR_NDT_DIRECT26> { static constexpr int N = 26; };
 
-__device__ __forceinline__ void nb_offset(int search, int ni, int& ox, int& oy, int& oz) {
-  if (search == PCR_NDT_DIRECT26) {
-    // the 26 non-centre cells, x-major
-    int k = ni >= 13 ? ni + 1 : ni;
+template <int SEARCH>
+__device__ __forceinline__ void nb_offset(int ni, int& ox, int& oy, int& oz) {
+  if (SEARCH == PCR_NDT_DIRECT26) {  // the 26 non-centre cells, x-major (pcl::getAllNeighborCellIndices)
+    const int k = ni >= 13 ? ni + 1 : ni;
     ox = k / 9 - 1; oy = (k / 3) % 3 - 1; oz = k % 3 - 1;
-  } else {
-    ox = c_off7[ni][0]; oy = c_off7[ni][1]; oz = c_off7[ni][2];
+  } else {  // centre, +x, -x, +y, -y, +z, -z (voxel_grid_covariance_omp_impl.hpp:423-430)
+    ox = (ni == 1) - (ni == 2); oy = (ni == 3) - (ni == 4); oz = (ni == 5) - (ni == 6);
   }
 }
 
-__global__ void __launch_bounds__(kNdtBlock)
-ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, NdtTargetView tgt, int search,
+// Per-thread FP64 accumulators live in shared memory (column `tid` of a [kNdtNV][kNdtBlock] array: conflict-free), which
+// frees ~58 registers per thread and lets more warps hide the table / leaf-record latency.
+struct SmemAcc {
+  double* p;
+  __device__ __forceinline__ void add(int k, double v) { p[k * kNdtBlock] += v; }
+};
+
+struct LeafRegs { float4 a, b, c, d; };
+__device__ __forceinline__ LeafRegs load_leaf(const NdtLeafRec* recs, int id) {
+  const float4* rp = reinterpret_cast<const float4*>(recs + id);
+  LeafRegs r;
+  r.a = __ldg(rp); r.b = __ldg(rp + 1); r.c = __ldg(rp + 2); r.d = __ldg(rp + 3);
+  return r;
+}
+
+// float path: computePointDerivatives (:399-440) + updateDerivatives (:485-537) for one (point, leaf) pair
+__device__ __forceinline__ void ndt_pair_f32(const LeafRegs& L, const float (&pt)[3], const float (&xj)[8], const float (&xh)[15], bool hess,
+                                             float d2f, double d1, SmemAcc acc) {
+  const double m0 = __hiloint2double(__float_as_int(L.a.y), __float_as_int(L.a.x));
+  const double m1 = __hiloint2double(__float_as_int(L.a.w), __float_as_int(L.a.z));
+  const double m2 = __hiloint2double(__float_as_int(L.b.y), __float_as_int(L.b.x));
+  const float C[3][3] = {{L.b.z, L.b.w, L.c.x}, {L.c.y, L.c.z, L.c.w}, {L.d.x, L.d.y, L.d.z}};
+  const float xt[3] = {float(double(pt[0]) - m0), float(double(pt[1]) - m1), float(double(pt[2]) - m2)};
+  float xC[3];
+#pragma unroll
+  for (int c = 0; c < 3; c++) xC[c] = (xt[0] * C[0][c] + xt[1] * C[1][c]) + xt[2] * C[2][c];
+  const float q = (xt[0] * xC[0] + xt[1] * xC[1]) + xt[2] * xC[2];
+  float e = expf(-d2f * q * 0.5f);
+  const float score_inc = float(-d1 * double(e));
+  e = d2f * e;
+  if (e > 1.f || e < 0.f || e != e) return;  // :506-507 contributes nothing, not even score
+  e = float(double(e) * d1);
+  float CJ[3][6];  // C * J, J = [I | Jang]
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    CJ[r][0] = C[r][0]; CJ[r][1] = C[r][1]; CJ[r][2] = C[r][2];
+    CJ[r][3] = C[r][1] * xj[0] + C[r][2] * xj[1];
+    CJ[r][4] = (C[r][0] * xj[2] + C[r][1] * xj[3]) + C[r][2] * xj[4];
+    CJ[r][5] = (C[r][0] * xj[5] + C[r][1] * xj[6]) + C[r][2] * xj[7];
+  }
+  float xCJ[6];
+#pragma unroll
+  for (int c = 0; c < 6; c++) xCJ[c] = (xt[0] * CJ[0][c] + xt[1] * CJ[1][c]) + xt[2] * CJ[2][c];
+  acc.add(0, double(score_inc));
+  acc.add(28, 1.0);
+#pragma unroll
+  for (int c = 0; c < 6; c++) acc.add(1 + c, double(e * xCJ[c]));
+  if (hess) {
+    float JCJ[6][6];  // J^T C J (rows 0..2 are CJ itself)
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      JCJ[0][c] = CJ[0][c]; JCJ[1][c] = CJ[1][c]; JCJ[2][c] = CJ[2][c];
+      JCJ[3][c] = xj[0] * CJ[1][c] + xj[1] * CJ[2][c];
+      JCJ[4][c] = (xj[2] * CJ[0][c] + xj[3] * CJ[1][c]) + xj[4] * CJ[2][c];
+      JCJ[5][c] = (xj[5] * CJ[0][c] + xj[6] * CJ[1][c]) + xj[7] * CJ[2][c];
+    }
+    // x^T C H_E blocks (only i, j >= 3 are nonzero): a b c / b d e / c e f
+    const float ha = xC[1] * xh[0] + xC[2] * xh[1];
+    const float hb = xC[1] * xh[2] + xC[2] * xh[3];
+    const float hc = xC[1] * xh[4] + xC[2] * xh[5];
+    const float hd = (xC[0] * xh[6] + xC[1] * xh[7]) + xC[2] * xh[8];
+    const float he = (xC[0] * xh[9] + xC[1] * xh[10]) + xC[2] * xh[11];
+    const float hf = (xC[0] * xh[12] + xC[1] * xh[13]) + xC[2] * xh[14];
+    const float xH[3][3] = {{ha, hb, hc}, {hb, hd, he}, {hc, he, hf}};
+    int k = 7;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = r; c < 6; c++) {
+        const float hx = (r >= 3) ? xH[r - 3][c - 3] : 0.f;
+        acc.add(k++, double(e * (-d2f * xCJ[r] * xCJ[c] + hx + JCJ[c][r])));
+      }
+  }
+}
+
+// double path: computeHessian / updateHessian (:541-645) for one pair
+__device__ __forceinline__ void ndt_pair_f64(const NdtTargetView& tgt, int id, const float (&pt)[3], const double (&xj)[8],
+                                             const double (&xh)[15], SmemAcc acc) {
+  const double Jc[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, xj[0], xj[1]}, {xj[2], xj[3], xj[4]}, {xj[5], xj[6], xj[7]}};
+  double C[3][3], xt[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    xt[r] = double(pt[r]) - __ldg(tgt.mean + size_t(id) * 3 + r);
+#pragma unroll
+    for (int c = 0; c < 3; c++) C[r][c] = __ldg(tgt.icov + size_t(id) * 9 + r * 3 + c);
+  }
+  double Cx[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) Cx[r] = C[r][0] * xt[0] + C[r][1] * xt[1] + C[r][2] * xt[2];
+  double e = tgt.d2 * exp(-tgt.d2 * (xt[0] * Cx[0] + xt[1] * Cx[1] + xt[2] * Cx[2]) / 2);
+  if (e > 1 || e < 0 || e != e) return;
+  e *= tgt.d1;
+  acc.add(28, 1.0);
+  double CJ[6][3], xCJ[6];  // C * J_i and x^T C J_i
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) CJ[c][r] = C[r][0] * Jc[c][0] + C[r][1] * Jc[c][1] + C[r][2] * Jc[c][2];
+    xCJ[c] = xt[0] * CJ[c][0] + xt[1] * CJ[c][1] + xt[2] * CJ[c][2];
+  }
+  auto xCh = [&](double h0, double h1, double h2) {
+    return xt[0] * (C[0][0] * h0 + C[0][1] * h1 + C[0][2] * h2) + xt[1] * (C[1][0] * h0 + C[1][1] * h1 + C[1][2] * h2) +
+           xt[2] * (C[2][0] * h0 + C[2][1] * h1 + C[2][2] * h2);
+  };
+  const double ha = xCh(0, xh[0], xh[1]), hb = xCh(0, xh[2], xh[3]), hc = xCh(0, xh[4], xh[5]);
+  const double hd = xCh(xh[6], xh[7], xh[8]), he = xCh(xh[9], xh[10], xh[11]), hf = xCh(xh[12], xh[13], xh[14]);
+  const double xH[3][3] = {{ha, hb, hc}, {hb, hd, he}, {hc, he, hf}};
+  int k = 7;
+#pragma unroll
+  for (int r = 0; r < 6; r++)
+#pragma unroll
+    for (int c = r; c < 6; c++) {
+      const double hx = (r >= 3) ? xH[r - 3][c - 3] : 0.0;
+      const double jd = Jc[c][0] * CJ[r][0] + Jc[c][1] * CJ[r][1] + Jc[c][2] * CJ[r][2];
+      acc.add(k++, e * (-tgt.d2 * xCJ[r] * xCJ[c] + hx + jd));
+    }
+}
+
+template <int SEARCH, bool DOUBLE_PATH>
+__global__ void __launch_bounds__(kNdtBlock, DOUBLE_PATH ? 2 : 5)
+ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, NdtTargetView tgt,
                 const NdtEvalParams* __restrict__ params, NdtEvalResult* __restrict__ results, double* __restrict__ partials,
-                unsigned* __restrict__ tickets, int max_blocks) {
-  const int req = blockIdx.y;
+                unsigned* __restrict__ tickets, int max_blocks, int req_base) {
+  constexpr int NNB = NbTraits<SEARCH>::N;
+  const int req = req_base + blockIdx.y;
   __shared__ NdtEvalParams sp;
-  __shared__ double sred[kNdtNV * (kNdtBlock / 32)];
+  __shared__ double sacc[kNdtNV * kNdtBlock];
   __shared__ int s_last;
   {
     const int nwords = sizeof(NdtEvalParams) / 4;
@@ -180,15 +308,16 @@ ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ off
   }
   __syncthreads();
   const uint32_t begin = offs[sp.scan], end = offs[sp.scan + 1];
-  const int nb = int((end - begin + kNdtBlock - 1) / kNdtBlock);
+  const int nb = min(int((end - begin + kNdtBlock - 1) / kNdtBlock), max_blocks);  // blocks working on this request
   if (int(blockIdx.x) >= nb) return;
 
-  double acc[kNdtNV];
+  SmemAcc acc{sacc + threadIdx.x};
 #pragma unroll
-  for (int k = 0; k < kNdtNV; k++) acc[k] = 0.0;
+  for (int k = 0; k < kNdtNV; k++) sacc[k * kNdtBlock + threadIdx.x] = 0.0;
+  const GridSpec& g = tgt.g;
+  const bool hess = sp.compute_hessian != 0;
 
-  const uint32_t i = begin + blockIdx.x * kNdtBlock + threadIdx.x;
-  if (i < end) {
+  for (uint32_t i = begin + blockIdx.x * kNdtBlock + threadIdx.x; i < end; i += uint32_t(nb) * kNdtBlock) {
     const float4 po = __ldg(src + i);
     // pcl::transformPointCloud (float): ((m00 x + m01 y) + m02 z) + m03
     float pt[3];
@@ -197,7 +326,6 @@ ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ off
       pt[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(sp.Tf[r], po.x), __fmul_rn(sp.Tf[4 + r], po.y)), __fmul_rn(sp.Tf[8 + r], po.z)),
                         sp.Tf[12 + r]);
     // voxel of the transformed point: floor(p / leaf)  (voxel_grid_covariance_omp_impl.hpp:379-381)
-    const GridSpec& g = tgt.g;
     float fi[3];
     bool ok = true;
 #pragma unroll
@@ -205,154 +333,79 @@ ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ off
       fi[a] = floorf(__fdiv_rn(pt[a], g.leaf[a]));
       if (!(fabsf(fi[a]) < 1.0e9f)) ok = false;
     }
-    if (ok) {
-      const int ijk[3] = {int(fi[0]), int(fi[1]), int(fi[2])};
-      const int nnb = (search == PCR_NDT_DIRECT7) ? 7 : (search == PCR_NDT_DIRECT1 ? 1 : 26);
-      if (sp.kind == 0) {
-        // ---------------- float path: computePointDerivatives (:399-440) + updateDerivatives (:485-537) ----------------
-        const bool hess = sp.compute_hessian != 0;
-        float xj[8], xh[15];
+    if (!ok) continue;
+    const int ijk[3] = {int(fi[0]), int(fi[1]), int(fi[2])};
+    // ---- phase 1: all neighbourhood table lookups in flight at once
+    int ids[NNB];
 #pragma unroll
-        for (int r = 0; r < 8; r++) xj[r] = (sp.j_ang[r][0] * po.x + sp.j_ang[r][1] * po.y) + sp.j_ang[r][2] * po.z;
-        if (hess) {
+    for (int ni = 0; ni < NNB; ni++) {
+      int ox, oy, oz;
+      nb_offset<SEARCH>(ni, ox, oy, oz);
+      const int cx = ijk[0] + ox, cy = ijk[1] + oy, cz = ijk[2] + oz;
+      const bool inb = cx >= g.min_b[0] && cx <= g.max_b[0] && cy >= g.min_b[1] && cy <= g.max_b[1] && cz >= g.min_b[2] && cz <= g.max_b[2];
+      const long long key = (long long)(cx - g.min_b[0]) * g.mul[0] + (long long)(cy - g.min_b[1]) * g.mul[1] +
+                            (long long)(cz - g.min_b[2]) * g.mul[2];
+      ids[ni] = inb ? __ldg(tgt.table + key) : -1;
+    }
+    unsigned mask = 0;
 #pragma unroll
-          for (int r = 0; r < 15; r++) xh[r] = (sp.h_ang[r][0] * po.x + sp.h_ang[r][1] * po.y) + sp.h_ang[r][2] * po.z;
+    for (int ni = 0; ni < NNB; ni++) mask |= (ids[ni] >= 0) ? (1u << ni) : 0u;
+    if (!mask) continue;
+    auto pick = [&](int k) {
+      int v = ids[0];
+#pragma unroll
+      for (int ni = 1; ni < NNB; ni++) v = (k == ni) ? ids[ni] : v;
+      return v;
+    };
+    if (!DOUBLE_PATH) {
+      float xj[8], xh[15];
+#pragma unroll
+      for (int r = 0; r < 8; r++) xj[r] = (sp.j_ang[r][0] * po.x + sp.j_ang[r][1] * po.y) + sp.j_ang[r][2] * po.z;
+#pragma unroll
+      for (int r = 0; r < 15; r++) xh[r] = hess ? (sp.h_ang[r][0] * po.x + sp.h_ang[r][1] * po.y) + sp.h_ang[r][2] * po.z : 0.f;
+      // ---- phase 2: neighbours in reference order, next leaf record prefetched while the current one is evaluated
+      int k = __ffs(mask) - 1;
+      mask &= mask - 1;
+      LeafRegs cur = load_leaf(tgt.recs, pick(k));
+      while (true) {
+        LeafRegs nxt = cur;
+        const bool more = mask != 0;
+        if (more) {
+          k = __ffs(mask) - 1;
+          mask &= mask - 1;
+          nxt = load_leaf(tgt.recs, pick(k));
         }
-        for (int ni = 0; ni < nnb; ni++) {
-          int ox, oy, oz;
-          nb_offset(search, ni, ox, oy, oz);
-          const int cx = ijk[0] + ox, cy = ijk[1] + oy, cz = ijk[2] + oz;
-          if (cx < g.min_b[0] || cx > g.max_b[0] || cy < g.min_b[1] || cy > g.max_b[1] || cz < g.min_b[2] || cz > g.max_b[2]) continue;
-          const long long key = (long long)(cx - g.min_b[0]) * g.mul[0] + (long long)(cy - g.min_b[1]) * g.mul[1] +
-                                (long long)(cz - g.min_b[2]) * g.mul[2];
-          const int id = __ldg(tgt.table + key);
-          if (id < 0) continue;
-          const float4* rp = reinterpret_cast<const float4*>(tgt.recs + id);
-          const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1), r2 = __ldg(rp + 2), r3 = __ldg(rp + 3);
-          const double m0 = __hiloint2double(__float_as_int(r0.y), __float_as_int(r0.x));
-          const double m1 = __hiloint2double(__float_as_int(r0.w), __float_as_int(r0.z));
-          const double m2 = __hiloint2double(__float_as_int(r1.y), __float_as_int(r1.x));
-          const float C[3][3] = {{r1.z, r1.w, r2.x}, {r2.y, r2.z, r2.w}, {r3.x, r3.y, r3.z}};
-          const float xt[3] = {float(double(pt[0]) - m0), float(double(pt[1]) - m1), float(double(pt[2]) - m2)};
-          float xC[3];
+        ndt_pair_f32(cur, pt, xj, xh, hess, tgt.d2f, tgt.d1, acc);
+        if (!more) break;
+        cur = nxt;
+      }
+    } else {
+      const double x[3] = {double(po.x), double(po.y), double(po.z)};
+      double xj[8], xh[15];
 #pragma unroll
-          for (int c = 0; c < 3; c++) xC[c] = (xt[0] * C[0][c] + xt[1] * C[1][c]) + xt[2] * C[2][c];
-          const float q = (xt[0] * xC[0] + xt[1] * xC[1]) + xt[2] * xC[2];
-          float e = expf(-tgt.d2f * q * 0.5f);
-          const float score_inc = float(-tgt.d1 * double(e));
-          e = tgt.d2f * e;
-          if (e > 1.f || e < 0.f || e != e) continue;  // :506-507 contributes nothing, not even score
-          e = float(double(e) * tgt.d1);
-          // CJ = C * J, J = [I | Jang]
-          float CJ[3][6];
+      for (int r = 0; r < 8; r++) xj[r] = x[0] * sp.j_ang_d[r][0] + x[1] * sp.j_ang_d[r][1] + x[2] * sp.j_ang_d[r][2];
 #pragma unroll
-          for (int r = 0; r < 3; r++) {
-            CJ[r][0] = C[r][0]; CJ[r][1] = C[r][1]; CJ[r][2] = C[r][2];
-            CJ[r][3] = C[r][1] * xj[0] + C[r][2] * xj[1];
-            CJ[r][4] = (C[r][0] * xj[2] + C[r][1] * xj[3]) + C[r][2] * xj[4];
-            CJ[r][5] = (C[r][0] * xj[5] + C[r][1] * xj[6]) + C[r][2] * xj[7];
-          }
-          float xCJ[6];
-#pragma unroll
-          for (int c = 0; c < 6; c++) xCJ[c] = (xt[0] * CJ[0][c] + xt[1] * CJ[1][c]) + xt[2] * CJ[2][c];
-          acc[0] += double(score_inc);
-          acc[28] += 1.0;
-#pragma unroll
-          for (int c = 0; c < 6; c++) acc[1 + c] += double(e * xCJ[c]);
-          if (hess) {
-            // J^T C J rows for the angular columns (rows 0..2 of J^T C J are CJ itself)
-            float JCJ[6][6];
-#pragma unroll
-            for (int c = 0; c < 6; c++) {
-              JCJ[0][c] = CJ[0][c]; JCJ[1][c] = CJ[1][c]; JCJ[2][c] = CJ[2][c];
-              JCJ[3][c] = xj[0] * CJ[1][c] + xj[1] * CJ[2][c];
-              JCJ[4][c] = (xj[2] * CJ[0][c] + xj[3] * CJ[1][c]) + xj[4] * CJ[2][c];
-              JCJ[5][c] = (xj[5] * CJ[0][c] + xj[6] * CJ[1][c]) + xj[7] * CJ[2][c];
-            }
-            // x^T C H_E blocks (only i, j >= 3 are nonzero): a b c / b d e / c e f
-            const float ha = xC[1] * xh[0] + xC[2] * xh[1];
-            const float hb = xC[1] * xh[2] + xC[2] * xh[3];
-            const float hc = xC[1] * xh[4] + xC[2] * xh[5];
-            const float hd = (xC[0] * xh[6] + xC[1] * xh[7]) + xC[2] * xh[8];
-            const float he = (xC[0] * xh[9] + xC[1] * xh[10]) + xC[2] * xh[11];
-            const float hf = (xC[0] * xh[12] + xC[1] * xh[13]) + xC[2] * xh[14];
-            const float xH[3][3] = {{ha, hb, hc}, {hb, hd, he}, {hc, he, hf}};
-            int k = 7;
-#pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-              for (int c = r; c < 6; c++) {
-                const float hx = (r >= 3) ? xH[r - 3][c - 3] : 0.f;
-                acc[k++] += double(e * (-tgt.d2f * xCJ[r] * xCJ[c] + hx + JCJ[c][r]));
-              }
-          }
-        }
-      } else {
-        // ---------------- double path: computeHessian / updateHessian (:541-645) ----------------
-        const double x[3] = {double(po.x), double(po.y), double(po.z)};
-        double xj[8], xh[15];
-#pragma unroll
-        for (int r = 0; r < 8; r++) xj[r] = x[0] * sp.j_ang_d[r][0] + x[1] * sp.j_ang_d[r][1] + x[2] * sp.j_ang_d[r][2];
-#pragma unroll
-        for (int r = 0; r < 15; r++) xh[r] = x[0] * sp.h_ang_d[r][0] + x[1] * sp.h_ang_d[r][1] + x[2] * sp.h_ang_d[r][2];
-        // J columns (3-vectors)
-        const double Jc[6][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, xj[0], xj[1]}, {xj[2], xj[3], xj[4]}, {xj[5], xj[6], xj[7]}};
-        for (int ni = 0; ni < nnb; ni++) {
-          int ox, oy, oz;
-          nb_offset(search, ni, ox, oy, oz);
-          const int cx = ijk[0] + ox, cy = ijk[1] + oy, cz = ijk[2] + oz;
-          if (cx < g.min_b[0] || cx > g.max_b[0] || cy < g.min_b[1] || cy > g.max_b[1] || cz < g.min_b[2] || cz > g.max_b[2]) continue;
-          const long long key = (long long)(cx - g.min_b[0]) * g.mul[0] + (long long)(cy - g.min_b[1]) * g.mul[1] +
-                                (long long)(cz - g.min_b[2]) * g.mul[2];
-          const int id = __ldg(tgt.table + key);
-          if (id < 0) continue;
-          double C[3][3], xt[3];
-#pragma unroll
-          for (int r = 0; r < 3; r++) {
-            xt[r] = double(pt[r]) - __ldg(tgt.mean + size_t(id) * 3 + r);
-#pragma unroll
-            for (int c = 0; c < 3; c++) C[r][c] = __ldg(tgt.icov + size_t(id) * 9 + r * 3 + c);
-          }
-          double Cx[3];
-#pragma unroll
-          for (int r = 0; r < 3; r++) Cx[r] = C[r][0] * xt[0] + C[r][1] * xt[1] + C[r][2] * xt[2];
-          double e = tgt.d2 * exp(-tgt.d2 * (xt[0] * Cx[0] + xt[1] * Cx[1] + xt[2] * Cx[2]) / 2);
-          if (e > 1 || e < 0 || e != e) continue;
-          e *= tgt.d1;
-          acc[28] += 1.0;
-          double CJ[6][3], xCJ[6];  // C * J_i and x^T C J_i
-#pragma unroll
-          for (int c = 0; c < 6; c++) {
-#pragma unroll
-            for (int r = 0; r < 3; r++) CJ[c][r] = C[r][0] * Jc[c][0] + C[r][1] * Jc[c][1] + C[r][2] * Jc[c][2];
-            xCJ[c] = xt[0] * CJ[c][0] + xt[1] * CJ[c][1] + xt[2] * CJ[c][2];
-          }
-          // x^T C h_ij for i,j >= 3
-          auto xCh = [&](double h0, double h1, double h2) {
-            return xt[0] * (C[0][0] * h0 + C[0][1] * h1 + C[0][2] * h2) + xt[1] * (C[1][0] * h0 + C[1][1] * h1 + C[1][2] * h2) +
-                   xt[2] * (C[2][0] * h0 + C[2][1] * h1 + C[2][2] * h2);
-          };
-          const double ha = xCh(0, xh[0], xh[1]), hb = xCh(0, xh[2], xh[3]), hc = xCh(0, xh[4], xh[5]);
-          const double hd = xCh(xh[6], xh[7], xh[8]), he = xCh(xh[9], xh[10], xh[11]), hf = xCh(xh[12], xh[13], xh[14]);
-          const double xH[3][3] = {{ha, hb, hc}, {hb, hd, he}, {hc, he, hf}};
-          int k = 7;
-#pragma unroll
-          for (int r = 0; r < 6; r++)
-#pragma unroll
-            for (int c = r; c < 6; c++) {
-              const double hx = (r >= 3) ? xH[r - 3][c - 3] : 0.0;
-              const double jd = Jc[c][0] * CJ[r][0] + Jc[c][1] * CJ[r][1] + Jc[c][2] * CJ[r][2];
-              acc[k++] += e * (-tgt.d2 * xCJ[r] * xCJ[c] + hx + jd);
-            }
-        }
+      for (int r = 0; r < 15; r++) xh[r] = x[0] * sp.h_ang_d[r][0] + x[1] * sp.h_ang_d[r][1] + x[2] * sp.h_ang_d[r][2];
+      while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        ndt_pair_f64(tgt, pick(k), pt, xj, xh, acc);
       }
     }
   }
 
-  double r = block_reduce_vec<kNdtNV, kNdtBlock>(acc, sred);
-  double* my = partials + (size_t(req) * max_blocks + blockIdx.x) * kNdtNV;
-  if (threadIdx.x < kNdtNV) my[threadIdx.x] = r;
-  __threadfence();
+  // fixed-order block reduction straight out of shared memory: warp w owns components w, w+4, ...
+  __syncthreads();
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = warp; k < kNdtNV; k += kNdtBlock / 32) {
+      const double* col = sacc + k * kNdtBlock;
+      double v = ((col[lane] + col[lane + 32]) + col[lane + 64]) + col[lane + 96];
+      v = warp_sum(v);
+      if (lane == 0) partials[(size_t(req) * max_blocks + blockIdx.x) * kNdtNV + k] = v;
+    }
+    if (lane == 0) __threadfence();  // one fence per writer warp, after all of its partial sums
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned t = atomicAdd(tickets + req, 1u);
@@ -365,7 +418,7 @@ ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ off
     const double* base = partials + size_t(req) * max_blocks * kNdtNV + threadIdx.x;
     double tsum = 0.0;
     for (int b = 0; b < nb; b++) tsum += __ldcg(base + size_t(b) * kNdtNV);
-    results[req].v[threadIdx.x] = tsum;
+    results[req].v[threadIdx.x] = tsum;  // host-mapped pinned memory
   }
   if (threadIdx.x == 0) tickets[req] = 0;
 }
@@ -373,23 +426,45 @@ ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ off
 NdtDriver::~NdtDriver() {
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  if (mapped_results) cudaFreeHost(mapped_results);
 }
 
+template <int SEARCH>
+static void launch_eval(bool double_path, dim3 grid, cudaStream_t s, const float4* src, const uint32_t* offs, const NdtTargetView& v,
+                        const NdtEvalParams* params, NdtEvalResult* results, double* partials, unsigned* tickets, int max_blocks, int base) {
+  if (double_path)
+    ndt_eval_kernel<SEARCH, true><<<grid, kNdtBlock, 0, s>>>(src, offs, v, params, results, partials, tickets, max_blocks, base);
+  else
+    ndt_eval_kernel<SEARCH, false><<<grid, kNdtBlock, 0, s>>>(src, offs, v, params, results, partials, tickets, max_blocks, base);
+}
+
+// Requests h_params[0..count) must be ordered: all float-path (kind 0) requests first, then the double-path (kind 1) ones.
 void NdtDriver::evaluate(const float4* src, const uint32_t* d_offs, size_t max_pts, const NdtTarget& tgt, int search, int count,
                          bool profile, cudaStream_t s) {
   if (count == 0) return;
-  int max_blocks = int((max_pts + kNdtBlock - 1) / kNdtBlock);
-  if (max_blocks < 1) max_blocks = 1;
+  int n0 = 0;
+  while (n0 < count && h_params.p[n0].kind == 0) n0++;
+  // enough blocks to fill the machine a few times over, never more than one block per 128 points
+  const int full_blocks = int((max_pts + kNdtBlock - 1) / kNdtBlock);
+  // 5 blocks of 128 threads are resident per SM: one resident wave, points strided over it
+  int max_blocks = std::max(1, std::min(full_blocks, (kNumSMs * 5 + count - 1) / count));
   d_params.ensure(count);
-  d_results.ensure(count);
   partials.ensure(size_t(count) * max_blocks * kNdtNV);
   if (tickets.cap < size_t(count)) {
     tickets.ensure(count);
     PCR_CUDA_CHECK(cudaMemsetAsync(tickets.p, 0, tickets.cap * sizeof(unsigned), s));
   }
+  if (mapped_cap < size_t(count)) {
+    if (mapped_results) cudaFreeHost(mapped_results);
+    mapped_cap = size_t(count) + 64;
+    PCR_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&mapped_results), mapped_cap * sizeof(NdtEvalResult), cudaHostAllocMapped));
+  }
+  memset(mapped_results, 0, size_t(count) * sizeof(NdtEvalResult));  // requests over empty scans launch no block
+  NdtEvalResult* dev_results = nullptr;
+  PCR_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_results), mapped_results, 0));
   PCR_CUDA_CHECK(cudaMemcpyAsync(d_params.p, h_params.p, size_t(count) * sizeof(NdtEvalParams), cudaMemcpyHostToDevice, s));
-  PCR_CUDA_CHECK(cudaMemsetAsync(d_results.p, 0, size_t(count) * sizeof(NdtEvalResult), s));
-  if (!tgt.overflow && tgt.nleaves > 0 && max_pts > 0) {
+  const bool run = !tgt.overflow && tgt.nleaves > 0 && max_pts > 0;
+  if (run) {
     NdtTargetView v;
     v.recs = tgt.recs.p; v.mean = tgt.mean.p; v.icov = tgt.icov.p; v.table = tgt.table.p; v.g = tgt.g;
     v.d1 = tgt.d1; v.d2 = tgt.d2; v.d2f = float(tgt.d2);
@@ -397,17 +472,25 @@ void NdtDriver::evaluate(const float4* src, const uint32_t* d_offs, size_t max_p
       if (!ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
       PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
     }
-    ndt_eval_kernel<<<dim3(max_blocks, count), kNdtBlock, 0, s>>>(src, d_offs, v, search, d_params.p, d_results.p, partials.p, tickets.p,
-                                                                  max_blocks);
+    for (int part = 0; part < 2; part++) {
+      const int base = part == 0 ? 0 : n0, n = part == 0 ? n0 : count - n0;
+      if (n == 0) continue;
+      dim3 grid(max_blocks, n);
+      switch (search) {
+        case PCR_NDT_DIRECT1: launch_eval<PCR_NDT_DIRECT1>(part == 1, grid, s, src, d_offs, v, d_params.p, dev_results, partials.p, tickets.p, max_blocks, base); break;
+        case PCR_NDT_DIRECT26: launch_eval<PCR_NDT_DIRECT26>(part == 1, grid, s, src, d_offs, v, d_params.p, dev_results, partials.p, tickets.p, max_blocks, base); break;
+        default: launch_eval<PCR_NDT_DIRECT7>(part == 1, grid, s, src, d_offs, v, d_params.p, dev_results, partials.p, tickets.p, max_blocks, base); break;
+      }
+      launches++;
+      hot_launches++;
+    }
     if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev1, s));
-    launches++;
-    hot_launches++;
   }
-  h_results.ensure(count);
-  PCR_CUDA_CHECK(cudaMemcpyAsync(h_results.p, d_results.p, size_t(count) * sizeof(NdtEvalResult), cudaMemcpyDeviceToHost, s));
   PCR_CUDA_CHECK(cudaStreamSynchronize(s));
   PCR_CUDA_CHECK(cudaGetLastError());
-  if (profile && !tgt.overflow && tgt.nleaves > 0 && max_pts > 0) {
+  h_results.ensure(count);
+  memcpy(h_results.p, mapped_results, size_t(count) * sizeof(NdtEvalResult));
+  if (profile && run) {
     float ms = 0.f;
     PCR_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
     hot_ms += ms;
@@ -631,6 +714,7 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
     for (size_t i = 0; i < n_scans; i++)
       if (st[i].phase != ScanState::FINISHED) active.push_back(int(i));
     if (active.empty()) break;
+    std::stable_partition(active.begin(), active.end(), [&](int i) { return st[i].eval_kind == 0; });
     for (size_t k = 0; k < active.size(); k++) {
       ScanState& ss = st[active[k]];
       fill_params(h_params.p[k], ss.eval_T, ss.eval_p, ss.eval_kind, ss.eval_hess, active[k]);

@@ -59,6 +59,8 @@ struct NdtDriver {
   int total_evals = 0, total_hess = 0;
   long long total_pairs = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  NdtEvalResult* mapped_results = nullptr;  // host-mapped pinned memory the last block writes into
+  size_t mapped_cap = 0;
   ~NdtDriver();
 
   // evaluate `count` requests (h_params[0..count)) -> h_results[0..count). Blocking.

@@ -12,21 +12,70 @@ constexpr int kVgNV = 29;  // cost, 21 H, 6 b, count
 constexpr int kMaxK = 32;
 
 // ================================================================================================================
-// exact k-NN on the uniform grid with Chebyshev ring expansion. Float metric of FLANN L2_Simple<float>
-// (float diff, float square, float accumulate x->y->z), ties broken by (d2, original index).
-// Terminates when the k-th distance is provably smaller than the distance to every unvisited cell.
+// Exact k-NN (k <= 32) on the uniform grid, ONE WARP PER QUERY, Chebyshev ring expansion.
+// Float metric of FLANN L2_Simple<float> (float diff, float square, float accumulate x->y->z), ties
+// broken by (d2, original index). Lane l holds the l-th best so far; candidates of a row of cells are read coalesced
+// (one float4 per lane) and those beating the current k-th are inserted with ballot / shuffle-up. The search stops as
+// soon as the k-th distance is provably smaller than the distance to every unvisited cell.
 // ================================================================================================================
 __device__ __forceinline__ float dist2_f32(float qx, float qy, float qz, const float4& m) {
   const float dx = __fsub_rn(qx, m.x), dy = __fsub_rn(qy, m.y), dz = __fsub_rn(qz, m.z);
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-__device__ int knn_ring_f32(const CellGridView& grid, float qx, float qy, float qz, int k, float* bd, int* bi, double slack_cells) {
+struct WarpKnn {
+  float bd;   // this lane's entry of the sorted result (lane < k), +inf when empty
+  int bi;
+  float td;   // current k-th best (threshold), warp-uniform
+  int ti;
+  int cnt;    // entries found so far (<= k), warp-uniform
+};
+
+constexpr unsigned kFull = 0xffffffffu;
+
+// scan the contiguous run [lo, hi) of the cell-sorted array
+__device__ __forceinline__ void knn_scan_run(WarpKnn& st, const float4* __restrict__ pts, int lo, int hi, float qx, float qy, float qz,
+                                             int k, int lane) {
+  for (int base = lo; base < hi; base += 32) {
+    const int j = base + lane;
+    float d2 = 0.f;
+    int idx = 0;
+    bool pass = false;
+    if (j < hi) {
+      const float4 m = __ldg(pts + j);
+      d2 = dist2_f32(qx, qy, qz, m);
+      idx = __float_as_int(m.w);
+      pass = d2 < st.td || (d2 == st.td && idx < st.ti);
+    }
+    unsigned mask = __ballot_sync(kFull, pass);
+    while (mask) {
+      const int s = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float cd = __shfl_sync(kFull, d2, s);
+      const int ci = __shfl_sync(kFull, idx, s);
+      if (!(cd < st.td || (cd == st.td && ci < st.ti))) continue;  // the threshold moved since the ballot
+      const bool less = st.bd < cd || (st.bd == cd && st.bi < ci);
+      const int pos = __popc(__ballot_sync(kFull, less && lane < k));
+      const float ud = __shfl_up_sync(kFull, st.bd, 1);
+      const int ui = __shfl_up_sync(kFull, st.bi, 1);
+      if (lane == pos) { st.bd = cd; st.bi = ci; }
+      else if (lane > pos && lane < k) { st.bd = ud; st.bi = ui; }
+      if (st.cnt < k) st.cnt++;
+      st.td = __shfl_sync(kFull, st.bd, k - 1);
+      st.ti = __shfl_sync(kFull, st.bi, k - 1);
+    }
+  }
+}
+
+// Warp-cooperative exact k-NN. On return lanes [0, cnt) hold the neighbours in ascending (d2, idx) order.
+__device__ __forceinline__ WarpKnn knn_warp_f32(const CellGridView& grid, float qx, float qy, float qz, int k, double slack_cells, int lane) {
   const GridSpec& g = grid.g;
-  int cnt = 0;
+  WarpKnn st;
+  st.bd = INFINITY; st.bi = 0x7fffffff; st.td = INFINITY; st.ti = 0x7fffffff; st.cnt = 0;
   const float q[3] = {qx, qy, qz};
   int c[3];
   double margin = 1e30;
+#pragma unroll
   for (int a = 0; a < 3; a++) {
     const float s = __fmul_rn(q[a], g.inv_leaf[a]);
     float fc = __fsub_rn(floorf(s), float(g.min_b[a]));
@@ -37,6 +86,7 @@ __device__ int knn_ring_f32(const CellGridView& grid, float qx, float qy, float 
   }
   margin -= slack_cells;
   int rstart = 0, rmax = 0;
+#pragma unroll
   for (int a = 0; a < 3; a++) {
     rstart = max(rstart, max(-c[a], c[a] - (g.div_b[a] - 1)));
     rmax = max(rmax, max(c[a], g.div_b[a] - 1 - c[a]));
@@ -48,33 +98,40 @@ __device__ int knn_ring_f32(const CellGridView& grid, float qx, float qy, float 
     for (int z = zlo; z <= zhi; z++) {
       const bool zedge = (z == c[2] - r) || (z == c[2] + r);
       for (int y = ylo; y <= yhi; y++) {
-        const bool edge = zedge || (y == c[1] - r) || (y == c[1] + r);
+        const bool edge = zedge || (y == c[1] - r) || (y == c[1] + r) || r == 0;
         const long long rowbase = (long long)y * g.mul[1] + (long long)z * g.mul[2];
-        const int xstep = (edge || r == 0) ? 1 : 2 * r;
-        for (int x = c[0] - r; x <= c[0] + r; x += xstep) {
-          if (x < 0 || x >= g.div_b[0]) continue;
-          const int2 rg = __ldg(grid.range + rowbase + x);
-          for (int j = rg.x; j < rg.y; j++) {
-            const float4 m = __ldg(grid.pts + j);
-            const float d2 = dist2_f32(qx, qy, qz, m);
-            const int idx = __float_as_int(m.w);
-            if (cnt == k && !(d2 < bd[k - 1] || (d2 == bd[k - 1] && idx < bi[k - 1]))) continue;
-            int p = (cnt < k) ? cnt : k - 1;
-            while (p > 0 && (bd[p - 1] > d2 || (bd[p - 1] == d2 && bi[p - 1] > idx))) {
-              bd[p] = bd[p - 1]; bi[p] = bi[p - 1]; p--;
+        if (edge) {
+          // the whole x-row [cx-r, cx+r] belongs to the shell: consecutive cells == one contiguous run
+          const int xa = max(c[0] - r, 0), xb = min(c[0] + r, g.div_b[0] - 1);
+          for (int x0 = xa; x0 <= xb; x0 += 32) {
+            const int x = x0 + lane;
+            int lo = 0x7fffffff, hi = 0;
+            if (x <= xb) {
+              const int2 rg = __ldg(grid.range + rowbase + x);
+              if (rg.y > rg.x) { lo = rg.x; hi = rg.y; }
             }
-            bd[p] = d2; bi[p] = idx;
-            if (cnt < k) cnt++;
+            lo = __reduce_min_sync(kFull, lo);
+            hi = __reduce_max_sync(kFull, hi);
+            if (hi > lo) knn_scan_run(st, grid.pts, lo, hi, qx, qy, qz, k, lane);
+          }
+        } else {
+          // interior row: only the two end cells x = cx-r and x = cx+r are on the shell
+          const int xs[2] = {c[0] - r, c[0] + r};
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            if (xs[e] < 0 || xs[e] >= g.div_b[0]) continue;
+            const int2 rg = __ldg(grid.range + rowbase + xs[e]);
+            if (rg.y > rg.x) knn_scan_run(st, grid.pts, rg.x, rg.y, qx, qy, qz, k, lane);
           }
         }
       }
     }
-    if (cnt == k) {
+    if (st.cnt == k) {
       const double reach = (double(r) + margin) * leaf;
-      if (reach > 0.0 && double(bd[k - 1]) < reach * reach * (1.0 - 1e-6)) break;
+      if (reach > 0.0 && double(st.td) < reach * reach * (1.0 - 1e-6)) break;
     }
   }
-  return cnt;
+  return st;
 }
 
 static double grid_slack_cells(const GridSpec& g) {
@@ -87,50 +144,70 @@ static double grid_slack_cells(const GridSpec& g) {
 // ================================================================================================================
 // V1. FastGICP::calculate_covariances (fast_gicp_impl.hpp:241-298): k-NN (self included), cov = N N^T / k of the
 // mean-centred neighbours (FP64), PLANE regularisation U diag(1,1,1e-3) V^T.
+// Two kernels: warp-per-query k-NN writes the neighbour indices, then one thread per point does the 3x3 algebra.
 // ================================================================================================================
+__global__ void __launch_bounds__(256)
+gicp_knn_kernel(const float4* __restrict__ pts, size_t n, CellGridView grid, int k, double slack, int32_t* __restrict__ knn_idx) {
+  const int lane = threadIdx.x & 31;
+  const size_t warps = size_t(gridDim.x) * (blockDim.x >> 5);
+  for (size_t i = size_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+    const float4 q = __ldg(pts + i);
+    const WarpKnn st = knn_warp_f32(grid, q.x, q.y, q.z, k, slack, lane);
+    if (lane < k) knn_idx[i * k + lane] = lane < st.cnt ? st.bi : -1;
+  }
+}
+
 __global__ void __launch_bounds__(128)
-gicp_cov_kernel(const float4* __restrict__ pts, size_t n, CellGridView grid, int k, double slack, double* __restrict__ covs,
-                int32_t* __restrict__ knn_idx) {
+gicp_cov_kernel(const float4* __restrict__ pts, size_t n, int k, const int32_t* __restrict__ knn_idx, double* __restrict__ covs) {
   size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   if (i >= n) return;
-  float bd[kMaxK];
-  int bi[kMaxK];
-  const float4 q = __ldg(pts + i);
-  const int found = knn_ring_f32(grid, q.x, q.y, q.z, k, bd, bi, slack);
-  if (knn_idx)
-    for (int j = 0; j < k; j++) knn_idx[i * k + j] = j < found ? bi[j] : -1;
+  const int32_t* nb = knn_idx + i * k;
   double mean[3] = {0, 0, 0};
-  for (int j = 0; j < found; j++) {
-    const float4 p = __ldg(pts + bi[j]);
+  for (int j = 0; j < k; j++) {
+    const int id = nb[j];
+    if (id < 0) break;
+    const float4 p = __ldg(pts + id);
     mean[0] += double(p.x); mean[1] += double(p.y); mean[2] += double(p.z);
   }
   const double dk = double(k);
   mean[0] /= dk; mean[1] /= dk; mean[2] /= dk;
   double cov[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-  for (int j = 0; j < found; j++) {
-    const float4 p = __ldg(pts + bi[j]);
+  for (int j = 0; j < k; j++) {
+    const int id = nb[j];
+    if (id < 0) break;
+    const float4 p = __ldg(pts + id);
     const double d[3] = {double(p.x) - mean[0], double(p.y) - mean[1], double(p.z) - mean[2]};
+#pragma unroll
     for (int r = 0; r < 3; r++)
+#pragma unroll
       for (int c = r; c < 3; c++) cov[r][c] += d[r] * d[c];
   }
+#pragma unroll
   for (int r = 0; r < 3; r++)
+#pragma unroll
     for (int c = r; c < 3; c++) { cov[r][c] /= dk; cov[c][r] = cov[r][c]; }
   double w[3], V[3][3];
   eig_sym3(cov, w, V);  // ascending; the SVD's descending singular values get (1, 1, 1e-3)
   const double vals[3] = {1e-3, 1.0, 1.0};
   double* o = covs + i * 6;
   int t = 0;
+#pragma unroll
   for (int r = 0; r < 3; r++)
+#pragma unroll
     for (int c = r; c < 3; c++) {
       double v = 0;
+#pragma unroll
       for (int e = 2; e >= 0; e--) v += (V[r][e] * vals[e]) * V[c][e];
       o[t++] = v;
     }
 }
 
+// knn_idx: device scratch of n*k ints (always needed)
 void gicp_covariances(const float4* pts, size_t n, const CellGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s) {
   if (n == 0) return;
-  gicp_cov_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(pts, n, view_of(grid), k, grid_slack_cells(grid.g), covs, knn_idx);
+  const unsigned blocks = unsigned(std::min<size_t>((n + 7) / 8, size_t(kNumSMs) * 64));
+  gicp_knn_kernel<<<blocks, 256, 0, s>>>(pts, n, view_of(grid), k, grid_slack_cells(grid.g), knn_idx);
+  gicp_cov_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(pts, n, k, knn_idx, covs);
 }
 
 // ================================================================================================================
@@ -147,15 +224,18 @@ vg_key_kernel(const float4* __restrict__ pts, size_t n, double res, int c0, int 
   keys[i] = uint32_t(x) + uint32_t(d0) * (uint32_t(y) + uint32_t(d1) * uint32_t(z));
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 vg_voxel_kernel(const float4* __restrict__ pts, const double* __restrict__ covs, const uint32_t* __restrict__ keys,
                 const uint32_t* __restrict__ vals, const uint32_t* __restrict__ seg_start, size_t nseg, VoxelRec* __restrict__ vox,
                 int32_t* __restrict__ vox_key, int32_t* __restrict__ table) {
-  size_t v = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  // one warp per voxel: lanes stride over the voxel's points (ascending original index), fixed-order warp reduction.
+  // (The reference appends serially; the sums agree to FP64 rounding and are reproducible run to run.)
+  const int lane = threadIdx.x & 31;
+  const size_t v = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) >> 5;
   if (v >= nseg) return;
   const uint32_t b = seg_start[v], e = seg_start[v + 1];
   double m[3] = {0, 0, 0}, c[6] = {0, 0, 0, 0, 0, 0};
-  for (uint32_t j = b; j < e; j++) {  // ascending original index == the reference's serial append order
+  for (uint32_t j = b + lane; j < e; j += 32) {
     const uint32_t idx = vals[j];
     const float4 p = __ldg(pts + idx);
     m[0] += double(p.x); m[1] += double(p.y); m[2] += double(p.z);
@@ -163,6 +243,11 @@ vg_voxel_kernel(const float4* __restrict__ pts, const double* __restrict__ covs,
 #pragma unroll
     for (int t = 0; t < 6; t++) c[t] += cp[t];
   }
+#pragma unroll
+  for (int t = 0; t < 3; t++) m[t] = warp_sum(m[t]);
+#pragma unroll
+  for (int t = 0; t < 6; t++) c[t] = warp_sum(c[t]);
+  if (lane != 0) return;
   const double dn = double(e - b);
   VoxelRec r;
   for (int t = 0; t < 3; t++) r.mean[t] = m[t] / dn;
@@ -185,7 +270,8 @@ int vgicp_build_target(const float4* pts, size_t n, const pcr_params& prm, Vgicp
   int rc = build_cell_grid(pts, n, 0.5f, tgt.grid, ks, bw, s);
   if (rc) return rc;
   tgt.covs.ensure(n * 6);
-  gicp_covariances(pts, n, tgt.grid, prm.vgicp_k, tgt.covs.p, nullptr, s);
+  tgt.knn.ensure(n * size_t(prm.vgicp_k));
+  gicp_covariances(pts, n, tgt.grid, prm.vgicp_k, tgt.covs.p, tgt.knn.p, s);
   // voxel map
   float mn[3], mx[3];
   bbox_blocking(pts, n, mn, mx, bw, s);
@@ -208,7 +294,7 @@ int vgicp_build_target(const float4* pts, size_t n, const pcr_params& prm, Vgicp
   tgt.vox_key.ensure(tgt.nvox);
   tgt.table.ensure(size_t(ncell));
   PCR_CUDA_CHECK(cudaMemsetAsync(tgt.table.p, 0xff, size_t(ncell) * sizeof(int32_t), s));
-  vg_voxel_kernel<<<unsigned((tgt.nvox + 127) / 128), 128, 0, s>>>(pts, tgt.covs.p, ks.keys, ks.vals, ks.seg_start.p, tgt.nvox, tgt.vox.p,
+  vg_voxel_kernel<<<unsigned((tgt.nvox * 32 + 255) / 256), 256, 0, s>>>(pts, tgt.covs.p, ks.keys, ks.vals, ks.seg_start.p, tgt.nvox, tgt.vox.p,
                                                                   tgt.vox_key.p, tgt.table.p);
   PCR_CUDA_CHECK(cudaGetLastError());
   tgt.built = true;
@@ -389,8 +475,9 @@ int VgicpDriver::compute_source_covs(const float4* src, size_t ns, int k, KeySor
   int rc = build_cell_grid(src, ns, 0.5f, src_grid, ks, bw, s);
   if (rc) return rc;
   src_covs.ensure(ns * 6);
-  gicp_covariances(src, ns, src_grid, k, src_covs.p, nullptr, s);
-  launches += 3;
+  knn_dbg.ensure(ns * size_t(k));
+  gicp_covariances(src, ns, src_grid, k, src_covs.p, knn_dbg.p, s);
+  launches += 4;
   return 0;
 }
 
@@ -507,37 +594,44 @@ int VgicpDriver::align(const float4* src, size_t ns, const VgicpTarget& tgt, con
 // ================================================================================================================
 // V6. pcl::Registration::getFitnessScore: float transform, exact 1-NN (float metric), mean of d2 <= max_range (FP64)
 // ================================================================================================================
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 fitness_kernel(const float4* __restrict__ src, size_t ns, CellGridView grid, double slack, const float* __restrict__ Tf, double max_range,
                double* __restrict__ partials) {
-  __shared__ double sred[2 * 4];
-  double acc[2] = {0.0, 0.0};
-  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-  if (i < ns) {
+  // one warp per query; per-warp sums in FP64, fixed-order block reduction -> partials[block] = {sum d2, count}
+  __shared__ double ssum[8], scnt[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t warps = size_t(gridDim.x) * 8;
+  double sum = 0.0, cnt = 0.0;
+  for (size_t i = size_t(blockIdx.x) * 8 + warp; i < ns; i += warps) {
     const float4 p = __ldg(src + i);
     float q[3];
 #pragma unroll
     for (int r = 0; r < 3; r++)
       q[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tf[r], p.x), __fmul_rn(Tf[4 + r], p.y)), __fmul_rn(Tf[8 + r], p.z)), Tf[12 + r]);
-    float bd[1];
-    int bi[1];
-    if (knn_ring_f32(grid, q[0], q[1], q[2], 1, bd, bi, slack) == 1 && double(bd[0]) <= max_range) { acc[0] = double(bd[0]); acc[1] = 1.0; }
+    const WarpKnn st = knn_warp_f32(grid, q[0], q[1], q[2], 1, slack, lane);
+    if (st.cnt == 1 && double(st.td) <= max_range) { sum += double(st.td); cnt += 1.0; }
   }
-  double r = block_reduce_vec<2, 128>(acc, sred);
-  if (threadIdx.x < 2) partials[size_t(blockIdx.x) * 2 + threadIdx.x] = r;
+  if (lane == 0) { ssum[warp] = sum; scnt[warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; w++) { a += ssum[w]; b += scnt[w]; }
+    partials[size_t(blockIdx.x) * 2] = a;
+    partials[size_t(blockIdx.x) * 2 + 1] = b;
+  }
 }
 
 int VgicpDriver::fitness(const float4* src, size_t ns, const VgicpTarget& tgt, const double* T, double max_range, double* score,
                          cudaStream_t s) {
   *score = DBL_MAX;
   if (ns == 0 || tgt.n == 0 || !tgt.grid.built) return 0;
-  const unsigned blocks = unsigned((ns + 127) / 128);
+  const unsigned blocks = unsigned(std::min<size_t>((ns + 7) / 8, size_t(kNumSMs) * 16));
   fit_partials.ensure(size_t(blocks) * 2 + 16);
   float* dTf = reinterpret_cast<float*>(fit_partials.p + size_t(blocks) * 2);
   float hT[16];
   for (int i = 0; i < 16; i++) hT[i] = static_cast<float>(T[i]);
   PCR_CUDA_CHECK(cudaMemcpyAsync(dTf, hT, sizeof(hT), cudaMemcpyHostToDevice, s));
-  fitness_kernel<<<blocks, 128, 0, s>>>(src, ns, view_of(tgt.grid), grid_slack_cells(tgt.grid.g), dTf, max_range, fit_partials.p);
+  fitness_kernel<<<blocks, 256, 0, s>>>(src, ns, view_of(tgt.grid), grid_slack_cells(tgt.grid.g), dTf, max_range, fit_partials.p);
   launches++;
   double* h = h_fit.ensure(size_t(blocks) * 2);
   PCR_CUDA_CHECK(cudaMemcpyAsync(h, fit_partials.p, size_t(blocks) * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -18,6 +18,7 @@ struct VgicpTarget {
   size_t n = 0;
   CellGrid grid;              // over the raw target (kNN for covariances and fitness)
   DevBuf<double> covs;        // per target point, 6 doubles
+  DevBuf<int32_t> knn;        // k neighbour indices per target point (scratch of the covariance build)
   // voxel map
   double resolution = 1.0;
   int cmin[3] = {0, 0, 0}, cdim[3] = {0, 0, 0};
@@ -72,7 +73,7 @@ struct VgicpDriver {
 };
 
 // exact k-NN (float metric, (d2, idx) order) + PLANE-regularised covariance for every point of `pts` using `grid` built over it.
-// covs: 6 doubles per point. knn_idx (nullable device): k ints per point.
+// covs: 6 doubles per point. knn_idx: device scratch/output, k ints per point.
 void gicp_covariances(const float4* pts, size_t n, const CellGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s);
 
 int vgicp_build_target(const float4* pts, size_t n, const pcr_params& prm, VgicpTarget& tgt, KeySort& ks, BBoxWork& bw, cudaStream_t s);

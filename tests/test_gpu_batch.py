@@ -34,7 +34,11 @@ def test_batch_equals_singles(method, case_fn):
     bT, bconv = c.batch_align(np.concatenate(srcs), offs, Ts)
     for (sT, sconv), T, conv in zip(singles, bT, bconv):
         assert sconv == conv
-        assert np.array_equal(sT, T), "batched result differs from the single-scan result"
+        # a batch uses fewer blocks per scan than a single registration, so the fixed-order FP64 reductions associate
+        # differently: equal to rounding, not bit for bit (each call on its own is deterministic, see below)
+        assert np.allclose(sT, T, rtol=0, atol=1e-9), "batched result differs from the single-scan result"
+    bT2, _ = c.batch_align(np.concatenate(srcs), offs, Ts)
+    assert all(np.array_equal(a, b) for a, b in zip(bT, bT2)), "the same call must be bit-reproducible"
     c.close()
 
 
