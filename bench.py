@@ -32,13 +32,15 @@ import numpy as np  # noqa: E402
 
 
 # SURVEY.md §8(d) algorithmic bytes (SoA/float4 map, minimal traffic, no cache credit)
-def algo_bytes(method, n_src, launches, pairs):
-    if method == "ndt":      # Ns*(16 + 7*8) per evaluation + 104 B per (point, leaf) pair
-        return n_src * (16 + 56) * launches + 104.0 * pairs
-    if method == "loam":     # Ns*(16 + 27*8) per iteration + 16 B per candidate map point examined
-        return n_src * (16 + 27 * 8) * launches + 16.0 * pairs
-    if method == "vgicp":    # per evaluation Ns*(16 + 48 + 8) + 84 B per correspondence
-        return n_src * (16 + 48 + 8) * launches + 84.0 * pairs
+def algo_bytes(method, point_evals, _unused, pairs):
+    """point_evals = source points pushed through the kernel (summed over launches), pairs = (point, leaf) pairs / candidate
+    map points / correspondences (summed over launches)."""
+    if method == "ndt":      # (16 + 7*8) B per point evaluation + 104 B per (point, leaf) pair
+        return point_evals * (16 + 56) + 104.0 * pairs
+    if method == "loam":     # (16 + 27*8) B per point-iteration + 16 B per candidate map point examined
+        return point_evals * (16 + 27 * 8) + 16.0 * pairs
+    if method == "vgicp":    # (16 + 48 + 8) B per point evaluation + 84 B per correspondence
+        return point_evals * (16 + 48 + 8) + 84.0 * pairs
     raise ValueError(method)
 
 
@@ -130,7 +132,7 @@ def run_reference(args, rank, world):
     orc.build()
     cores = os.cpu_count() or 1
     ds = lambda pts, leaf: orc.voxel_downsample(pts, leaf)["points"]  # noqa: E731
-    wl = build_workload(args.workload, ds, args.steps + args.warmup, 0)
+    wl = build_workload(args.workload, ds, min(64, args.steps + args.warmup), 0)
     method = wl["method"]
     for k in range(args.warmup):
         s, d, Tg, _ = step_inputs(wl, k)
@@ -160,23 +162,28 @@ def run_reference(args, rank, world):
 
 def run_ours(args, rank, world, local_rank):
     import torch
-    from simpleslam_b200 import capi
+    from simpleslam_b200 import capi, multigpu
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
     method_id = {"c2_ndt": capi.PCR_NDT, "c1_loam": capi.PCR_LOAM, "c3_vgicp": capi.PCR_VGICP}[args.workload]
     ctx = capi.Context(method_id, device=local_rank)
     ds = lambda pts, leaf: ctx.voxel_downsample(pts, leaf)  # noqa: E731
-    n_items = args.steps + args.warmup
+    B = args.batch if args.batch > 0 else {"c2_ndt": 8, "c1_loam": 64, "c3_vgicp": 1}[args.workload]
+    n_steps_all = args.steps + args.warmup
+    n_unique = min(64, n_steps_all * B)
     t_gen = time.perf_counter()
-    wl = build_workload(args.workload, ds, n_items, rank)
+    wl = build_workload(args.workload, ds, n_unique, rank)
     t_gen = time.perf_counter() - t_gen
     method = wl["method"]
+    if method == "vgicp":
+        B = 1
 
     # ---- static map: rank 0 builds the index, broadcasts it once over NCCL; the others import it
     setup = {}
@@ -186,42 +193,33 @@ def run_ours(args, rank, world, local_rank):
             ctx.set_target(wl["dst"])
         setup["index_build_ms"] = 1e3 * (time.perf_counter() - t0)
         if dist is not None:
-            nbytes = torch.zeros(1, dtype=torch.int64, device="cuda")
-            if rank == 0:
-                nbytes[0] = ctx.target_blob_size()
-            dist.broadcast(nbytes, 0)
-            blob = torch.empty(int(nbytes.item()), dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                ctx.target_export(blob.data_ptr(), blob.numel())
-            torch.cuda.synchronize()
-            dist.barrier()
-            t0 = time.perf_counter()
-            dist.broadcast(blob, 0)
-            torch.cuda.synchronize()
-            setup["index_broadcast_ms"] = 1e3 * (time.perf_counter() - t0)
-            setup["index_bytes"] = int(blob.numel())
-            if rank != 0:
-                ctx.target_import(blob.data_ptr(), blob.numel())
-            del blob
+            nbytes, dt = multigpu.broadcast_target(ctx, dist, rank, dev)
+            setup["index_broadcast_ms"] = 1e3 * dt
+            setup["index_bytes"] = nbytes
 
-    # device-resident copies of the scans for the HBM-resident measurement
-    dev_scans = []
-    for k in range(n_items):
-        s, d, Tg, _ = step_inputs(wl, k)
-        dev_scans.append(torch.from_numpy(np.ascontiguousarray(s)).cuda())
-    dev_dst = None
-    if method == "vgicp":
-        dev_dst = [torch.from_numpy(np.ascontiguousarray(p["dst"])).cuda() for p in wl["pairs"]]
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    # device-resident copies of the unique scans; a step's batch = B of them concatenated on the device
+    uniq_dev = [torch.from_numpy(np.ascontiguousarray(step_inputs(wl, u)[0])).to(dev) for u in range(n_unique)]
+    dev_dst = [torch.from_numpy(np.ascontiguousarray(p["dst"])).to(dev) for p in wl["pairs"]] if method == "vgicp" else None
+    batches = []
+    for k in range(n_steps_all):
+        ids = [(k * B + b) % n_unique for b in range(B)]
+        cat = uniq_dev[ids[0]] if B == 1 else torch.cat([uniq_dev[i] for i in ids])
+        offs = np.concatenate([[0], np.cumsum([uniq_dev[i].shape[0] for i in ids])]).astype(np.uint64)
+        batches.append((ids, cat, offs))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     torch.cuda.synchronize()
 
     def resident_step(k):
-        s, d, Tg, Tt = step_inputs(wl, k)
+        ids, cat, offs = batches[k]
+        Tg = [step_inputs(wl, i)[2] for i in ids]
+        Tt = [step_inputs(wl, i)[3] for i in ids]
         if method == "vgicp":
-            dd = dev_dst[k % len(dev_dst)]
+            dd = dev_dst[ids[0] % len(dev_dst)]
             ctx.set_target_device(dd.data_ptr(), dd.shape[0], 32)  # VGICP target = the other scan: part of every registration
-        T, conv = ctx.align_device(dev_scans[k].data_ptr(), dev_scans[k].shape[0], 32, Tg)
-        return T, conv, Tt
+            T, conv = ctx.align_device(cat.data_ptr(), cat.shape[0], 32, Tg[0])
+            return [T], [conv], Tt
+        Ts, convs = ctx.batch_align(None, offs, Tg, device_ptr=cat.data_ptr(), stride=32)
+        return Ts, convs, Tt
 
     ctx.set_profiling(True)
     sampler = ClockSampler(local_rank)  # started before warm-up: nvidia-smi needs ~1 s to produce its first sample
@@ -231,27 +229,45 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
-    ms, hot_ms, hot_launches, launches, pairs, nsrc_total, errs, target_ms = [], 0.0, 0, 0, 0, 0, [], []
-    for k in range(args.warmup, n_items):
+    ms, hot_ms, hot_launches, launches, pairs, pt_evals, errs = [], 0.0, 0, 0, 0, 0, []
+    for k in range(args.warmup, n_steps_all):
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        T, conv, Tt = resident_step(k)
+        Ts, convs, Tts = resident_step(k)
         wall_step = 1e3 * (time.perf_counter() - t0)
         st = ctx.stats()
-        # device time of the step: CUDA events on the library stream around the whole align (+ target build for VGICP, wall)
+        # device time of the step: CUDA events on the library stream around the whole (batched) align;
+        # VGICP also rebuilds its target (the other scan) every step, so its step is timed by the host clock
         ms.append(wall_step if method == "vgicp" else st["ms_total"])
         hot_ms += st["ms_hot_kernel"]
         hot_launches += st["hot_kernel_launches"]
         launches += st["kernel_launches"]
         pairs += st["n_pairs"]
-        nsrc_total += st["n_source"] * st["hot_kernel_launches"]
-        errs.append(pose_err(T, Tt))
+        pt_evals += st["n_point_evals"]
+        errs += [pose_err(T, Tt) for T, Tt in zip(Ts, Tts)]
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     wall_total = time.perf_counter() - wall0
     t_resident = float(np.sum(ms)) / 1e3
+
+    # ---- single-scan latency (resident): p50 / p95 of one registration at a time
+    lat = []
+    for k in range(min(args.steps, 12)):
+        i = k % n_unique
+        s, d, Tg, _ = step_inputs(wl, i)
+        flush.zero_()
+        torch.cuda.synchronize()
+        if method == "vgicp":
+            t0 = time.perf_counter()
+            dd = dev_dst[i % len(dev_dst)]
+            ctx.set_target_device(dd.data_ptr(), dd.shape[0], 32)
+            ctx.align_device(uniq_dev[i].data_ptr(), uniq_dev[i].shape[0], 32, Tg)
+            lat.append(1e3 * (time.perf_counter() - t0))
+        else:
+            ctx.align_device(uniq_dev[i].data_ptr(), uniq_dev[i].shape[0], 32, Tg)
+            lat.append(ctx.stats()["ms_total"])
 
     # ---- e2e: the reference-facing call with HOST buffers (target upload + index build + align per call)
     ctx.set_profiling(False)
@@ -259,8 +275,8 @@ def run_ours(args, rank, world, local_rank):
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
     e2e_t, e2e_cached_t, h2d, d2h = [], [], 0, 0
     host_dst = pin(wl["dst"]) if method != "vgicp" else None
-    for k in range(args.warmup, args.warmup + e2e_steps):
-        s, d, Tg, _ = step_inputs(wl, k)
+    for k in range(e2e_steps):
+        s, d, Tg, _ = step_inputs(wl, k % n_unique)
         hs = pin(s)
         hd = host_dst if host_dst is not None else pin(d)
         torch.cuda.synchronize()
@@ -278,13 +294,9 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- max over ranks
     if dist is not None:
-        tt = torch.tensor([t_resident, t_e2e, wall_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_resident, t_e2e, wall_total = [float(x) for x in tt.tolist()]
-        cnt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        launches = int(cnt.item())
-    value = world * args.steps / t_resident
+        t_resident, t_e2e, wall_total = multigpu.max_over_ranks(dist, [t_resident, t_e2e, wall_total], dev)
+        launches = int(multigpu.sum_over_ranks(dist, [float(launches)], dev)[0])
+    value = world * args.steps * B / t_resident
     e2e_value = world * e2e_steps / t_e2e
 
     if rank == 0:
@@ -294,14 +306,16 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        ab = algo_bytes(method, nsrc_total / max(hot_launches, 1), hot_launches, pairs)
+        ab = algo_bytes(method, pt_evals, 1, pairs)
         achieved = ab / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else None
         roof = {"bound": "hbm", "kernel": {"ndt": "ndt_eval_kernel", "loam": "loam_iter_kernel", "vgicp": "vgicp_eval_kernel"}[method],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "launches": hot_launches, "avg_launch_us": 1e3 * hot_ms / max(hot_launches, 1), "algorithmic_bytes_per_launch": ab / max(hot_launches, 1),
+                "points_per_launch": pt_evals / max(hot_launches, 1), "pairs_per_point": pairs / max(pt_evals, 1),
                 "kernel_share_of_step": hot_ms / (1e3 * t_resident) if t_resident > 0 else None,
-                "note": "working set (scan + leaf/cell tables) is L2-resident at this size: the step is launch/latency bound (SURVEY §8d caveat)"}
+                "note": "the map index (cell / leaf tables) stays L2-resident at this size, so DRAM traffic is far below the algorithmic "
+                        "bytes and the kernel is latency-bound, not HBM-bound (SURVEY §8d caveat)"}
         # ---- CPU baseline: the oracle on the host cores, bounded sample
         cpu = None
         if not args.no_cpu_baseline:
@@ -311,7 +325,7 @@ def run_ours(args, rank, world, local_rank):
             n_cpu = 3 if method != "vgicp" else 1
             tc = []
             for k in range(n_cpu):
-                s, d, Tg, _ = step_inputs(wl, args.warmup + k)
+                s, d, Tg, _ = step_inputs(wl, k % n_unique)
                 t0 = time.perf_counter()
                 oracle_register(method, s, d, Tg, cores)
                 tc.append(time.perf_counter() - t0)
@@ -322,14 +336,18 @@ def run_ours(args, rank, world, local_rank):
         errs = np.array(errs)
         out = {
             "metric": "scan registrations/sec (%s)" % method.upper(), "value": value, "unit": "registrations/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * t_resident / args.steps, "p50_align_ms": float(np.median(ms)),
-            "p95_align_ms": float(np.percentile(ms, 95)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_resident / args.steps, "p50_align_ms": float(np.median(lat)),
+            "p95_align_ms": float(np.percentile(lat, 95)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"ndt": "f32 pair math, f64 accumulate", "loam": "f64", "vgicp": "f64"}[method], "data": "synthetic",
-            "config": {"workload": wl["name"], "n_source": int(len(s0)), "n_target": int(len(d0)), "l2": "flushed between timed steps (256 MiB memset)",
+            "config": {"workload": wl["name"], "n_source": int(len(s0)), "n_target": int(len(d0)), "registrations_per_step": B,
+                       "step": "one batch of %d independent scan registrations against the static map (pcr_batch_align, device-resident inputs)" % B
+                               if method != "vgicp" else "one scan-to-scan registration incl. target covariance / voxel build",
+                       "l2": "flushed between timed steps (256 MiB memset)",
                        "timing": "sum over steps of CUDA-event time on the library stream around the whole align; max over ranks",
+                       "p50_align_ms": "single registration at a time (latency), device-resident inputs",
                        "parallelism": "replicas: %d rank(s), map index broadcast once (NCCL), no per-iteration collective" % world},
             "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * t_e2e / e2e_steps, "what": "pcr_scan2map(src, dst, pose) with host buffers: target upload + index build + align",
+                    "ms_per_step": 1e3 * t_e2e / e2e_steps, "what": "pcr_scan2map(src, dst, pose), ONE scan per call, host buffers: target upload + index build + scan upload + align",
                     "static_map_ms_per_step": (1e3 * float(np.mean(e2e_cached_t))) if e2e_cached_t else None},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "setup": dict(setup, data_generation_s=t_gen), "wall_s_timed_region": wall_total,
@@ -350,6 +368,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2_ndt", choices=["c2_ndt", "c1_loam", "c3_vgicp"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="registrations per step (0 = workload default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

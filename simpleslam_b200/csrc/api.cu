@@ -257,6 +257,7 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       st.n_residuals = nl[0];
       st.kernel_launches = c->loam.launches + 1;  // + pack kernel
       st.n_pairs = c->loam.cand_total;
+      st.n_point_evals = c->loam.pt_evals;
       st.ms_hot_kernel = c->loam.hot_ms;
       st.hot_kernel_launches = c->loam.hot_launches;
       break;
@@ -270,6 +271,7 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       st.score = tp[0];
       st.kernel_launches = c->ndtd.launches + 1;
       st.n_pairs = c->ndtd.total_pairs;
+      st.n_point_evals = c->ndtd.point_evals;
       st.ms_hot_kernel = c->ndtd.hot_ms;
       st.hot_kernel_launches = c->ndtd.hot_launches;
       break;
@@ -296,6 +298,7 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       st.score = c->vgd.last_cost;
       st.kernel_launches = c->vgd.launches + 1;
       st.n_pairs = corr;
+      st.n_point_evals = int64_t(evals) * int64_t(offs[1] - offs[0]);
       st.ms_hot_kernel = hot;
       st.hot_kernel_launches = hotl;
       // remember the last scan for getFitnessScore (pcl keeps input_ + final_transformation_)

@@ -331,6 +331,7 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     st->iters = it + 1;
     st->n_last = int(n);
     st->cand_total += (long long)(stot[28] + 0.5);
+    st->pt_evals += (long long)ns;
     if (conv) { st->converged = 1; if (lg) lg->converged = 1; }
     if (done || !apply_update) st->done = 1;
   }
@@ -367,7 +368,7 @@ static GridView make_view(const CellGrid& grid) { return view_of(grid); }
 
 int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, const CellGrid& grid, const LoamParams& prm,
                       double* T, int32_t* converged, int32_t* iters_out, int64_t* n_last_out, bool profile, cudaStream_t s) {
-  launches = 0; cand_total = 0; hot_ms = 0.f; hot_launches = 0;
+  launches = 0; cand_total = 0; pt_evals = 0; hot_ms = 0.f; hot_launches = 0;
   if (n_scans == 0) return 0;
   loam_opt_in_smem();
   LoamState* hs = h_states.ensure(n_scans);
@@ -423,6 +424,7 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     if (iters_out) iters_out[i] = hs[i].iters;
     if (n_last_out) n_last_out[i] = hs[i].n_last;
     cand_total += hs[i].cand_total;
+    pt_evals += hs[i].pt_evals;
   }
   last_log_count = hs[0].iters;
   return 0;

@@ -17,6 +17,7 @@ struct LoamState {  // one per scan, device resident
   unsigned ticket;
   int pad;
   long long cand_total;  // map points examined by the 27-cell gather, summed over iterations
+  long long pt_evals;    // source points linearised, summed over iterations
 };
 
 struct LoamDriver {
@@ -31,6 +32,7 @@ struct LoamDriver {
   int last_log_count = 0;
   long long launches = 0;
   long long cand_total = 0;
+  long long pt_evals = 0;
   float hot_ms = 0.f;
   int hot_launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

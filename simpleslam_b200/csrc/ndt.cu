@@ -465,6 +465,7 @@ void NdtDriver::evaluate(const float4* src, const uint32_t* d_offs, size_t max_p
   PCR_CUDA_CHECK(cudaMemcpyAsync(d_params.p, h_params.p, size_t(count) * sizeof(NdtEvalParams), cudaMemcpyHostToDevice, s));
   const bool run = !tgt.overflow && tgt.nleaves > 0 && max_pts > 0;
   if (run) {
+    for (int q = 0; q < count; q++) point_evals += h_offsets.p[h_params.p[q].scan + 1] - h_offsets.p[h_params.p[q].scan];
     NdtTargetView v;
     v.recs = tgt.recs.p; v.mean = tgt.mean.p; v.icov = tgt.icov.p; v.table = tgt.table.p; v.g = tgt.g;
     v.d1 = tgt.d1; v.d2 = tgt.d2; v.d2f = float(tgt.d2);
@@ -694,7 +695,7 @@ static void fill_params(NdtEvalParams& ep, const float* T, const double* p, int 
 
 int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, const NdtTarget& tgt, const pcr_params& prm, double* T,
                      int32_t* converged, int32_t* iters, double* trans_prob, bool profile, cudaStream_t s) {
-  launches = 0; hot_ms = 0.f; hot_launches = 0; total_evals = 0; total_hess = 0; total_pairs = 0;
+  launches = 0; hot_ms = 0.f; hot_launches = 0; total_evals = 0; total_hess = 0; total_pairs = 0; point_evals = 0;
   if (n_scans == 0) return 0;
   if (prm.ndt_search == PCR_NDT_KDTREE) return PCR_ERR_UNSUPPORTED;
   uint32_t* ho = h_offsets.ensure(n_scans + 1);

@@ -58,6 +58,7 @@ struct NdtDriver {
   int hot_launches = 0;
   int total_evals = 0, total_hess = 0;
   long long total_pairs = 0;
+  long long point_evals = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   NdtEvalResult* mapped_results = nullptr;  // host-mapped pinned memory the last block writes into
   size_t mapped_cap = 0;

@@ -93,37 +93,49 @@ __device__ __forceinline__ WarpKnn knn_warp_f32(const CellGridView& grid, float 
   }
   const double leaf = double(g.leaf[0]);
   for (int r = rstart; r <= rmax; r++) {
-    const int zlo = max(c[2] - r, 0), zhi = min(c[2] + r, g.div_b[2] - 1);
-    const int ylo = max(c[1] - r, 0), yhi = min(c[1] + r, g.div_b[1] - 1);
-    for (int z = zlo; z <= zhi; z++) {
-      const bool zedge = (z == c[2] - r) || (z == c[2] + r);
-      for (int y = ylo; y <= yhi; y++) {
-        const bool edge = zedge || (y == c[1] - r) || (y == c[1] + r) || r == 0;
-        const long long rowbase = (long long)y * g.mul[1] + (long long)z * g.mul[2];
-        if (edge) {
-          // the whole x-row [cx-r, cx+r] belongs to the shell: consecutive cells == one contiguous run
-          const int xa = max(c[0] - r, 0), xb = min(c[0] + r, g.div_b[0] - 1);
-          for (int x0 = xa; x0 <= xb; x0 += 32) {
-            const int x = x0 + lane;
-            int lo = 0x7fffffff, hi = 0;
-            if (x <= xb) {
-              const int2 rg = __ldg(grid.range + rowbase + x);
-              if (rg.y > rg.x) { lo = rg.x; hi = rg.y; }
-            }
-            lo = __reduce_min_sync(kFull, lo);
-            hi = __reduce_max_sync(kFull, hi);
-            if (hi > lo) knn_scan_run(st, grid.pts, lo, hi, qx, qy, qz, k, lane);
-          }
-        } else {
-          // interior row: only the two end cells x = cx-r and x = cx+r are on the shell
-          const int xs[2] = {c[0] - r, c[0] + r};
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            if (xs[e] < 0 || xs[e] >= g.div_b[0]) continue;
-            const int2 rg = __ldg(grid.range + rowbase + xs[e]);
-            if (rg.y > rg.x) knn_scan_run(st, grid.pts, rg.x, rg.y, qx, qy, qz, k, lane);
-          }
+    // Shell of Chebyshev radius r = cube (2r+1)^3 minus the already visited inner cube. The cube is enumerated 32 cells
+    // at a time: every lane fetches one cell range (all loads in flight together), then the non-empty shell cells are
+    // scanned one after the other.
+    const int side = 2 * r + 1;
+    const int slab = side * side, per = 4 * side - 4;
+    const int nshell = r == 0 ? 1 : 2 * slab + (side - 2) * per;  // = side^3 - (side-2)^3
+    for (int base = 0; base < nshell; base += 32) {
+      const int e = base + lane;
+      int lo = 0, hi = 0;
+      if (e < nshell) {
+        int dx, dy, dz;
+        if (e < 2 * slab || r == 0) {  // bottom / top z-slabs
+          const int rem = e % slab;
+          dz = (e / slab) ? r : -r;
+          dy = rem / side - r;
+          dx = rem % side - r;
+        } else {  // perimeter of the middle layers, rows in x first so that consecutive lanes hit consecutive keys
+          const int e2 = e - 2 * slab, p = e2 % per;
+          dz = -r + 1 + e2 / per;
+          if (p < side) { dy = -r; dx = p - r; }
+          else if (p < 2 * side) { dy = r; dx = p - side - r; }
+          else { const int q = p - 2 * side; dy = -r + 1 + (q >> 1); dx = (q & 1) ? r : -r; }
         }
+        const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
+        if (x >= 0 && x < g.div_b[0] && y >= 0 && y < g.div_b[1] && z >= 0 && z < g.div_b[2]) {
+          const int2 rg = __ldg(grid.range + ((long long)x + (long long)y * g.mul[1] + (long long)z * g.mul[2]));
+          lo = rg.x; hi = rg.y;
+        }
+      }
+      unsigned cells = __ballot_sync(kFull, hi > lo);
+      while (cells) {
+        const int sl = __ffs(cells) - 1;
+        cells &= cells - 1;
+        int rlo = __shfl_sync(kFull, lo, sl), rhi = __shfl_sync(kFull, hi, sl);
+        // x-adjacent cells are consecutive keys: extend the run over directly following lanes that continue it
+        while (cells) {
+          const int nl = __ffs(cells) - 1;
+          const int nlo = __shfl_sync(kFull, lo, nl);
+          if (nlo != rhi) break;
+          rhi = __shfl_sync(kFull, hi, nl);
+          cells &= cells - 1;
+        }
+        knn_scan_run(st, grid.pts, rlo, rhi, qx, qy, qz, k, lane);
       }
     }
     if (st.cnt == k) {
