@@ -32,15 +32,17 @@ import numpy as np  # noqa: E402
 
 
 # SURVEY.md §8(d) algorithmic bytes (SoA/float4 map, minimal traffic, no cache credit)
-def algo_bytes(method, point_evals, _unused, pairs):
-    """point_evals = source points pushed through the kernel (summed over launches), pairs = (point, leaf) pairs / candidate
-    map points / correspondences (summed over launches)."""
-    if method == "ndt":      # (16 + 7*8) B per point evaluation + 104 B per (point, leaf) pair
-        return point_evals * (16 + 56) + 104.0 * pairs
-    if method == "loam":     # (16 + 27*8) B per point-iteration + 16 B per candidate map point examined
-        return point_evals * (16 + 27 * 8) + 16.0 * pairs
-    if method == "vgicp":    # (16 + 48 + 8) B per point evaluation + 84 B per correspondence
-        return point_evals * (16 + 48 + 8) + 84.0 * pairs
+def algo_bytes(method, point_evals, index_reads, pairs):
+    """Algorithmic bytes of the hot kernel: what the algorithm has to read once, no cache credit.
+    point_evals = source points pushed through the kernel (summed over launches); index_reads = spatial-index entries read
+    (LOAM: x-rows looked up, 2 x 4 B each; NDT / VGICP: 4-byte voxel-table entries); pairs = candidate map points examined
+    (LOAM, 16 B) / (point, leaf) pairs (NDT, 64-byte leaf record) / correspondences (VGICP, 80-byte voxel record)."""
+    if method == "ndt":
+        return point_evals * 16.0 + index_reads * 4.0 + 64.0 * pairs
+    if method == "loam":
+        return point_evals * 16.0 + index_reads * 8.0 + 16.0 * pairs
+    if method == "vgicp":    # point 16 B + source covariance 48 B + table entry + voxel record
+        return point_evals * (16.0 + 48.0) + index_reads * 4.0 + 80.0 * pairs
     raise ValueError(method)
 
 
@@ -97,6 +99,8 @@ def build_workload(name, downsample, n_scans, seed_offset):
         return workloads.c1_loam(downsample, n_scans, seed_offset=seed_offset)
     if name == "c3_vgicp":
         return workloads.c3_vgicp(n_scans, seed_offset=seed_offset)
+    if name in ("c4_loam", "c4_ndt"):
+        return workloads.c4_batched(name[3:], downsample, n_scans, seed_offset=seed_offset)
     raise SystemExit("unknown workload " + name)
 
 
@@ -172,10 +176,12 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
-    method_id = {"c2_ndt": capi.PCR_NDT, "c1_loam": capi.PCR_LOAM, "c3_vgicp": capi.PCR_VGICP}[args.workload]
+    method_id = {"c2_ndt": capi.PCR_NDT, "c1_loam": capi.PCR_LOAM, "c3_vgicp": capi.PCR_VGICP, "c4_loam": capi.PCR_LOAM,
+                 "c4_ndt": capi.PCR_NDT}[args.workload]
+    static_map = args.workload.startswith("c4")  # loc.cpp mode: the map is registered once, e2e = batches of host scans
     ctx = capi.Context(method_id, device=local_rank)
     ds = lambda pts, leaf: ctx.voxel_downsample(pts, leaf)  # noqa: E731
-    B = args.batch if args.batch > 0 else {"c2_ndt": 8, "c1_loam": 64, "c3_vgicp": 1}[args.workload]
+    B = args.batch if args.batch > 0 else {"c2_ndt": 8, "c1_loam": 64, "c3_vgicp": 1, "c4_loam": 128, "c4_ndt": 16}[args.workload]
     n_steps_all = args.steps + args.warmup
     n_unique = min(64, n_steps_all * B)
     t_gen = time.perf_counter()
@@ -229,7 +235,7 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
-    ms, hot_ms, hot_launches, launches, pairs, pt_evals, errs = [], 0.0, 0, 0, 0, 0, []
+    ms, hot_ms, hot_launches, launches, pairs, pt_evals, idx_reads, errs = [], 0.0, 0, 0, 0, 0, 0, []
     for k in range(args.warmup, n_steps_all):
         flush.zero_()
         torch.cuda.synchronize()
@@ -245,6 +251,7 @@ def run_ours(args, rank, world, local_rank):
         launches += st["kernel_launches"]
         pairs += st["n_pairs"]
         pt_evals += st["n_point_evals"]
+        idx_reads += st["n_index_reads"]
         errs += [pose_err(T, Tt) for T, Tt in zip(Ts, Tts)]
     torch.cuda.synchronize()
     if dist is not None:
@@ -274,21 +281,37 @@ def run_ours(args, rank, world, local_rank):
     e2e_steps = args.steps
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
     e2e_t, e2e_cached_t, h2d, d2h = [], [], 0, 0
-    host_dst = pin(wl["dst"]) if method != "vgicp" else None
-    for k in range(e2e_steps):
-        s, d, Tg, _ = step_inputs(wl, k % n_unique)
-        hs = pin(s)
-        hd = host_dst if host_dst is not None else pin(d)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ctx.scan2map(hs, hd, Tg)
-        e2e_t.append(time.perf_counter() - t0)
-        h2d = hs.nbytes + hd.nbytes
-        d2h = 16 * 8 + 4
-        if method != "vgicp":  # static-map (loc.cpp) variant: target stays registered, only the scan crosses PCIe
+    host_dst = pin(wl["dst"]) if method != "vgicp" and not static_map else None
+    e2e_regs_per_step = B if static_map else 1
+    if static_map:
+        # loc.cpp mode: the static map stays registered; every step uploads a batch of B host scans and reads B poses back
+        host_batches = []
+        for k in range(min(e2e_steps, 4)):
+            ids = batches[k][0]
+            host_batches.append((pin(np.concatenate([step_inputs(wl, i)[0] for i in ids])), batches[k][2], [step_inputs(wl, i)[2] for i in ids]))
+        for k in range(e2e_steps):
+            hb, offs, Tg = host_batches[k % len(host_batches)]
+            torch.cuda.synchronize()
             t0 = time.perf_counter()
-            ctx.align(hs, Tg)
-            e2e_cached_t.append(time.perf_counter() - t0)
+            ctx.batch_align(hb, offs, Tg)
+            e2e_t.append(time.perf_counter() - t0)
+            h2d = hb.nbytes
+            d2h = B * (16 * 8 + 4)
+    else:
+        for k in range(e2e_steps):
+            s, d, Tg, _ = step_inputs(wl, k % n_unique)
+            hs = pin(s)
+            hd = host_dst if host_dst is not None else pin(d)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx.scan2map(hs, hd, Tg)
+            e2e_t.append(time.perf_counter() - t0)
+            h2d = hs.nbytes + hd.nbytes
+            d2h = 16 * 8 + 4
+            if method != "vgicp":  # static-map (loc.cpp) variant: target stays registered, only the scan crosses PCIe
+                t0 = time.perf_counter()
+                ctx.align(hs, Tg)
+                e2e_cached_t.append(time.perf_counter() - t0)
     t_e2e = float(np.sum(e2e_t))
     clocks = sampler.stop()  # covers warm-up, the timed resident steps and the timed e2e steps
 
@@ -297,7 +320,7 @@ def run_ours(args, rank, world, local_rank):
         t_resident, t_e2e, wall_total = multigpu.max_over_ranks(dist, [t_resident, t_e2e, wall_total], dev)
         launches = int(multigpu.sum_over_ranks(dist, [float(launches)], dev)[0])
     value = world * args.steps * B / t_resident
-    e2e_value = world * e2e_steps / t_e2e
+    e2e_value = world * e2e_steps * e2e_regs_per_step / t_e2e
 
     if rank == 0:
         peaks = {}
@@ -306,13 +329,13 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        ab = algo_bytes(method, pt_evals, 1, pairs)
+        ab = algo_bytes(method, pt_evals, idx_reads, pairs)
         achieved = ab / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else None
         roof = {"bound": "hbm", "kernel": {"ndt": "ndt_eval_kernel", "loam": "loam_iter_kernel", "vgicp": "vgicp_eval_kernel"}[method],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "launches": hot_launches, "avg_launch_us": 1e3 * hot_ms / max(hot_launches, 1), "algorithmic_bytes_per_launch": ab / max(hot_launches, 1),
-                "points_per_launch": pt_evals / max(hot_launches, 1), "pairs_per_point": pairs / max(pt_evals, 1),
+                "points_per_launch": pt_evals / max(hot_launches, 1), "pairs_per_point": pairs / max(pt_evals, 1), "index_reads_per_point": idx_reads / max(pt_evals, 1),
                 "kernel_share_of_step": hot_ms / (1e3 * t_resident) if t_resident > 0 else None,
                 "note": "the map index (cell / leaf tables) stays L2-resident at this size, so DRAM traffic is far below the algorithmic "
                         "bytes and the kernel is latency-bound, not HBM-bound (SURVEY §8d caveat)"}
@@ -347,7 +370,8 @@ def run_ours(args, rank, world, local_rank):
                        "p50_align_ms": "single registration at a time (latency), device-resident inputs",
                        "parallelism": "replicas: %d rank(s), map index broadcast once (NCCL), no per-iteration collective" % world},
             "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * t_e2e / e2e_steps, "what": "pcr_scan2map(src, dst, pose), ONE scan per call, host buffers: target upload + index build + scan upload + align",
+                    "ms_per_step": 1e3 * t_e2e / e2e_steps, "what": ("pcr_batch_align of %d host scans per call against the registered static map (loc.cpp mode): scan upload + align + pose read-back" % B) if static_map
+                    else "pcr_scan2map(src, dst, pose), ONE scan per call, host buffers: target upload + index build + scan upload + align",
                     "static_map_ms_per_step": (1e3 * float(np.mean(e2e_cached_t))) if e2e_cached_t else None},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
             "setup": dict(setup, data_generation_s=t_gen), "wall_s_timed_region": wall_total,
@@ -366,11 +390,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2_ndt", choices=["c2_ndt", "c1_loam", "c3_vgicp"])
+    ap.add_argument("--workload", default="c2_ndt", choices=["c2_ndt", "c1_loam", "c3_vgicp", "c4_loam", "c4_ndt"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="registrations per step (0 = workload default)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 0)
+    args.warmup = max(args.warmup, 3)  # timing rules: W >= 3
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -86,6 +86,8 @@ typedef struct pcr_stats {
   int64_t n_pairs;           /* LOAM: map points examined by the 27-cell gather (sum over iterations and scans); NDT: (point, leaf)
                                 pairs evaluated (sum over evaluations); VGICP: correspondences (sum over evaluations) */
   int64_t n_point_evals;     /* source points pushed through the hot kernel, summed over its launches (roofline numerator) */
+  int64_t n_index_reads;     /* spatial-index entries read by the hot kernel: LOAM x-row lookups (2 x 4 B each), NDT voxel-table
+                                lookups (4 B each), VGICP voxel-table lookups (4 B each); summed over launches */
   double score;              /* NDT trans_probability; VGICP last cost */
   float ms_total;            /* device time of the last align call (CUDA events on the context's stream) */
   float ms_hot_kernel;       /* summed device time of the dominant correspondence/accumulation kernel */

@@ -1,8 +1,17 @@
-import json,sys
-for w in sys.argv[1:]:
+"""One line per bench JSON: python profiles/bench_summary.py gpurun_out/bench_*.json"""
+import json
+import sys
+
+for f in sys.argv[1:]:
     try:
-        d=json.load(open("gpurun_out/bench_%s.json"%w))
+        d = json.load(open(f))
     except Exception as e:
-        print(w,'FAILED',e); continue
-    r=d["roofline"]
-    print(w, "value %.1f"%d["value"], "ms/step %.3f"%d["ms_per_step"], "e2e %.1f (%.3f ms, static %s)"%(d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"]["static_map_ms_per_step"]), "kern us %.1f frac %.3f share %.2f launches %d"%(r["avg_launch_us"], r["frac"] or 0, r["kernel_share_of_step"], r["launches"]), "cpu", d["cpu_baseline"] and d["cpu_baseline"]["ms_per_registration"], "p50 %.3f B %s"%(d["p50_align_ms"], d["config"].get("registrations_per_step")), "n", d["config"]["n_source"], d["config"]["n_target"], "err", d["pose_error_vs_truth"])
+        print(f, "FAILED", e)
+        continue
+    r = d["roofline"]
+    cpu = d.get("cpu_baseline") or {}
+    print("%s\n  value %.1f/s  ms/step %.3f  p50 %.3f ms | e2e %.1f/s (%.3f ms/step, static-map %s) | kernel %s: %.1f us/launch, frac %.3f (%.0f GB/s), share %.2f, launches %d, pts/launch %.0f, pairs/pt %.1f | cpu %.2f ms/reg (%s cores) | n %s / %s | setup %s | err %s | clocks %s"
+          % (f, d["value"], d["ms_per_step"], d["p50_align_ms"], d["e2e"]["value"], d["e2e"]["ms_per_step"], d["e2e"].get("static_map_ms_per_step"),
+             r["kernel"], r["avg_launch_us"], r["frac"] or 0, r["achieved"] or 0, r["kernel_share_of_step"] or 0, r["launches"], r["points_per_launch"],
+             r["pairs_per_point"], cpu.get("ms_per_registration", float("nan")), cpu.get("cores"), d["config"]["n_source"], d["config"]["n_target"],
+             d.get("setup"), d.get("pose_error_vs_truth"), d.get("clocks")))

@@ -44,6 +44,7 @@ class Stats(ctypes.Structure):
     _fields_ = [
         ("iterations", ctypes.c_int32), ("evaluations", ctypes.c_int32), ("hessian_evals", ctypes.c_int32), ("converged", ctypes.c_int32),
         ("n_source", ctypes.c_int64), ("n_target", ctypes.c_int64), ("n_residuals", ctypes.c_int64), ("kernel_launches", ctypes.c_int64), ("n_pairs", ctypes.c_int64), ("n_point_evals", ctypes.c_int64),
+        ("n_index_reads", ctypes.c_int64),
         ("score", ctypes.c_double), ("ms_total", ctypes.c_float), ("ms_hot_kernel", ctypes.c_float),
         ("hot_kernel_launches", ctypes.c_int32), ("pad", ctypes.c_int32),
     ]

@@ -202,8 +202,7 @@ static int build_target(pcr_ctx* c, const float4* pts, size_t n) {
   int rc = 0;
   switch (c->prm.method) {
     case PCR_LOAM:
-      // the gate radius is sqrt(max_knn_d2): cells at least that wide make the 27-cell gather exact
-      rc = build_cell_grid(pts, n, std::max(1.0f, std::sqrt(c->prm.loam_max_knn_d2) * 1.00001f), c->loam_grid, c->ks, c->bw, c->stream);
+      rc = loam_build_target(pts, n, double(c->prm.loam_max_knn_d2), c->loam_grid, c->ks, c->bw, c->stream);
       break;
     case PCR_NDT:
       rc = ndt_build_target(pts, n, c->prm, c->ndt, c->ks, c->bw, c->stream);
@@ -258,6 +257,7 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       st.kernel_launches = c->loam.launches + 1;  // + pack kernel
       st.n_pairs = c->loam.cand_total;
       st.n_point_evals = c->loam.pt_evals;
+      st.n_index_reads = c->loam.rows_total;
       st.ms_hot_kernel = c->loam.hot_ms;
       st.hot_kernel_launches = c->loam.hot_launches;
       break;
@@ -272,6 +272,7 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       st.kernel_launches = c->ndtd.launches + 1;
       st.n_pairs = c->ndtd.total_pairs;
       st.n_point_evals = c->ndtd.point_evals;
+      st.n_index_reads = c->ndtd.point_evals * (c->prm.ndt_search == PCR_NDT_DIRECT1 ? 1 : c->prm.ndt_search == PCR_NDT_DIRECT7 ? 7 : c->prm.ndt_search == PCR_NDT_DIRECT26 ? 26 : 27);
       st.ms_hot_kernel = c->ndtd.hot_ms;
       st.hot_kernel_launches = c->ndtd.hot_launches;
       break;
@@ -299,6 +300,7 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       st.kernel_launches = c->vgd.launches + 1;
       st.n_pairs = corr;
       st.n_point_evals = int64_t(evals) * int64_t(offs[1] - offs[0]);
+      st.n_index_reads = st.n_point_evals;
       st.ms_hot_kernel = hot;
       st.hot_kernel_launches = hotl;
       // remember the last scan for getFitnessScore (pcl keeps input_ + final_transformation_)
@@ -308,7 +310,7 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       break;
     }
   }
-  if (rc == PCR_ERR_UNSUPPORTED) return fail(c, rc, "unsupported option (NDT KDTREE neighbourhood is not built yet)");
+  if (rc == PCR_ERR_UNSUPPORTED) return fail(c, rc, "unsupported option");
   if (rc) return fail(c, rc, "align failed");
   PCR_CUDA_CHECK(cudaEventRecord(c->ev_b, c->stream));
   PCR_CUDA_CHECK(cudaEventSynchronize(c->ev_b));
@@ -490,9 +492,10 @@ int collect_sections(pcr_ctx* c, BlobHeader& h, const void* ptrs[8]) {
     case PCR_LOAM:
       h.g = c->loam_grid.g;
       h.i[0] = c->loam_grid.built ? 1 : 0;
+      h.i[1] = c->loam_grid.max_ring;
       if (c->loam_grid.built) {
         ptrs[0] = c->loam_grid.pts.p; h.sizes[0] = c->loam_grid.n * sizeof(float4);
-        ptrs[1] = c->loam_grid.range.p; h.sizes[1] = size_t(c->loam_grid.g.ncell) * sizeof(int2);
+        ptrs[1] = c->loam_grid.start.p; h.sizes[1] = (size_t(c->loam_grid.g.ncell) + 1) * sizeof(int32_t);
       }
       break;
     case PCR_NDT:
@@ -509,6 +512,7 @@ int collect_sections(pcr_ctx* c, BlobHeader& h, const void* ptrs[8]) {
         ptrs[4] = c->ndt.cov.p; h.sizes[4] = L * 9 * sizeof(double);
         ptrs[5] = c->ndt.keys.p; h.sizes[5] = L * sizeof(int32_t);
         ptrs[6] = c->ndt.npts.p; h.sizes[6] = L * sizeof(int32_t);
+        ptrs[7] = c->ndt.centroids.p; h.sizes[7] = L * sizeof(float4);
       }
       break;
     default:
@@ -571,11 +575,13 @@ extern "C" int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes)
     c->loam_grid.g = h.g;
     c->loam_grid.n = h.sizes[0] / sizeof(float4);
     c->loam_grid.built = h.i[0] != 0;
+    c->loam_grid.max_ring = h.i[1];
     if (c->loam_grid.built) {
       c->loam_grid.pts.ensure(c->loam_grid.n);
-      c->loam_grid.range.ensure(size_t(h.g.ncell));
+      c->loam_grid.start.ensure(size_t(h.g.ncell) + 1);
+      c->loam_grid.has_start = true;
       take(c->loam_grid.pts.p, 0);
-      take(c->loam_grid.range.p, 1);
+      take(c->loam_grid.start.p, 1);
     }
   } else if (h.method == PCR_NDT) {
     NdtTarget& t = c->ndt;
@@ -586,8 +592,9 @@ extern "C" int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes)
     if (!t.overflow && t.nleaves) {
       const size_t L = t.nleaves;
       t.recs.ensure(L); t.table.ensure(size_t(h.g.ncell)); t.mean.ensure(L * 3); t.icov.ensure(L * 9); t.cov.ensure(L * 9);
-      t.keys.ensure(L); t.npts.ensure(L);
+      t.keys.ensure(L); t.npts.ensure(L); t.centroids.ensure(L);
       take(t.recs.p, 0); take(t.table.p, 1); take(t.mean.p, 2); take(t.icov.p, 3); take(t.cov.p, 4); take(t.keys.p, 5); take(t.npts.p, 6);
+      take(t.centroids.p, 7);
     }
     t.built = true;
   } else {
@@ -646,7 +653,6 @@ extern "C" int pcr_ndt_get_leaves(pcr_ctx* c, int32_t* keys, int32_t* npts, doub
 static int ndt_eval_one(pcr_ctx* c, const void* src, size_t ns, size_t stride, const double p[6], const float* Tf, int kind, int hess,
                         NdtEvalResult& out) {
   if (c->prm.method != PCR_NDT || !c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no NDT target");
-  if (c->prm.ndt_search == PCR_NDT_KDTREE) return fail(c, PCR_ERR_UNSUPPORTED, "NDT KDTREE neighbourhood is not built yet");
   const float4* d = upload_points(c, src, ns, stride, c->raw_src, c->src);
   uint32_t* ho = c->ndtd.h_offsets.ensure(2);
   ho[0] = 0; ho[1] = uint32_t(ns);

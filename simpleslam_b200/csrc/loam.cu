@@ -1,9 +1,11 @@
-// LOAM scan-to-map: one fused kernel per Gauss-Newton iteration. A warp owns a tile of 32 query points:
-//   phase 1 (warp-cooperative, one query at a time): exact 5-NN in the 27-cell neighbourhood. Lanes 0..26 fetch the 27
-//     cell ranges; the nine x-rows are contiguous runs of the cell-sorted map, flattened into one candidate list that
-//     the 32 lanes read coalesced (float4 per lane, FP64 metric). Every lane keeps a sorted private top-5; five rounds
-//     of hardware warp-min (redux.sync on the FP64 bit pattern, then on the original index: bit-exact (d2, index)
-//     tie-break) merge them. Lane t keeps the five winners of query t.
+// LOAM scan-to-map: one fused kernel per Gauss-Newton iteration. A warp owns a tile of up to 32 query points.
+//   phase 1: exact 5-NN on a uniform grid whose cells are HALF the gate radius wide (gate: 5th neighbour closer than 1 m,
+//     LoamRegister.cpp:59). LPQ lanes (1, 2, 4 or 8, picked from the problem size) co-operate on one query: the 3x3 x-rows
+//     of the 27-cell ring are contiguous runs of the cell-sorted map (two loads of the dense `start` table per row), the
+//     rows are dealt out to the lanes, every lane keeps a sorted private top-5 (FP64 metric on FP32 coordinates, bit
+//     pattern compare), five rounds of hardware redux.sync min over (d2 bits, original index) merge them: bit-exact
+//     (d2, index) tie-break. If the 5th distance is not provably inside the ring (d < (1 + margin) cells) the 5x5x5 ring is
+//     searched instead; it covers the whole gate radius, so every ACCEPTED query has its exact 5-NN.
 //   phase 2 (one query per lane): gate, 5x3 column-pivoted QR plane fit, validity / weight gates, residual + SE(3)
 //     Jacobian in FP64; the 21 + 6 + 1 normal-equation terms accumulate per thread in shared memory.
 //   epilogue: fixed-order block + last-block FP64 reduction, 6x6 LDLT solve, convergence test and exp-map pose update
@@ -13,33 +15,44 @@
 #include "dev_linalg.cuh"
 #include <cfloat>
 #include <algorithm>
+#include <cstdlib>
 
 namespace pcr {
 
 constexpr int kLoamBlock = 256;
 constexpr int kLoamWarps = kLoamBlock / 32;
-constexpr int kNV = 29;  // 21 upper JtJ + 6 JtE + count + candidates examined
+constexpr int kNV = 30;  // 21 upper JtJ + 6 JtE + count + candidates examined + x-rows looked up
 constexpr size_t kLoamDynSmem = size_t(kNV) * kLoamBlock * sizeof(double);
 
 using GridView = CellGridView;
 
 struct Cand {  // one entry of a lane's private top-5
-  unsigned hi, lo;  // bit pattern of the (non-negative) FP64 squared distance: unsigned order == numeric order
-  int idx;          // original map index (tie-break)
-  int j;            // position in the cell-sorted array (to re-fetch the coordinates)
+  unsigned long long key;  // bit pattern of the (non-negative) FP64 squared distance: unsigned order == numeric order
+  int idx;                 // original map index (tie-break)
+  int j;                   // position in the cell-sorted array (to re-fetch the coordinates)
 };
-__device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) {
-  return a.hi < b.hi || (a.hi == b.hi && (a.lo < b.lo || (a.lo == b.lo && a.idx < b.idx)));
+__device__ __forceinline__ bool cand_less(const Cand& a, const Cand& b) { return a.key < b.key || (a.key == b.key && a.idx < b.idx); }
+__device__ __forceinline__ Cand cand_sel(bool p, const Cand& a, const Cand& b) {
+  Cand r;
+  r.key = p ? a.key : b.key; r.idx = p ? a.idx : b.idx; r.j = p ? a.j : b.j;
+  return r;
 }
 
-template <bool DEBUG>
+// (dy, dz) of the x-rows of the 5x5 neighbourhood, nearest first: centre, 4 faces, 4 corners (ring 1), then the 16 rows of
+// ring 2. With R rings the first (2R+1)^2 entries are used.
+__constant__ signed char c_row_dy[25] = {0, 1, -1, 0, 0, 1, 1, -1, -1, 2, -2, 0, 0, 2, 2, -2, -2, 1, -1, 1, -1, 2, 2, -2, -2};
+__constant__ signed char c_row_dz[25] = {0, 0, 0, 1, -1, 1, -1, 1, -1, 0, 0, 2, -2, 1, -1, 1, -1, 2, 2, -2, -2, 2, -2, 2, -2};
+
+template <int LPQ, bool DEBUG>
 __global__ void __launch_bounds__(kLoamBlock, 2)
 loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, GridView grid, LoamParams prm,
                  LoamState* __restrict__ states, double* __restrict__ partials, int max_blocks,
-                 pcr_loam_iter_log* __restrict__ logs, int apply_update, int tile, int32_t* __restrict__ dbg_knn,
-                 int32_t* __restrict__ dbg_status) {
-  // `tile` (power of two <= 32) = queries a warp owns per pass: 32 for throughput on large batches, smaller when there
+                 pcr_loam_iter_log* __restrict__ logs, int apply_update, int tile, double slack, int max_ring,
+                 int32_t* __restrict__ dbg_knn, int32_t* __restrict__ dbg_status) {
+  // LPQ = lanes co-operating on one query, G = 32 / LPQ queries searched concurrently by a warp.
+  // `tile` (multiple of G, <= 32) = queries a warp owns per pass: 32 for throughput on large batches, smaller when there
   // are too few queries to fill the machine (a single scan), trading phase-2 lane utilisation for shorter latency chains.
+  constexpr int G = 32 / LPQ;
   const int scan = blockIdx.y;
   const uint32_t begin = offs[scan], end = offs[scan + 1];
   const uint32_t ns = end - begin;
@@ -60,9 +73,12 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane % LPQ, gi = lane / LPQ;  // lane within its group, group within the warp
   const GridSpec& g = grid.g;
   double* acc = sacc + threadIdx.x;
   constexpr unsigned FULL = 0xffffffffu;
+  const unsigned gmask = LPQ == 32 ? FULL : (((1u << LPQ) - 1u) << (gi * LPQ));
+  const double leaf = double(g.leaf[0]);
 
   for (uint32_t tile0 = begin + (blockIdx.x * kLoamWarps + warp) * uint32_t(tile); tile0 < end; tile0 += uint32_t(nb) * per_block) {
     // ---- my own query (lane-private)
@@ -86,80 +102,138 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
 #pragma unroll
       for (int a = 0; a < 3; a++) {
         const float fc = __fsub_rn(floorf(__fmul_rn(pmf[a], g.inv_leaf[a])), float(g.min_b[a]));
-        if (!(fc >= -1.f && fc <= float(g.div_b[a]))) near = false;
-        c[a] = near ? int(fc) : 0;
+        if (!(fc >= float(-max_ring) && fc <= float(g.div_b[a] - 1 + max_ring))) near = false;  // the rings would not touch the grid
       }
     }
     int wj[5] = {-1, -1, -1, -1, -1};  // cell-sorted positions of my query's five nearest neighbours
-    int my_ncand = 0;
+    int my_ncand = 0, my_nrows = 0;
 
-    // ---- phase 1: the warp searches the tile's queries one after the other
+    // ---- phase 1: G queries of the tile are searched per round, LPQ lanes each
     const unsigned todo = __ballot_sync(FULL, have && near);
-    for (unsigned rem = todo; rem; rem &= rem - 1) {
-      const int t = __ffs(rem) - 1;
-      const double q0 = double(__shfl_sync(FULL, pmf[0], t)), q1 = double(__shfl_sync(FULL, pmf[1], t)), q2 = double(__shfl_sync(FULL, pmf[2], t));
-      const int cx = __shfl_sync(FULL, c[0], t), cy = __shfl_sync(FULL, c[1], t), cz = __shfl_sync(FULL, c[2], t);
-      // lanes 0..26 fetch the 27 cell ranges: lane = row*3 + dx, row = (dz+1)*3 + (dy+1)
-      int lo = 0x7fffffff, hi = 0;
-      if (lane < 27) {
-        const int row = lane / 3, x = cx + lane % 3 - 1;
-        const int z = cz + row / 3 - 1, y = cy + row % 3 - 1;
-        if (x >= 0 && x < g.div_b[0] && y >= 0 && y < g.div_b[1] && z >= 0 && z < g.div_b[2]) {
-          const int2 rg = __ldg(grid.range + ((long long)x + (long long)y * g.mul[1] + (long long)z * g.mul[2]));
-          if (rg.y > rg.x) { lo = rg.x; hi = rg.y; }
-        }
-      }
-      // the three cells of a row are consecutive keys -> one contiguous run of the cell-sorted array
-      lo = min(lo, min(__shfl_down_sync(FULL, lo, 1), __shfl_down_sync(FULL, lo, 2)));
-      hi = max(hi, max(__shfl_down_sync(FULL, hi, 1), __shfl_down_sync(FULL, hi, 2)));
-      int rlo[9], pre[10];
-      pre[0] = 0;
+    const int rounds = (tile + G - 1) / G;
+    for (int r = 0; r < rounds; r++) {
+      const unsigned round_bits = (G == 32 ? todo : ((todo >> (r * G)) & ((1u << G) - 1u)));
+      if (round_bits == 0) continue;  // warp-uniform
+      const int t = r * G + gi;        // the query (lane of the tile) my group works on
+      const float qf0 = __shfl_sync(FULL, pmf[0], t), qf1 = __shfl_sync(FULL, pmf[1], t), qf2 = __shfl_sync(FULL, pmf[2], t);
+      const double q0 = double(qf0), q1 = double(qf1), q2 = double(qf2);
+      const bool act = (todo >> t) & 1u;
+      int jw[5] = {-1, -1, -1, -1, -1};
+      int ncand = 0, nrows = 0;
+      if (act) {  // group-uniform
+        // cell and in-cell position of the query (cells; same float key math as the build)
+        const float sx = __fmul_rn(qf0, g.inv_leaf[0]), sy = __fmul_rn(qf1, g.inv_leaf[1]), sz = __fmul_rn(qf2, g.inv_leaf[2]);
+        const float flx = floorf(sx), fly = floorf(sy), flz = floorf(sz);
+        const int cx = int(__fsub_rn(flx, float(g.min_b[0]))), cy = int(__fsub_rn(fly, float(g.min_b[1]))), cz = int(__fsub_rn(flz, float(g.min_b[2])));
+        const float fx = sx - flx, fy = sy - fly, fz = sz - flz;
+        const float h2 = float(leaf * leaf) * 0.99999f;
+        const float slk = float(slack);
+        // private sorted top-5
+        Cand best[5];
 #pragma unroll
-      for (int row = 0; row < 9; row++) {
-        const int l = __shfl_sync(FULL, lo, row * 3), h = __shfl_sync(FULL, hi, row * 3);
-        rlo[row] = l;
-        pre[row + 1] = pre[row] + max(h - l, 0);
-      }
-      const int total = pre[9];
-      if (lane == t) my_ncand = total;
-      // private sorted top-5
-      Cand best[5];
-#pragma unroll
-      for (int k = 0; k < 5; k++) { best[k].hi = 0xffffffffu; best[k].lo = 0xffffffffu; best[k].idx = 0x7fffffff; best[k].j = -1; }
-      for (int f = lane; f < total; f += 32) {
-        int j = rlo[0] + f;
-#pragma unroll
-        for (int row = 1; row < 9; row++) j = (f >= pre[row]) ? rlo[row] + (f - pre[row]) : j;
-        const float4 m = __ldg(grid.pts + j);
-        const double dx = q0 - double(m.x), dyy = q1 - double(m.y), dzz = q2 - double(m.z);
-        const double d2 = dx * dx + dyy * dyy + dzz * dzz;  // exact products; fused or not gives the same bits
-        Cand cnd;
-        cnd.hi = unsigned(__double2hiint(d2)); cnd.lo = unsigned(__double2loint(d2)); cnd.idx = __float_as_int(m.w); cnd.j = j;
-        if (cand_less(cnd, best[4])) {
-          best[4] = cnd;
-#pragma unroll
-          for (int k = 4; k > 0; k--) {
-            if (cand_less(best[k], best[k - 1])) { Cand tmp = best[k]; best[k] = best[k - 1]; best[k - 1] = tmp; }
+        for (int k = 0; k < 5; k++) { best[k].key = ~0ull; best[k].idx = 0x7fffffff; best[k].j = -1; }
+        // FP32 pre-filter. thr is a float upper bound (1e-5 relative head-room; the float evaluation is good to 3e-7) of
+        // min(gate, current 5th-best exact distance): a candidate that the exact FP64 (d2, index) compare would accept AND
+        // that can matter for an accepted query (5th neighbour closer than the gate, LoamRegister.cpp:59) is never dropped.
+        // Rows and x-cells are pruned against the same bound, so only the cells that can still hold a top-5 point are read.
+        float thr = float(prm.max_knn_d2) * 1.00001f;
+        auto exact = [&](float mx, float my, float mz, int midx, int j) {
+          const double dx = q0 - double(mx), dyy = q1 - double(my), dzz = q2 - double(mz);
+          const double d2 = dx * dx + dyy * dyy + dzz * dzz;  // exact products; fused or not gives the same bits
+          Cand cnd;
+          cnd.key = (unsigned long long)__double_as_longlong(d2); cnd.idx = midx; cnd.j = j;
+          if (cand_less(cnd, best[4])) {  // branch-free sorted insertion
+            const bool l0 = cand_less(best[0], cnd), l1 = cand_less(best[1], cnd), l2 = cand_less(best[2], cnd), l3 = cand_less(best[3], cnd);
+            best[4] = cand_sel(l3, cnd, best[3]);
+            best[3] = cand_sel(l3, best[3], cand_sel(l2, cnd, best[2]));
+            best[2] = cand_sel(l2, best[2], cand_sel(l1, cnd, best[1]));
+            best[1] = cand_sel(l1, best[1], cand_sel(l0, cnd, best[0]));
+            best[0] = cand_sel(l0, best[0], cnd);
+            if (best[4].j >= 0) thr = fminf(thr, __double2float_ru(__longlong_as_double((long long)best[4].key)) * 1.00001f);
+          }
+        };
+        auto d2f_of = [&](const float4& m) {
+          const float ax = qf0 - m.x, ay = qf1 - m.y, az = qf2 - m.z;
+          return fmaf(az, az, fmaf(ay, ay, ax * ax));
+        };
+        // distance (cells) from the query to the cells at x-offset +-2: below it one x-cell either side is enough
+        const float ax2 = fmaxf(1.f + fminf(fx, 1.f - fx) - slk, 0.f);
+        const int NR = (2 * max_ring + 1) * (2 * max_ring + 1);
+        // every row of ring 2 is at least this far (squared): once the bound is below it the second ring is skipped as a whole
+        const float ring2 = fmaxf(1.f + fminf(fminf(fy, 1.f - fy), fminf(fz, 1.f - fz)) - slk, 0.f);
+        const float ring2_min2 = ring2 * ring2 * h2;
+#pragma unroll 1
+        for (int k = gl; k < NR; k += LPQ) {
+          if (k >= 9 && thr < ring2_min2) break;
+          const int dy = c_row_dy[k], dz = c_row_dz[k];
+          // squared distance from the query to the row's (y, z) slab, shrunk by the cell-assignment slack
+          const float ay = fmaxf((dy == 0 ? 0.f : (dy > 0 ? float(dy) - fy : fy + float(-dy - 1))) - slk, 0.f);
+          const float az = fmaxf((dz == 0 ? 0.f : (dz > 0 ? float(dz) - fz : fz + float(-dz - 1))) - slk, 0.f);
+          const float row2 = (ay * ay + az * az) * h2;
+          if (row2 > thr) continue;  // every point of this row is farther than the current bound
+          const int y = cy + dy, z = cz + dz;
+          if (y < 0 || y >= g.div_b[1] || z < 0 || z >= g.div_b[2]) continue;
+          const int rx = (max_ring > 1 && thr < row2 + ax2 * ax2 * h2) ? 1 : max_ring;
+          const int x0 = max(cx - rx, 0), x1 = min(cx + rx, g.div_b[0] - 1);
+          if (x0 > x1) continue;
+          // a row is ONE contiguous run of the cell-sorted map: two loads of the dense start table
+          const long long key0 = (long long)x0 + (long long)y * g.mul[1] + (long long)z * g.mul[2];
+          const int lo = __ldg(grid.start + key0);
+          const int hi = __ldg(grid.start + key0 + (x1 - x0) + 1);
+          ncand += hi - lo;
+          nrows++;
+#pragma unroll 1
+          for (int j = lo; j < hi; j += 4) {  // four independent float4 loads in flight
+            const int rem = hi - j;
+            const float4 none = make_float4(0.f, 0.f, 0.f, 0.f);  // masked out below
+            const float4 m0 = __ldg(grid.pts + j);
+            const float4 m1 = rem > 1 ? __ldg(grid.pts + j + 1) : none;
+            const float4 m2 = rem > 2 ? __ldg(grid.pts + j + 2) : none;
+            const float4 m3 = rem > 3 ? __ldg(grid.pts + j + 3) : none;
+            const float f0 = d2f_of(m0), f1 = d2f_of(m1), f2 = d2f_of(m2), f3 = d2f_of(m3);
+            unsigned pass = (f0 <= thr ? 1u : 0u) | (rem > 1 && f1 <= thr ? 2u : 0u) | (rem > 2 && f2 <= thr ? 4u : 0u) |
+                            (rem > 3 && f3 <= thr ? 8u : 0u);
+            while (pass) {  // rare once five candidates are in
+              const int u = __ffs(pass) - 1;
+              pass &= pass - 1;
+              const float4 m = u == 0 ? m0 : (u == 1 ? m1 : (u == 2 ? m2 : m3));
+              exact(m.x, m.y, m.z, __float_as_int(m.w), j + u);
+            }
           }
         }
-      }
-      // merge: five rounds of hardware warp-min over the lanes' heads, (d2 bits, original index) lexicographic
+        // merge: five rounds of hardware min over the group's heads, (d2 bits, original index) lexicographic
+        if (LPQ == 1) {
 #pragma unroll
-      for (int r = 0; r < 5; r++) {
-        const unsigned mh = __reduce_min_sync(FULL, best[0].hi);
-        const bool e1 = best[0].hi == mh;
-        const unsigned ml = __reduce_min_sync(FULL, e1 ? best[0].lo : 0xffffffffu);
-        const bool e2 = e1 && best[0].lo == ml;
-        const unsigned mi = __reduce_min_sync(FULL, e2 ? unsigned(best[0].idx) : 0x7fffffffu);
-        const bool mine = e2 && unsigned(best[0].idx) == mi && best[0].j >= 0;
-        const int jw = int(__reduce_min_sync(FULL, mine ? unsigned(best[0].j) : 0xffffffffu));  // -1 when fewer than r+1 exist
-        if (lane == t) wj[r] = jw;
-        if (mine) {
+          for (int q = 0; q < 5; q++) jw[q] = best[q].j;
+        } else {
 #pragma unroll
-          for (int k = 0; k < 4; k++) best[k] = best[k + 1];
-          best[4].hi = 0xffffffffu; best[4].lo = 0xffffffffu; best[4].idx = 0x7fffffff; best[4].j = -1;
+          for (int q = 0; q < 5; q++) {
+            const unsigned bh = unsigned(best[0].key >> 32), bl = unsigned(best[0].key);
+            const unsigned mh = __reduce_min_sync(gmask, bh);
+            const bool e1 = bh == mh;
+            const unsigned ml = __reduce_min_sync(gmask, e1 ? bl : 0xffffffffu);
+            const bool e2 = e1 && bl == ml;
+            const unsigned mi = __reduce_min_sync(gmask, e2 ? unsigned(best[0].idx) : 0x7fffffffu);
+            const bool mine = e2 && unsigned(best[0].idx) == mi && best[0].j >= 0;
+            jw[q] = int(__reduce_min_sync(gmask, mine ? unsigned(best[0].j) : 0xffffffffu));  // -1 when fewer than q+1 exist
+            if (mine) {
+#pragma unroll
+              for (int k = 0; k < 4; k++) best[k] = best[k + 1];
+              best[4].key = ~0ull; best[4].idx = 0x7fffffff; best[4].j = -1;
+            }
+          }
+          ncand = int(__reduce_add_sync(gmask, unsigned(ncand)));  // candidates examined / rows looked up by the group
+          nrows = int(__reduce_add_sync(gmask, unsigned(nrows)));
         }
       }
+      // hand the winners to the lane that owns the query
+#pragma unroll
+      for (int q = 0; q < 5; q++) {
+        const int v = __shfl_sync(FULL, jw[q], (lane % G) * LPQ);
+        if (lane / G == r) wj[q] = v;
+      }
+      const int nc = __shfl_sync(FULL, ncand, (lane % G) * LPQ), nr = __shfl_sync(FULL, nrows, (lane % G) * LPQ);
+      if (lane / G == r) { my_ncand = nc; my_nrows = nr; }
     }
 
     // ---- phase 2: one query per lane
@@ -226,6 +300,7 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
         }
       }
       acc[28 * kLoamBlock] += double(my_ncand);
+      acc[29 * kLoamBlock] += double(my_nrows);
       if (DEBUG && dbg_status) dbg_status[i] = status;
     }
   }
@@ -331,6 +406,7 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     st->iters = it + 1;
     st->n_last = int(n);
     st->cand_total += (long long)(stot[28] + 0.5);
+    st->rows_total += (long long)(stot[29] + 0.5);
     st->pt_evals += (long long)ns;
     if (conv) { st->converged = 1; if (lg) lg->converged = 1; }
     if (done || !apply_update) st->done = 1;
@@ -348,15 +424,71 @@ __global__ void loam_finalize_kernel(LoamState* states, int n_scans) {
   for (int q = 0; q < 16; q++) states[s].T[q] = T[q];
 }
 
+template <int LPQ, bool DEBUG>
+static void opt_in_one() {
+  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<LPQ, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
+}
 static void loam_opt_in_smem() {
   static bool done_dev[64] = {false};
   int dev = 0;
   PCR_CUDA_CHECK(cudaGetDevice(&dev));
   bool& done = done_dev[dev & 63];
   if (done) return;
-  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
-  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
+  opt_in_one<1, false>(); opt_in_one<2, false>(); opt_in_one<4, false>(); opt_in_one<8, false>();
+  opt_in_one<1, true>(); opt_in_one<2, true>(); opt_in_one<4, true>(); opt_in_one<8, true>();
   done = true;
+}
+
+// lanes per query and queries per warp pass from the problem size: one lane per query once the queries alone fill the
+// machine (batches), up to 8 lanes per query and short tiles for a single scan (latency)
+static int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+static void pick_shape(size_t total_q, int& lpq, int& tile) {
+  const size_t lanes_wave = size_t(kNumSMs) * 2 * kLoamBlock;
+  lpq = 1;
+  while (lpq < 8 && total_q * size_t(lpq) < 2 * lanes_wave) lpq <<= 1;
+  const int forced = env_int("PCR_LOAM_LPQ", 0);  // tuning knob (1, 2, 4, 8)
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) lpq = forced;
+  const int G = 32 / lpq;
+  tile = 32;
+  while (tile > G && (total_q / size_t(tile)) * 32 < lanes_wave) tile >>= 1;
+  const int ftile = env_int("PCR_LOAM_TILE", 0);
+  if (ftile >= G && ftile <= 32 && (ftile & (ftile - 1)) == 0) tile = ftile;
+}
+
+template <bool DEBUG>
+static void launch_iter(int lpq, dim3 grid, cudaStream_t s, const float4* src, const uint32_t* offs, const GridView& view, const LoamParams& prm,
+                        LoamState* states, double* partials, int max_blocks, pcr_loam_iter_log* logs, int apply, int tile, double slack,
+                        int max_ring, int32_t* dbg_knn, int32_t* dbg_status) {
+#define PCR_LOAM_LAUNCH(L)                                                                                                          \
+  loam_iter_kernel<L, DEBUG><<<grid, kLoamBlock, kLoamDynSmem, s>>>(src, offs, view, prm, states, partials, max_blocks, logs, apply, tile, \
+                                                                    slack, max_ring, dbg_knn, dbg_status)
+  switch (lpq) {
+    case 1: PCR_LOAM_LAUNCH(1); break;
+    case 2: PCR_LOAM_LAUNCH(2); break;
+    case 4: PCR_LOAM_LAUNCH(4); break;
+    default: PCR_LOAM_LAUNCH(8); break;
+  }
+#undef PCR_LOAM_LAUNCH
+}
+
+int loam_build_target(const float4* pts, size_t n, double max_knn_d2, CellGrid& grid, KeySort& ks, BBoxWork& bw, cudaStream_t s) {
+  // gate radius r = sqrt(max_knn_d2) (LoamRegister.cpp:59 compares the SQUARED 5th distance with 1.0). With cells of
+  // r / (R - 4 * slack) the R-ring cube around a query's cell contains every map point closer than r even after the float
+  // rounding of the cell assignment (slack <= 2e-3 cells below ~2 km, grid_slack_cells()).
+  const float r = std::sqrt(float(max_knn_d2));
+  int rc = build_cell_grid(pts, n, r / (1.0f - 0.008f), grid, ks, bw, s, true);
+  grid.max_ring = 1;
+  if (rc || n == 0) return rc;
+  const double per_cell = double(n) / double(std::max<size_t>(grid.occupied, 1));
+  if (per_cell > double(env_int("PCR_LOAM_FINE_ABOVE", 6))) {  // dense map: most 5-NN balls fit inside the 27 half-width cells, 8x fewer candidates per query
+    CellGrid& fine = grid;
+    rc = build_cell_grid(pts, n, r / (2.0f - 0.008f), fine, ks, bw, s, true);
+    grid.max_ring = 2;
+  }
+  return rc;
 }
 
 LoamDriver::~LoamDriver() {
@@ -368,7 +500,7 @@ static GridView make_view(const CellGrid& grid) { return view_of(grid); }
 
 int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, const CellGrid& grid, const LoamParams& prm,
                       double* T, int32_t* converged, int32_t* iters_out, int64_t* n_last_out, bool profile, cudaStream_t s) {
-  launches = 0; cand_total = 0; pt_evals = 0; hot_ms = 0.f; hot_launches = 0;
+  launches = 0; cand_total = 0; rows_total = 0; pt_evals = 0; hot_ms = 0.f; hot_launches = 0;
   if (n_scans == 0) return 0;
   loam_opt_in_smem();
   LoamState* hs = h_states.ensure(n_scans);
@@ -383,11 +515,12 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
   }
   // a warp owns 32 queries per pass; at most one resident wave of blocks (2 x 256 threads per SM) shared by the scans
   const size_t total_q = offs[n_scans] - offs[0];
-  int tile = 32;
-  while (tile > 1 && total_q / size_t(tile) < size_t(kNumSMs) * 16) tile >>= 1;
+  int tile = 32, lpq = 1;
+  pick_shape(total_q, lpq, tile);
+  const double slack = grid_slack_cells(grid.g);
   const size_t per_block = size_t(kLoamWarps) * tile;
   int max_blocks = int((max_pts + per_block - 1) / per_block);
-  max_blocks = std::max(1, std::min(max_blocks, std::max(2, int((kNumSMs * 2 + n_scans - 1) / n_scans))));
+  max_blocks = std::max(1, std::min(max_blocks, int(size_t(kNumSMs) * 2 / n_scans)));  // all scans' blocks resident in one wave
   states.ensure(n_scans);
   offsets.ensure(n_scans + 1);
   partials.ensure(n_scans * size_t(max_blocks) * kNV);
@@ -400,10 +533,9 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     if (!ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
     PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
   }
-  if (grid.built && max_pts > 0) {
+  if (grid.built && grid.has_start && max_pts > 0) {
     for (int it = 0; it < prm.max_iters; it++) {
-      loam_iter_kernel<false><<<gridDim, kLoamBlock, kLoamDynSmem, s>>>(src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 1,
-                                                             tile, nullptr, nullptr);
+      launch_iter<false>(lpq, gridDim, s, src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 1, tile, slack, grid.max_ring, nullptr, nullptr);
       launches++;
       hot_launches++;
     }
@@ -424,6 +556,7 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     if (iters_out) iters_out[i] = hs[i].iters;
     if (n_last_out) n_last_out[i] = hs[i].n_last;
     cand_total += hs[i].cand_total;
+    rows_total += hs[i].rows_total;
     pt_evals += hs[i].pt_evals;
   }
   last_log_count = hs[0].iters;
@@ -438,8 +571,9 @@ int LoamDriver::linearize(const float4* src, size_t ns, const CellGrid& grid, co
   ho[0] = 0; ho[1] = uint32_t(ns);
   memset(hs, 0, sizeof(LoamState));
   for (int q = 0; q < 16; q++) hs->T[q] = T[q];
-  int tile = 32;
-  while (tile > 1 && ns / size_t(tile) < size_t(kNumSMs) * 16) tile >>= 1;
+  int tile = 32, lpq = 1;
+  pick_shape(ns, lpq, tile);
+  const double slack = grid_slack_cells(grid.g);
   const size_t per_block = size_t(kLoamWarps) * tile;
   int max_blocks = int((ns + per_block - 1) / per_block);
   max_blocks = std::max(1, std::min(max_blocks, kNumSMs * 2));
@@ -450,10 +584,10 @@ int LoamDriver::linearize(const float4* src, size_t ns, const CellGrid& grid, co
   PCR_CUDA_CHECK(cudaMemcpyAsync(states.p, hs, sizeof(LoamState), cudaMemcpyHostToDevice, s));
   PCR_CUDA_CHECK(cudaMemcpyAsync(offsets.p, ho, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   PCR_CUDA_CHECK(cudaMemsetAsync(logs.p, 0, sizeof(pcr_loam_iter_log), s));
-  if (ns > 0 && grid.built) {
+  if (ns > 0 && grid.built && grid.has_start) {
     GridView view = make_view(grid);
-    loam_iter_kernel<true><<<dim3(max_blocks, 1), kLoamBlock, kLoamDynSmem, s>>>(src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p,
-                                                                     0, tile, dbg_knn.p, dbg_status.p);
+    launch_iter<true>(lpq, dim3(max_blocks, 1), s, src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 0, tile, slack,
+                      grid.max_ring, dbg_knn.p, dbg_status.p);
   }
   pcr_loam_iter_log* hl = h_logs.ensure(size_t(prm.max_iters));
   PCR_CUDA_CHECK(cudaMemcpyAsync(hl, logs.p, sizeof(pcr_loam_iter_log), cudaMemcpyDeviceToHost, s));

@@ -16,9 +16,15 @@ struct LoamState {  // one per scan, device resident
   int done, converged, iters, n_last;
   unsigned ticket;
   int pad;
-  long long cand_total;  // map points examined by the 27-cell gather, summed over iterations
+  long long cand_total;  // map points examined by the neighbour search, summed over iterations
+  long long rows_total;  // x-rows of cells looked up in the start table (two 4-byte entries each), summed over iterations
   long long pt_evals;    // source points linearised, summed over iterations
 };
+
+// Target index of the LOAM search: uniform grid with a dense start table. Cell width = gate radius (one 27-cell ring
+// covers the gate ball) for sparse maps, half of it (second ring on demand) when the map is dense — picked from the mean
+// number of points per occupied cell. Returns a PCR error code.
+int loam_build_target(const float4* pts, size_t n, double max_knn_d2, CellGrid& grid, KeySort& ks, BBoxWork& bw, cudaStream_t s);
 
 struct LoamDriver {
   DevBuf<LoamState> states;
@@ -32,6 +38,7 @@ struct LoamDriver {
   int last_log_count = 0;
   long long launches = 0;
   long long cand_total = 0;
+  long long rows_total = 0;
   long long pt_evals = 0;
   float hot_ms = 0.f;
   int hot_launches = 0;

@@ -93,7 +93,11 @@ ndt_leaf_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ key
   recs[l] = rec;
   okeys[l] = int32_t(key);
   onpts[l] = npts;
+  // dense cell -> leaf table: l for usable leaves; -2 - l for leaves that entered the centroid cloud (n >= min_points) but
+  // were rejected by the eigenvalue / inverse checks — only the KDTREE radius search still sees those (its centroid
+  // kd-tree is built before the checks, voxel_grid_covariance_omp_impl.hpp:297-326 vs :337-364)
   if (npts >= min_points) table[key] = int32_t(l);
+  else if (in_cloud) table[key] = -2 - int32_t(l);
   const float fn = float(n);
   centroids[l] = make_float4(__fdiv_rn(fx, fn), __fdiv_rn(fy, fn), __fdiv_rn(fz, fn), in_cloud ? 1.f : 0.f);
 }
@@ -151,8 +155,10 @@ struct NdtTargetView {
   const double* mean;
   const double* icov;
   const int32_t* table;
+  const float4* centroids;
   GridSpec g;
   float d2f;
+  float radius2;
   double d1, d2;
 };
 
@@ -161,10 +167,13 @@ struct NbTraits;
 template <> struct NbTraits<PCR_NDT_DIRECT7> { static constexpr int N = 7; };
 template <> struct NbTraits<PCR_NDT_DIRECT1> { static constexpr int N = 1; };
 template <> struct NbTraits<PCR_NDT_DIRECT26> { static constexpr int N = 26; };
+template <> struct NbTraits<PCR_NDT_KDTREE> { static constexpr int N = 27; };
 
 template <int SEARCH>
 __device__ __forceinline__ void nb_offset(int ni, int& ox, int& oy, int& oz) {
-  if (SEARCH == PCR_NDT_DIRECT26) {  // the 26 non-centre cells, x-major (pcl::getAllNeighborCellIndices)
+  if (SEARCH == PCR_NDT_KDTREE) {  // all 27 cells: a centroid within `resolution` of the point lies in one of them
+    ox = ni / 9 - 1; oy = (ni / 3) % 3 - 1; oz = ni % 3 - 1;
+  } else if (SEARCH == PCR_NDT_DIRECT26) {  // the 26 non-centre cells, x-major (pcl::getAllNeighborCellIndices)
     const int k = ni >= 13 ? ni + 1 : ni;
     ox = k / 9 - 1; oy = (k / 3) % 3 - 1; oz = k % 3 - 1;
   } else {  // centre, +x, -x, +y, -y, +z, -z (voxel_grid_covariance_omp_impl.hpp:423-430)
@@ -347,6 +356,22 @@ ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ off
                             (long long)(cz - g.min_b[2]) * g.mul[2];
       ids[ni] = inb ? __ldg(tgt.table + key) : -1;
     }
+    if (SEARCH == PCR_NDT_KDTREE) {
+      // N6: VoxelGridCovariance::radiusSearch — leaves of the centroid cloud whose float centroid is within `resolution`
+      // of the point: FLANN L2_Simple<float> metric (x->y->z float accumulate), strict d2 < r^2
+#pragma unroll
+      for (int ni = 0; ni < NNB; ni++) {
+        int id = ids[ni];
+        if (id <= -2) id = -2 - id;
+        if (id >= 0) {
+          const float4 c = __ldg(tgt.centroids + id);
+          const float dx = __fsub_rn(pt[0], c.x), dy = __fsub_rn(pt[1], c.y), dz = __fsub_rn(pt[2], c.z);
+          const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          if (!(d2 < tgt.radius2)) id = -1;
+        }
+        ids[ni] = id;
+      }
+    }
     unsigned mask = 0;
 #pragma unroll
     for (int ni = 0; ni < NNB; ni++) mask |= (ids[ni] >= 0) ? (1u << ni) : 0u;
@@ -468,7 +493,9 @@ void NdtDriver::evaluate(const float4* src, const uint32_t* d_offs, size_t max_p
     for (int q = 0; q < count; q++) point_evals += h_offsets.p[h_params.p[q].scan + 1] - h_offsets.p[h_params.p[q].scan];
     NdtTargetView v;
     v.recs = tgt.recs.p; v.mean = tgt.mean.p; v.icov = tgt.icov.p; v.table = tgt.table.p; v.g = tgt.g;
+    v.centroids = tgt.centroids.p;
     v.d1 = tgt.d1; v.d2 = tgt.d2; v.d2f = float(tgt.d2);
+    v.radius2 = float(double(tgt.resolution) * double(tgt.resolution));  // KdTreeFLANN::radiusSearch: (float)(radius * radius)
     if (profile) {
       if (!ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
       PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
@@ -480,6 +507,7 @@ void NdtDriver::evaluate(const float4* src, const uint32_t* d_offs, size_t max_p
       switch (search) {
         case PCR_NDT_DIRECT1: launch_eval<PCR_NDT_DIRECT1>(part == 1, grid, s, src, d_offs, v, d_params.p, dev_results, partials.p, tickets.p, max_blocks, base); break;
         case PCR_NDT_DIRECT26: launch_eval<PCR_NDT_DIRECT26>(part == 1, grid, s, src, d_offs, v, d_params.p, dev_results, partials.p, tickets.p, max_blocks, base); break;
+        case PCR_NDT_KDTREE: launch_eval<PCR_NDT_KDTREE>(part == 1, grid, s, src, d_offs, v, d_params.p, dev_results, partials.p, tickets.p, max_blocks, base); break;
         default: launch_eval<PCR_NDT_DIRECT7>(part == 1, grid, s, src, d_offs, v, d_params.p, dev_results, partials.p, tickets.p, max_blocks, base); break;
       }
       launches++;
@@ -697,7 +725,6 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
                      int32_t* converged, int32_t* iters, double* trans_prob, bool profile, cudaStream_t s) {
   launches = 0; hot_ms = 0.f; hot_launches = 0; total_evals = 0; total_hess = 0; total_pairs = 0; point_evals = 0;
   if (n_scans == 0) return 0;
-  if (prm.ndt_search == PCR_NDT_KDTREE) return PCR_ERR_UNSUPPORTED;
   uint32_t* ho = h_offsets.ensure(n_scans + 1);
   size_t max_pts = 0;
   for (size_t i = 0; i <= n_scans; i++) ho[i] = uint32_t(offs[i] - offs[0]);

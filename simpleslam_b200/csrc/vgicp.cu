@@ -146,12 +146,6 @@ __device__ __forceinline__ WarpKnn knn_warp_f32(const CellGridView& grid, float 
   return st;
 }
 
-static double grid_slack_cells(const GridSpec& g) {
-  // float rounding of x*inv_leaf moves a point by at most ~|cell index| * 2^-23 cells across a cell face
-  double m = 1.0;
-  for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs(double(g.min_b[a])), std::fabs(double(g.max_b[a]))));
-  return std::max(1e-3, m * 4.8e-7);
-}
 
 // ================================================================================================================
 // V1. FastGICP::calculate_covariances (fast_gicp_impl.hpp:241-298): k-NN (self included), cov = N N^T / k of the

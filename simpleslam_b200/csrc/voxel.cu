@@ -5,6 +5,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/device/device_scan.cuh>
+#include <thrust/iterator/reverse_iterator.h>
 #include <cmath>
 #include <limits>
 
@@ -242,19 +244,71 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float4* __restr
   if (i == n - 1 || keys[i + 1] != k) range[k].y = int(i + 1);
 }
 
-int build_cell_grid(const float4* pts, size_t n, float cell, CellGrid& grid, KeySort& ks, BBoxWork& bw, cudaStream_t s) {
+// start-table variant: scatter only (cell-sorted points) + heads of the key runs
+__global__ void __launch_bounds__(256) grid_scatter_start_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ keys,
+                                                                 const uint32_t* __restrict__ vals, size_t n, long long ncell,
+                                                                 float4* __restrict__ sorted, int32_t* __restrict__ start,
+                                                                 unsigned* __restrict__ occupied) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  bool head = false;
+  if (i < n) {
+    uint32_t k = keys[i], v = vals[i];
+    float4 p = __ldg(pts + v);
+    p.w = __int_as_float(int(v));
+    sorted[i] = p;
+    head = i == 0 || keys[i - 1] != k;
+    if (head) start[k] = int32_t(i);
+    if (i == n - 1) start[ncell] = int32_t(n);
+  }
+  const unsigned heads = __ballot_sync(0xffffffffu, head);  // occupied-cell count, one atomic per warp
+  if ((threadIdx.x & 31) == 0 && heads) atomicAdd(occupied, unsigned(__popc(heads)));
+}
+
+struct MinOp {
+  __device__ __forceinline__ int32_t operator()(const int32_t& a, const int32_t& b) const { return a < b ? a : b; }
+};
+
+double grid_slack_cells(const GridSpec& g) {
+  double m = 1.0;
+  for (int a = 0; a < 3; a++) m = std::max(m, std::max(std::fabs(double(g.min_b[a])), std::fabs(double(g.max_b[a]))));
+  return std::max(1e-3, m * 4.8e-7);
+}
+
+int build_cell_grid(const float4* pts, size_t n, float cell, CellGrid& grid, KeySort& ks, BBoxWork& bw, cudaStream_t s, bool start_table) {
   grid.built = false;
+  grid.has_start = false;
   grid.n = n;
   if (n == 0) return 0;
   float mn[3], mx[3];
   bbox_blocking(pts, n, mn, mx, bw, s);
   bool ok = make_grid_spec(mn, mx, cell, grid.g);
-  if (!ok || grid.g.ncell > (1ll << 28)) return -5;
+  if (!ok || grid.g.ncell > (1ll << 29)) return -5;
   ks.sort(pts, n, grid.g, s);
   grid.pts.ensure(n);
-  grid.range.ensure(size_t(grid.g.ncell));
-  PCR_CUDA_CHECK(cudaMemsetAsync(grid.range.p, 0, size_t(grid.g.ncell) * sizeof(int2), s));
-  grid_scatter_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(pts, ks.keys, ks.vals, n, grid.pts.p, grid.range.p);
+  const size_t ncell = size_t(grid.g.ncell);
+  if (start_table) {
+    // heads of the key runs scattered into a table preset to INT_MAX-ish, then a reverse running minimum fills the empty
+    // cells with the start of the next occupied one
+    grid.start.ensure(ncell + 1);
+    PCR_CUDA_CHECK(cudaMemsetAsync(grid.start.p, 0x7f, (ncell + 1) * sizeof(int32_t), s));
+    unsigned* dc = ks.d_count.ensure(1);
+    unsigned* hc = ks.h_count.ensure(1);
+    PCR_CUDA_CHECK(cudaMemsetAsync(dc, 0, sizeof(unsigned), s));
+    grid_scatter_start_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(pts, ks.keys, ks.vals, n, grid.g.ncell, grid.pts.p, grid.start.p, dc);
+    PCR_CUDA_CHECK(cudaMemcpyAsync(hc, dc, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    auto rit = thrust::make_reverse_iterator(grid.start.p + ncell + 1);
+    size_t bytes = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, bytes, rit, rit, MinOp(), int(ncell + 1), s);
+    ks.tmp.ensure(bytes);
+    PCR_CUDA_CHECK(cub::DeviceScan::InclusiveScan(ks.tmp.p, bytes, rit, rit, MinOp(), int(ncell + 1), s));
+    PCR_CUDA_CHECK(cudaStreamSynchronize(s));
+    grid.occupied = *hc;
+    grid.has_start = true;
+  } else {
+    grid.range.ensure(ncell);
+    PCR_CUDA_CHECK(cudaMemsetAsync(grid.range.p, 0, ncell * sizeof(int2), s));
+    grid_scatter_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(pts, ks.keys, ks.vals, n, grid.pts.p, grid.range.p);
+  }
   grid.built = true;
   return 0;
 }

@@ -44,6 +44,11 @@ struct CellGrid {
   GridSpec g{};
   DevBuf<float4> pts;      // cell-sorted, w = original index bits
   DevBuf<int2> range;      // per cell [start, end)
+  DevBuf<int32_t> start;   // optional dense prefix table: start[k] = first sorted position whose key >= k, start[ncell] = n;
+                           // a run of consecutive cells [k0, k1] is the contiguous slice [start[k0], start[k1 + 1])
+  bool has_start = false;
+  size_t occupied = 0;     // occupied cells (start-table builds only)
+  int max_ring = 1;        // LOAM search: rings of cells (1 = 27 cells, 2 = 125 cells) needed to cover the gate radius
   size_t n = 0;
   bool built = false;
 };
@@ -51,16 +56,23 @@ struct CellGrid {
 struct CellGridView {
   const float4* pts;
   const int2* range;
+  const int32_t* start;
   GridSpec g;
 };
 inline CellGridView view_of(const CellGrid& grid) {
   CellGridView v;
   v.pts = grid.pts.p;
   v.range = grid.range.p;
+  v.start = grid.has_start ? grid.start.p : nullptr;
   v.g = grid.g;
   return v;
 }
 // Returns PCR error code (0 ok, -5 grid too large).
-int build_cell_grid(const float4* pts, size_t n, float cell, CellGrid& grid, KeySort& ks, BBoxWork& bw, cudaStream_t s);
+// start_table: build `start` (LOAM row-run lookups) instead of `range`.
+int build_cell_grid(const float4* pts, size_t n, float cell, CellGrid& grid, KeySort& ks, BBoxWork& bw, cudaStream_t s,
+                    bool start_table = false);
+// float rounding of x * inv_leaf moves a point by at most ~|cell index| * 2^-23 cells across a cell face: slack (in cells)
+// that exactness arguments about "every point outside the scanned cells is farther than ..." have to subtract
+double grid_slack_cells(const GridSpec& g);
 
 }  // namespace pcr

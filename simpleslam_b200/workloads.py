@@ -41,20 +41,20 @@ def c2_ndt(downsample, n_scans, n_map_scans=192, seed_offset=0):
                 truths=truths, guesses=guesses, raw_map_points=len(raw))
 
 
-def c1_loam(downsample, n_scans, seed_offset=0):
-    """C1: VLP-16 scan (28.8k rays, 0.5 m downsample) vs ~200k-point local submap (0.5 m downsample of 80 scans along a
-    70 m arc), LOAM; guess = truth o exp([0.3,-0.2,0.05 m; 0.5,-0.5,2 deg]-scale perturbations)."""
-    sc = synth.Scene(seed=SEED, tiles=(1, 1))
+def c1_loam(downsample, n_scans, seed_offset=0, n_map_scans=200, radius=50.0):
+    """C1: VLP-16 scan (28.8k rays, 0.5 m downsample) vs ~200k-point local submap (0.5 m downsample of 200 scans along a
+    50 m-radius loop), LOAM; guess = truth o exp([0.3,-0.2,0.05 m; 0.5,-0.5,2 deg]-scale perturbations)."""
+    sc = synth.Scene(seed=SEED, tiles=(2, 2))
     clouds, poses = [], []
-    for i in range(80):
-        T = sc.free_pose_near(60 + i * 0.9, 100 + 6 * np.sin(i * 0.08), 2.0, 0.1 * np.sin(i * 0.05))
+    for i in range(n_map_scans):
+        T = _loop_pose(sc, i, n_map_scans, 200.0, 200.0, radius)
         poses.append(T)
         clouds.append(synth.transform_cloud(T, sc.scan(T, "vlp16", seed=100 + i)))
     dst = downsample(np.concatenate(clouds), 0.5)
     rng = np.random.RandomState(23 + seed_offset)
     scans, truths, guesses = [], [], []
     for k in range(n_scans):
-        T = poses[(5 + 7 * k) % len(poses)] @ synth.se3_exp([0.4, 0.1, 0, 0, 0, 0.01])
+        T = poses[(5 + 7 * (k + 1009 * seed_offset)) % len(poses)] @ synth.se3_exp([0.4, 0.1, 0, 0, 0, 0.01])
         raw = sc.scan(T, "vlp16", seed=7000 + k + 100000 * seed_offset)
         scans.append(downsample(raw, 0.5))
         truths.append(T)
@@ -76,6 +76,43 @@ def c3_vgicp(n_pairs, seed_offset=0):
         T_true = np.linalg.inv(Ta) @ Tb
         pairs.append(dict(src=src, dst=dst, T_true=T_true, T_guess=T_true @ _perturb(rng, 0.2, 1.0)))
     return dict(name="C3 VGICP scan-to-scan: 128-beam scans (~260k pts each), res 1.0", method="vgicp", pairs=pairs)
+
+
+def _big_map(sc, extent, spacing, seed=7, strips=16):
+    """direct surface sampling of the whole world, strip-parallel (ctypes releases the GIL)"""
+    from concurrent.futures import ThreadPoolExecutor
+    edges = np.linspace(0.0, extent, strips + 1)
+    with ThreadPoolExecutor(max_workers=min(strips, 16)) as ex:
+        parts = list(ex.map(lambda k: sc.sample_map(0.0, edges[k], extent, edges[k + 1], spacing, seed=seed + k), range(strips)))
+    return np.concatenate(parts)
+
+
+def c4_batched(method, downsample, n_scans, seed_offset=0, tiles=4, spacing=0.24):
+    """C4 batched localisation (loc.cpp mode): independent scans at random poses all over a static map of ~20M points
+    (4x4 tiles of 200 m, surfaces sampled at 0.24 m then voxel-downsampled at 0.2 m). LOAM: VLP-16 scans downsampled at
+    0.5 m; NDT: raw 64-beam scans. Guess = truth o small perturbation."""
+    sc = synth.Scene(seed=SEED, tiles=(tiles, tiles))
+    extent = 200.0 * tiles
+    raw = _big_map(sc, extent, spacing)
+    dst = downsample(raw, 0.2)
+    n_raw = len(raw)
+    del raw
+    rng = np.random.RandomState(41 + seed_offset)
+    scans, truths, guesses = [], [], []
+    for k in range(n_scans):
+        T = sc.free_pose_near(rng.uniform(60.0, extent - 60.0), rng.uniform(60.0, extent - 60.0), 2.0, rng.uniform(-np.pi, np.pi))
+        if method == "loam":
+            s = downsample(sc.scan(T, "vlp16", seed=11000 + k + 100000 * seed_offset), 0.5)
+            G = T @ _perturb(rng, 0.3, 2.0)
+        else:
+            s = sc.scan(T, "hdl64", seed=12000 + k + 100000 * seed_offset)
+            G = T @ _perturb(rng, 0.5, 3.0)
+        scans.append(s)
+        truths.append(T)
+        guesses.append(G)
+    name = "C4 batched localisation (%s): independent %s scans vs a %.1fM-pt static map (%dx%d tiles)" % (
+        method.upper(), "VLP-16 (0.5 m downsample)" if method == "loam" else "64-beam", len(dst) / 1e6, tiles, tiles)
+    return dict(name=name, method=method, dst=dst, scans=scans, truths=truths, guesses=guesses, raw_map_points=n_raw)
 
 
 def shard(n_items, rank, world):

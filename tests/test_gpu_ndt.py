@@ -73,8 +73,8 @@ def test_double_path_hessian_parity(ctx, ondt, case):
     assert data.rel_err(ctx.ndt_hessian(case["src"], p), ondt.hessian(case["src"], p)) < 1e-9
 
 
-@pytest.mark.parametrize("search", ["DIRECT1", "DIRECT26"])
-def test_other_direct_neighbourhoods(case, search):
+@pytest.mark.parametrize("search", ["DIRECT1", "DIRECT26", "KDTREE"])
+def test_other_neighbourhoods(case, search):
     c = capi.Context(capi.PCR_NDT, ndt_search=getattr(capi, "PCR_NDT_" + search))
     c.set_target(case["dst"])
     p = _pvec(case["T_guess"])
@@ -82,6 +82,13 @@ def test_other_direct_neighbourhoods(case, search):
     g = c.ndt_derivatives(case["src"], p)
     assert abs(g["score"] - o["score"]) <= TOL_REL * abs(o["score"])
     assert data.rel_err(g["H"], o["H"]) < TOL_REL
+    assert np.abs(g["g"] - o["g"]).sum() <= TOL_REL * np.abs(o["g"]).sum() + 1e-9
+    if search == "KDTREE":  # N6: the double-path Hessian and a whole registration through the radius neighbourhood
+        assert data.rel_err(c.ndt_hessian(case["src"], p), orc.Ndt(case["dst"], 1.0).hessian(case["src"], p, search=search)) < 1e-9
+        oa = orc.Ndt(case["dst"], 1.0).align(case["src"], case["T_guess"], search=search)
+        T, conv = c.align(case["src"], case["T_guess"])
+        dt, dr = data.pose_err(T, oa["T"])
+        assert conv == oa["converged"] and dt < TOL_T and dr < TOL_R, (dt, dr)
     c.close()
 
 
@@ -138,10 +145,3 @@ def test_register_interface_and_edges(case):
     far[:, :3] += 5000.0
     T, conv = reg.ctx.align(far, case["T_guess"])
     assert conv and np.allclose(T, case["T_guess"].astype(np.float32).astype(np.float64))
-    # KDTREE neighbourhood is declared but not built yet
-    c = capi.Context(capi.PCR_NDT, ndt_search=capi.PCR_NDT_KDTREE)
-    c.set_target(case["dst"])
-    with pytest.raises(capi.PcrError) as e:
-        c.align(case["src"], case["T_guess"])
-    assert e.value.code == -6
-    c.close()
