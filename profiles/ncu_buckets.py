@@ -1,6 +1,7 @@
 """Stall samples and executed instructions bucketed by SASS index range / source line: where does the kernel's time go.
 usage: python profiles/ncu_buckets.py report.ncu-rep [bucket_size]"""
-import csv, subprocess, sys, collections
+import csv, subprocess, sys, signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 rep = sys.argv[1]
 bs = int(sys.argv[2]) if len(sys.argv) > 2 else 250
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
