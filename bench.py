@@ -181,6 +181,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
+        # NCCL writes its banner / debug lines to stdout: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_bench_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
     method_id = {"c2_ndt": capi.PCR_NDT, "c1_loam": capi.PCR_LOAM, "c3_vgicp": capi.PCR_VGICP, "c4_loam": capi.PCR_LOAM,
                  "c4_ndt": capi.PCR_NDT}[args.workload]

@@ -704,8 +704,8 @@ extern "C" int pcr_gicp_covariances(pcr_ctx* c, const void* pts, size_t n, size_
   if (n == 0) return PCR_OK;
   const float4* d = upload_points(c, pts, n, stride, c->raw_src, c->src);
   c->has_last = false;
-  CellGrid& grid = c->vgd.src_grid;
-  int rc = build_cell_grid(d, n, 0.5f, grid, c->ks, c->bw, c->stream);
+  MortonGrid& grid = c->vgd.src_grid;
+  int rc = build_morton_grid(d, n, grid, c->bw, c->stream);
   if (rc) return fail(c, rc, "grid too large");
   c->vgd.src_covs.ensure(n * 6);
   int32_t* dk = c->vgd.knn_dbg.ensure(n * size_t(k));

@@ -86,7 +86,6 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     const bool have = lane < tile && i < end;
     float4 po = make_float4(0.f, 0.f, 0.f, 0.f);
     float pmf[3] = {0.f, 0.f, 0.f};
-    int c[3] = {0, 0, 0};
     bool near = false;
     if (have) {
       po = __ldg(src + i);

@@ -9,143 +9,7 @@ namespace pcr {
 
 constexpr int kVgBlock = 128;
 constexpr int kVgNV = 29;  // cost, 21 H, 6 b, count
-constexpr int kMaxK = 32;
-
-// ================================================================================================================
-// Exact k-NN (k <= 32) on the uniform grid, ONE WARP PER QUERY, Chebyshev ring expansion.
-// Float metric of FLANN L2_Simple<float> (float diff, float square, float accumulate x->y->z), ties
-// broken by (d2, original index). Lane l holds the l-th best so far; candidates of a row of cells are read coalesced
-// (one float4 per lane) and those beating the current k-th are inserted with ballot / shuffle-up. The search stops as
-// soon as the k-th distance is provably smaller than the distance to every unvisited cell.
-// ================================================================================================================
-__device__ __forceinline__ float dist2_f32(float qx, float qy, float qz, const float4& m) {
-  const float dx = __fsub_rn(qx, m.x), dy = __fsub_rn(qy, m.y), dz = __fsub_rn(qz, m.z);
-  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-}
-
-struct WarpKnn {
-  float bd;   // this lane's entry of the sorted result (lane < k), +inf when empty
-  int bi;
-  float td;   // current k-th best (threshold), warp-uniform
-  int ti;
-  int cnt;    // entries found so far (<= k), warp-uniform
-};
-
-constexpr unsigned kFull = 0xffffffffu;
-
-// scan the contiguous run [lo, hi) of the cell-sorted array
-__device__ __forceinline__ void knn_scan_run(WarpKnn& st, const float4* __restrict__ pts, int lo, int hi, float qx, float qy, float qz,
-                                             int k, int lane) {
-  for (int base = lo; base < hi; base += 32) {
-    const int j = base + lane;
-    float d2 = 0.f;
-    int idx = 0;
-    bool pass = false;
-    if (j < hi) {
-      const float4 m = __ldg(pts + j);
-      d2 = dist2_f32(qx, qy, qz, m);
-      idx = __float_as_int(m.w);
-      pass = d2 < st.td || (d2 == st.td && idx < st.ti);
-    }
-    unsigned mask = __ballot_sync(kFull, pass);
-    while (mask) {
-      const int s = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const float cd = __shfl_sync(kFull, d2, s);
-      const int ci = __shfl_sync(kFull, idx, s);
-      if (!(cd < st.td || (cd == st.td && ci < st.ti))) continue;  // the threshold moved since the ballot
-      const bool less = st.bd < cd || (st.bd == cd && st.bi < ci);
-      const int pos = __popc(__ballot_sync(kFull, less && lane < k));
-      const float ud = __shfl_up_sync(kFull, st.bd, 1);
-      const int ui = __shfl_up_sync(kFull, st.bi, 1);
-      if (lane == pos) { st.bd = cd; st.bi = ci; }
-      else if (lane > pos && lane < k) { st.bd = ud; st.bi = ui; }
-      if (st.cnt < k) st.cnt++;
-      st.td = __shfl_sync(kFull, st.bd, k - 1);
-      st.ti = __shfl_sync(kFull, st.bi, k - 1);
-    }
-  }
-}
-
-// Warp-cooperative exact k-NN. On return lanes [0, cnt) hold the neighbours in ascending (d2, idx) order.
-__device__ __forceinline__ WarpKnn knn_warp_f32(const CellGridView& grid, float qx, float qy, float qz, int k, double slack_cells, int lane) {
-  const GridSpec& g = grid.g;
-  WarpKnn st;
-  st.bd = INFINITY; st.bi = 0x7fffffff; st.td = INFINITY; st.ti = 0x7fffffff; st.cnt = 0;
-  const float q[3] = {qx, qy, qz};
-  int c[3];
-  double margin = 1e30;
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    const float s = __fmul_rn(q[a], g.inv_leaf[a]);
-    float fc = __fsub_rn(floorf(s), float(g.min_b[a]));
-    fc = fminf(fmaxf(fc, -1.0e9f), 1.0e9f);
-    c[a] = int(fc);
-    const double fr = double(s) - floor(double(s));
-    margin = fmin(margin, fmin(fr, 1.0 - fr));
-  }
-  margin -= slack_cells;
-  int rstart = 0, rmax = 0;
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    rstart = max(rstart, max(-c[a], c[a] - (g.div_b[a] - 1)));
-    rmax = max(rmax, max(c[a], g.div_b[a] - 1 - c[a]));
-  }
-  const double leaf = double(g.leaf[0]);
-  for (int r = rstart; r <= rmax; r++) {
-    // Shell of Chebyshev radius r = cube (2r+1)^3 minus the already visited inner cube. The cube is enumerated 32 cells
-    // at a time: every lane fetches one cell range (all loads in flight together), then the non-empty shell cells are
-    // scanned one after the other.
-    const int side = 2 * r + 1;
-    const int slab = side * side, per = 4 * side - 4;
-    const int nshell = r == 0 ? 1 : 2 * slab + (side - 2) * per;  // = side^3 - (side-2)^3
-    for (int base = 0; base < nshell; base += 32) {
-      const int e = base + lane;
-      int lo = 0, hi = 0;
-      if (e < nshell) {
-        int dx, dy, dz;
-        if (e < 2 * slab || r == 0) {  // bottom / top z-slabs
-          const int rem = e % slab;
-          dz = (e / slab) ? r : -r;
-          dy = rem / side - r;
-          dx = rem % side - r;
-        } else {  // perimeter of the middle layers, rows in x first so that consecutive lanes hit consecutive keys
-          const int e2 = e - 2 * slab, p = e2 % per;
-          dz = -r + 1 + e2 / per;
-          if (p < side) { dy = -r; dx = p - r; }
-          else if (p < 2 * side) { dy = r; dx = p - side - r; }
-          else { const int q = p - 2 * side; dy = -r + 1 + (q >> 1); dx = (q & 1) ? r : -r; }
-        }
-        const int x = c[0] + dx, y = c[1] + dy, z = c[2] + dz;
-        if (x >= 0 && x < g.div_b[0] && y >= 0 && y < g.div_b[1] && z >= 0 && z < g.div_b[2]) {
-          const int2 rg = __ldg(grid.range + ((long long)x + (long long)y * g.mul[1] + (long long)z * g.mul[2]));
-          lo = rg.x; hi = rg.y;
-        }
-      }
-      unsigned cells = __ballot_sync(kFull, hi > lo);
-      while (cells) {
-        const int sl = __ffs(cells) - 1;
-        cells &= cells - 1;
-        int rlo = __shfl_sync(kFull, lo, sl), rhi = __shfl_sync(kFull, hi, sl);
-        // x-adjacent cells are consecutive keys: extend the run over directly following lanes that continue it
-        while (cells) {
-          const int nl = __ffs(cells) - 1;
-          const int nlo = __shfl_sync(kFull, lo, nl);
-          if (nlo != rhi) break;
-          rhi = __shfl_sync(kFull, hi, nl);
-          cells &= cells - 1;
-        }
-        knn_scan_run(st, grid.pts, rlo, rhi, qx, qy, qz, k, lane);
-      }
-    }
-    if (st.cnt == k) {
-      const double reach = (double(r) + margin) * leaf;
-      if (reach > 0.0 && double(st.td) < reach * reach * (1.0 - 1e-6)) break;
-    }
-  }
-  return st;
-}
-
+constexpr int kMaxK = kKnnMaxK;
 
 // ================================================================================================================
 // V1. FastGICP::calculate_covariances (fast_gicp_impl.hpp:241-298): k-NN (self included), cov = N N^T / k of the
@@ -153,13 +17,15 @@ __device__ __forceinline__ WarpKnn knn_warp_f32(const CellGridView& grid, float 
 // Two kernels: warp-per-query k-NN writes the neighbour indices, then one thread per point does the 3x3 algebra.
 // ================================================================================================================
 __global__ void __launch_bounds__(256)
-gicp_knn_kernel(const float4* __restrict__ pts, size_t n, CellGridView grid, int k, double slack, int32_t* __restrict__ knn_idx) {
+gicp_knn_kernel(size_t n, MortonView grid, int k, int32_t* __restrict__ knn_idx) {
+  // one warp per query; queries are taken in Morton order (the sorted copy), so neighbouring warps touch the same cells
   const int lane = threadIdx.x & 31;
   const size_t warps = size_t(gridDim.x) * (blockDim.x >> 5);
   for (size_t i = size_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
-    const float4 q = __ldg(pts + i);
-    const WarpKnn st = knn_warp_f32(grid, q.x, q.y, q.z, k, slack, lane);
-    if (lane < k) knn_idx[i * k + lane] = lane < st.cnt ? st.bi : -1;
+    const float4 q = __ldg(grid.pts + i);
+    const WarpKnn st = knn_warp_morton(grid, q.x, q.y, q.z, k, 16, lane);
+    const size_t orig = size_t(__float_as_int(q.w));
+    if (lane < k) knn_idx[orig * k + lane] = lane < st.cnt ? st.bi : -1;
   }
 }
 
@@ -209,10 +75,10 @@ gicp_cov_kernel(const float4* __restrict__ pts, size_t n, int k, const int32_t* 
 }
 
 // knn_idx: device scratch of n*k ints (always needed)
-void gicp_covariances(const float4* pts, size_t n, const CellGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s) {
+void gicp_covariances(const float4* pts, size_t n, const MortonGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s) {
   if (n == 0) return;
   const unsigned blocks = unsigned(std::min<size_t>((n + 7) / 8, size_t(kNumSMs) * 64));
-  gicp_knn_kernel<<<blocks, 256, 0, s>>>(pts, n, view_of(grid), k, grid_slack_cells(grid.g), knn_idx);
+  gicp_knn_kernel<<<blocks, 256, 0, s>>>(n, view_of(grid), k, knn_idx);
   gicp_cov_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(pts, n, k, knn_idx, covs);
 }
 
@@ -272,8 +138,8 @@ int vgicp_build_target(const float4* pts, size_t n, const pcr_params& prm, Vgicp
   tgt.resolution = prm.vgicp_resolution;
   if (n == 0) { tgt.built = true; return 0; }
   if (prm.vgicp_k > kMaxK || prm.vgicp_k < 1) return PCR_ERR_INVALID;
-  // kNN grid (0.5 m cells) + per-point covariances
-  int rc = build_cell_grid(pts, n, 0.5f, tgt.grid, ks, bw, s);
+  // nested kNN grid + per-point covariances
+  int rc = build_morton_grid(pts, n, tgt.grid, bw, s);
   if (rc) return rc;
   tgt.covs.ensure(n * 6);
   tgt.knn.ensure(n * size_t(prm.vgicp_k));
@@ -478,7 +344,7 @@ void VgicpDriver::evaluate(const float4* src, const double* covs, const uint32_t
 int VgicpDriver::compute_source_covs(const float4* src, size_t ns, int k, KeySort& ks, BBoxWork& bw, cudaStream_t s) {
   if (ns == 0) return 0;
   if (k > kMaxK || k < 1) return PCR_ERR_INVALID;
-  int rc = build_cell_grid(src, ns, 0.5f, src_grid, ks, bw, s);
+  int rc = build_morton_grid(src, ns, src_grid, bw, s);
   if (rc) return rc;
   src_covs.ensure(ns * 6);
   knn_dbg.ensure(ns * size_t(k));
@@ -601,7 +467,7 @@ int VgicpDriver::align(const float4* src, size_t ns, const VgicpTarget& tgt, con
 // V6. pcl::Registration::getFitnessScore: float transform, exact 1-NN (float metric), mean of d2 <= max_range (FP64)
 // ================================================================================================================
 __global__ void __launch_bounds__(256)
-fitness_kernel(const float4* __restrict__ src, size_t ns, CellGridView grid, double slack, const float* __restrict__ Tf, double max_range,
+fitness_kernel(const float4* __restrict__ src, size_t ns, MortonView grid, const float* __restrict__ Tf, double max_range,
                double* __restrict__ partials) {
   // one warp per query; per-warp sums in FP64, fixed-order block reduction -> partials[block] = {sum d2, count}
   __shared__ double ssum[8], scnt[8];
@@ -614,7 +480,7 @@ fitness_kernel(const float4* __restrict__ src, size_t ns, CellGridView grid, dou
 #pragma unroll
     for (int r = 0; r < 3; r++)
       q[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tf[r], p.x), __fmul_rn(Tf[4 + r], p.y)), __fmul_rn(Tf[8 + r], p.z)), Tf[12 + r]);
-    const WarpKnn st = knn_warp_f32(grid, q[0], q[1], q[2], 1, slack, lane);
+    const WarpKnn st = knn_warp_morton(grid, q[0], q[1], q[2], 1, 1, lane);
     if (st.cnt == 1 && double(st.td) <= max_range) { sum += double(st.td); cnt += 1.0; }
   }
   if (lane == 0) { ssum[warp] = sum; scnt[warp] = cnt; }
@@ -637,7 +503,7 @@ int VgicpDriver::fitness(const float4* src, size_t ns, const VgicpTarget& tgt, c
   float hT[16];
   for (int i = 0; i < 16; i++) hT[i] = static_cast<float>(T[i]);
   PCR_CUDA_CHECK(cudaMemcpyAsync(dTf, hT, sizeof(hT), cudaMemcpyHostToDevice, s));
-  fitness_kernel<<<blocks, 256, 0, s>>>(src, ns, view_of(tgt.grid), grid_slack_cells(tgt.grid.g), dTf, max_range, fit_partials.p);
+  fitness_kernel<<<blocks, 256, 0, s>>>(src, ns, view_of(tgt.grid), dTf, max_range, fit_partials.p);
   launches++;
   double* h = h_fit.ensure(size_t(blocks) * 2);
   PCR_CUDA_CHECK(cudaMemcpyAsync(h, fit_partials.p, size_t(blocks) * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));

@@ -3,6 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "voxel.cuh"
+#include "knn.cuh"
 #include "../../include/pcr_cuda.h"
 
 namespace pcr {
@@ -16,7 +17,7 @@ struct __align__(16) VoxelRec {  // 80 B
 struct VgicpTarget {
   bool built = false;
   size_t n = 0;
-  CellGrid grid;              // over the raw target (kNN for covariances and fitness)
+  MortonGrid grid;            // over the raw target (kNN for covariances and fitness)
   DevBuf<double> covs;        // per target point, 6 doubles
   DevBuf<int32_t> knn;        // k neighbour indices per target point (scratch of the covariance build)
   // voxel map
@@ -51,7 +52,7 @@ struct VgicpDriver {
   PinBuf<VgicpEvalResult> h_results;
   PinBuf<uint32_t> h_offsets;
   PinBuf<double> h_fit;
-  CellGrid src_grid;
+  MortonGrid src_grid;
   long long launches = 0;
   float hot_ms = 0.f;
   int hot_launches = 0;
@@ -74,7 +75,7 @@ struct VgicpDriver {
 
 // exact k-NN (float metric, (d2, idx) order) + PLANE-regularised covariance for every point of `pts` using `grid` built over it.
 // covs: 6 doubles per point. knn_idx: device scratch/output, k ints per point.
-void gicp_covariances(const float4* pts, size_t n, const CellGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s);
+void gicp_covariances(const float4* pts, size_t n, const MortonGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s);
 
 int vgicp_build_target(const float4* pts, size_t n, const pcr_params& prm, VgicpTarget& tgt, KeySort& ks, BBoxWork& bw, cudaStream_t s);
 
