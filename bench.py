@@ -32,16 +32,31 @@ import numpy as np  # noqa: E402
 
 
 # SURVEY.md §8(d) algorithmic bytes (SoA/float4 map, minimal traffic, no cache credit)
-def algo_bytes(method, point_evals, index_reads, pairs):
-    """Algorithmic bytes of the hot kernel: what the algorithm has to read once, no cache credit.
-    point_evals = source points pushed through the kernel (summed over launches); index_reads = spatial-index entries read
-    (LOAM: x-rows looked up, 2 x 4 B each; NDT / VGICP: 4-byte voxel-table entries); pairs = candidate map points examined
-    (LOAM, 16 B) / (point, leaf) pairs (NDT, 64-byte leaf record) / correspondences (VGICP, 80-byte voxel record)."""
+def algo_bytes_8d(method, point_evals, pairs, c_bar=None):
+    """Algorithmic bytes by SURVEY.md §8(d)'s per-unit figures (SoA / float4 map, minimal traffic, no cache credit) — the
+    numerator of roofline.achieved. point_evals = source points pushed through the kernel, summed over its launches.
+      LOAM iteration   Ns * (16 + 27*8 + 16*C_bar), C_bar = mean population of the 27 one-metre cells around a query (oracle)
+      NDT evaluation   Ns * (16 + 7*8 + 104*V_bar), V_bar = (point, leaf) pairs per point (counted by the kernel)
+      VGICP evaluation Ns * (16 + 48 + 8) + 84 * correspondences"""
+    if method == "ndt":
+        return point_evals * (16.0 + 56.0) + 104.0 * pairs
+    if method == "loam":
+        return None if c_bar is None else point_evals * (16.0 + 27 * 8.0 + 16.0 * c_bar)
+    if method == "vgicp":
+        return point_evals * (16.0 + 48.0 + 8.0) + 84.0 * pairs
+    raise ValueError(method)
+
+
+def algo_bytes_examined(method, point_evals, index_reads, pairs):
+    """Bytes THIS implementation's algorithm has to read once (its own record sizes, its pruned search), no cache credit:
+    index_reads = spatial-index entries read (LOAM: x-rows looked up, 2 x 4 B each; NDT / VGICP: 4-byte table entries);
+    pairs = candidate map points examined (LOAM, 16 B) / (point, leaf) pairs (NDT, 64-byte leaf record) / correspondences
+    (VGICP, 80-byte voxel record). Always <= the §8(d) figure; reported next to it as roofline.achieved_examined."""
     if method == "ndt":
         return point_evals * 16.0 + index_reads * 4.0 + 64.0 * pairs
     if method == "loam":
         return point_evals * 16.0 + index_reads * 8.0 + 16.0 * pairs
-    if method == "vgicp":    # point 16 B + source covariance 48 B + table entry + voxel record
+    if method == "vgicp":
         return point_evals * (16.0 + 48.0) + index_reads * 4.0 + 80.0 * pairs
     raise ValueError(method)
 
@@ -342,23 +357,6 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        ab = algo_bytes(method, pt_evals, idx_reads, pairs)
-        traffic, traffic_src = None, None
-        try:  # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of the same workload
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
-            if tr:
-                traffic, traffic_src = tr["dram_bytes_per_launch"], "profiles/" + tr["source"].replace(".ncu-rep", "") + " (ncu --set full, one launch)"
-        except Exception:
-            pass
-        achieved = ab / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else None
-        roof = {"bound": "hbm", "kernel": {"ndt": "ndt_eval_kernel", "loam": "loam_iter_kernel", "vgicp": "vgicp_eval_kernel"}[method],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "launches": hot_launches, "avg_launch_us": 1e3 * hot_ms / max(hot_launches, 1), "algorithmic_bytes_per_launch": ab / max(hot_launches, 1),
-                "points_per_launch": pt_evals / max(hot_launches, 1), "pairs_per_point": pairs / max(pt_evals, 1), "index_reads_per_point": idx_reads / max(pt_evals, 1),
-                "kernel_share_of_step": hot_ms / (1e3 * t_resident) if t_resident > 0 else None,
-                "note": "achieved = algorithmic bytes (no cache credit) / kernel time; the index is L2-friendly, DRAM traffic is far below the "
-                        "algorithmic bytes and the kernel is latency / issue bound, not HBM bound (DESIGN.md §4, profiles/)"}
         # ---- CPU baseline: the oracle on the host cores, bounded sample
         cpu = None
         if not args.no_cpu_baseline:
@@ -375,8 +373,43 @@ def run_ours(args, rank, world, local_rank):
             cpu = {"value": n_cpu / float(np.sum(tc)), "unit": "registrations/s", "cores": cores, "kind": "port",
                    "sample": "%d full scan2Map calls (index rebuilt per call) of the same workload with the CPU oracle, OpenMP %d threads" % (n_cpu, cores),
                    "ms_per_registration": 1e3 * float(np.mean(tc))}
-        s0, d0, _, _ = step_inputs(wl, 0)
+        s0, d0, Tg0, _ = step_inputs(wl, 0)
         errs = np.array(errs)
+        c_bar = None
+        if method == "loam" and not args.no_cpu_baseline:
+            # C_bar of SURVEY §8(d), reported by the oracle: population of the 27 one-metre cells around the scan's points
+            # at the initial guess (part of the cpu_baseline leg: the only place bench.py runs oracle/)
+            qs = []
+            for u in range(min(4, n_unique)):
+                su, _, Tu, _ = step_inputs(wl, u)
+                qs.append(su[:, :3].astype(np.float64) @ Tu[:3, :3].T + Tu[:3, 3])
+            c_bar = float(orc.neighbourhood27(d0, np.concatenate(qs), 1.0, threads=cores))
+        ab = algo_bytes_8d(method, pt_evals, pairs, c_bar)
+        abx = algo_bytes_examined(method, pt_evals, idx_reads, pairs)
+        formula = "SURVEY §8(d)"
+        if ab is None:  # LOAM without the oracle's C_bar (--no-cpu-baseline): fall back to the bytes really examined
+            ab, formula = abx, "examined bytes (C_bar not measured: --no-cpu-baseline)"
+        achieved = ab / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else None
+        achieved_x = abx / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else None
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of the same workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload)
+            if tr and tr["kernel"] == {"ndt": "ndt_eval_kernel", "loam": "loam_iter_kernel", "vgicp": "vgicp_eval_kernel"}[method]:
+                traffic, traffic_src = tr["dram_bytes_per_launch"], "profiles/" + tr["source"].replace(".ncu-rep", "") + " (ncu --set full, one launch)"
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": {"ndt": "ndt_eval_kernel", "loam": "loam_iter_kernel", "vgicp": "vgicp_eval_kernel"}[method],
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                "traffic_source": traffic_src, "formula": formula, "c_bar": c_bar,
+                "achieved_examined": achieved_x, "frac_examined": (achieved_x / peak) if achieved_x else None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                "launches": hot_launches, "avg_launch_us": 1e3 * hot_ms / max(hot_launches, 1), "algorithmic_bytes_per_launch": ab / max(hot_launches, 1),
+                "examined_bytes_per_launch": abx / max(hot_launches, 1),
+                "points_per_launch": pt_evals / max(hot_launches, 1), "pairs_per_point": pairs / max(pt_evals, 1), "index_reads_per_point": idx_reads / max(pt_evals, 1),
+                "kernel_share_of_step": hot_ms / (1e3 * t_resident) if t_resident > 0 else None,
+                "note": "achieved = §8(d) algorithmic bytes (no cache credit) / measured kernel time; achieved_examined = the bytes this pruned / "
+                        "compact-record implementation really needs. DRAM traffic is far below both: the index is L2-friendly and the kernel is "
+                        "latency / issue bound, not HBM bound (DESIGN.md §4, profiles/)"}
         out = {
             "metric": "scan registrations/sec (%s)" % method.upper(), "value": value, "unit": "registrations/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_resident / args.steps, "p50_align_ms": float(np.median(lat)),

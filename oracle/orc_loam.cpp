@@ -94,6 +94,37 @@ extern "C" int orc_knn(const float* map, size_t nm, size_t stride_f, const doubl
   return 0;
 }
 
+// C-bar of SURVEY.md §8(d): mean number of map points in the 27 cells (cell = gate radius, 1 m) around a query — the
+// per-unit figure of the LOAM algorithmic-bytes formula. Queries are doubles (xyz). Returns the mean.
+extern "C" double orc_neighbourhood27(const float* map, size_t nm, size_t stride_f, const double* queries, size_t nq, float cell,
+                                      int threads) {
+  Cloud c{map, nm, stride_f};
+  KnnGrid grid;
+  grid.build(c, cell > 0 ? cell : 1.0f);
+  if (threads <= 0) threads = 1;
+  double total = 0;
+#pragma omp parallel for num_threads(threads) schedule(static) reduction(+ : total)
+  for (long long qi = 0; qi < (long long)nq; qi++) {
+    int c0[3];
+    bool far = false;
+    for (int a = 0; a < 3; a++) {
+      double f = std::floor((queries[qi * 3 + a] - double(grid.origin[a])) / double(grid.cell));
+      if (f < -1 || f > double(grid.dim[a])) far = true;
+      c0[a] = int(std::max(-2.0, std::min(f, double(grid.dim[a]) + 1)));
+    }
+    if (far) continue;
+    long long cnt = 0;
+    for (int z = std::max(c0[2] - 1, 0); z <= std::min(c0[2] + 1, grid.dim[2] - 1); z++)
+      for (int y = std::max(c0[1] - 1, 0); y <= std::min(c0[1] + 1, grid.dim[1] - 1); y++)
+        for (int x = std::max(c0[0] - 1, 0); x <= std::min(c0[0] + 1, grid.dim[0] - 1); x++) {
+          size_t cid = size_t(x) + size_t(grid.dim[0]) * (size_t(y) + size_t(grid.dim[1]) * size_t(z));
+          cnt += grid.start[cid + 1] - grid.start[cid];
+        }
+    total += double(cnt);
+  }
+  return nq ? total / double(nq) : 0.0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // geometry: manifolds::exp(V6 -> M4) (common/geometry/manifolds.hpp:33-60), trans::T2SE3
 // (common/geometry/trans.hpp:54-65) via Eigen::Quaternion(R).normalized().toRotationMatrix().

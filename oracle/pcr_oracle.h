@@ -33,6 +33,9 @@ int orc_voxel_downsample(const float* pts, size_t n, size_t stride_f, float leaf
 int orc_knn(const float* map, size_t nm, size_t stride_f, const double* queries, size_t nq, int k,
             int metric_float, int brute, float cell, int threads, int64_t* idx_out, double* d2_out);
 
+/* C-bar of SURVEY.md 8(d): mean population of the 27 cells (cell = gate radius) around a query */
+double orc_neighbourhood27(const float* map, size_t nm, size_t stride_f, const double* queries, size_t nq, float cell, int threads);
+
 /* ---- LOAM (PCR/src/LoamRegister.cpp:99-223) ----------------------------------------------------- */
 typedef struct orc_loam_iter_log {
   double T_before[16]; /* pose the iteration linearised at */

@@ -117,6 +117,15 @@ def knn(map_pts, queries, k, metric_float=False, brute=False, cell=1.0, threads=
     return idx, d2
 
 
+def neighbourhood27(map_pts, queries, cell=1.0, threads=8):
+    """C-bar of SURVEY.md §8(d): mean number of map points in the 27 cells around a query"""
+    a, n, st = _pts(map_pts)
+    q = np.ascontiguousarray(queries, dtype=np.float64)
+    L = lib()
+    L.orc_neighbourhood27.restype = ctypes.c_double
+    return L.orc_neighbourhood27(_p(a), ctypes.c_size_t(n), ctypes.c_size_t(st), _p(q), ctypes.c_size_t(q.shape[0]), ctypes.c_float(cell), threads)
+
+
 def ref_knn(map_pts, queries, k, metric_float=False):
     L = ref_lib()
     if L is None:

@@ -4,6 +4,7 @@
 #include "dev_linalg.cuh"
 #include "host_math.hpp"
 #include <cfloat>
+#include <cstdlib>
 
 namespace pcr {
 
@@ -17,13 +18,13 @@ constexpr int kMaxK = kKnnMaxK;
 // Two kernels: warp-per-query k-NN writes the neighbour indices, then one thread per point does the 3x3 algebra.
 // ================================================================================================================
 __global__ void __launch_bounds__(256)
-gicp_knn_kernel(size_t n, MortonView grid, int k, int32_t* __restrict__ knn_idx) {
+gicp_knn_kernel(size_t n, MortonView grid, int k, int min_pop, int32_t* __restrict__ knn_idx) {
   // one warp per query; queries are taken in Morton order (the sorted copy), so neighbouring warps touch the same cells
   const int lane = threadIdx.x & 31;
   const size_t warps = size_t(gridDim.x) * (blockDim.x >> 5);
   for (size_t i = size_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
     const float4 q = __ldg(grid.pts + i);
-    const WarpKnn st = knn_warp_morton(grid, q.x, q.y, q.z, k, 16, lane);
+    const WarpKnn st = knn_warp_morton(grid, q.x, q.y, q.z, k, min_pop, lane);
     const size_t orig = size_t(__float_as_int(q.w));
     if (lane < k) knn_idx[orig * k + lane] = lane < st.cnt ? st.bi : -1;
   }
@@ -78,7 +79,9 @@ gicp_cov_kernel(const float4* __restrict__ pts, size_t n, int k, const int32_t* 
 void gicp_covariances(const float4* pts, size_t n, const MortonGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s) {
   if (n == 0) return;
   const unsigned blocks = unsigned(std::min<size_t>((n + 7) / 8, size_t(kNumSMs) * 64));
-  gicp_knn_kernel<<<blocks, 256, 0, s>>>(n, view_of(grid), k, knn_idx);
+  static const int min_pop_env = std::getenv("PCR_KNN_MINPOP") ? std::atoi(std::getenv("PCR_KNN_MINPOP")) : 0;  // tuning knob
+  const int min_pop = min_pop_env > 0 ? min_pop_env : std::max(1, (k * 3) / 4);
+  gicp_knn_kernel<<<blocks, 256, 0, s>>>(n, view_of(grid), k, min_pop, knn_idx);
   gicp_cov_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(pts, n, k, knn_idx, covs);
 }
 
