@@ -138,6 +138,18 @@ int pcr_voxel_downsample(pcr_ctx* c, const void* pts, size_t n, size_t stride, f
 int pcr_voxel_downsample_device(pcr_ctx* c, const void* dev_pts, size_t n, size_t stride, float leaf, void* dev_out, size_t cap,
                                 size_t* m);
 
+/* Submap assembly on the device. Replaces the body of MapManager::updateMap (frontend/src/MapManager.cpp:177-192) and of
+ * LoopClosureManager::loopFindNearKeyframes (backend/src/LoopClosureManager.cpp:40-60): every keyframe cloud i is
+ * transformed by poses[i] (cast to float, pcp::transformPointCloud, common/pcp/pcp.hpp:38-62), the clouds are
+ * concatenated in the given order and voxel-downsampled at `leaf` (pcp::voxelDownSample). The result becomes the
+ * context's current target (index built as by pcr_set_target) and stays on the device; `out` (nullable, HOST) receives
+ * up to `cap` 32-byte PointXYZI records, *m their number. Keyframe clouds are immutable in the reference (KeyFrame::pc is
+ * a const shared_ptr): their device copies are cached by (host pointer, count) so that a keyframe crosses PCIe once;
+ * pcr_submap_cache_clear drops the cache. poses: 16 doubles per cloud, column-major. */
+int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const size_t* counts, size_t n_clouds, size_t stride, const double* poses,
+                     float leaf, void* out, size_t cap, size_t* m);
+int pcr_submap_cache_clear(pcr_ctx* c);
+
 /* Multi-GPU: serialise the built target index into one contiguous DEVICE blob so that it can be broadcast with NCCL
  * (torch.distributed) and imported on the other ranks without rebuilding. */
 int pcr_target_blob_size(pcr_ctx* c, size_t* bytes);

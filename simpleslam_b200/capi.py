@@ -23,6 +23,7 @@ SYMBOLS = [
     "pcr_target_blob_size", "pcr_target_export", "pcr_target_import", "pcr_debug_voxel", "pcr_loam_linearize",
     "pcr_loam_get_logs", "pcr_ndt_num_leaves", "pcr_ndt_get_leaves", "pcr_ndt_derivatives", "pcr_ndt_hessian",
     "pcr_gicp_covariances", "pcr_vgicp_num_voxels", "pcr_vgicp_get_voxels", "pcr_vgicp_evaluate",
+    "pcr_submap_build", "pcr_submap_cache_clear",
 ]
 
 
@@ -226,6 +227,26 @@ class Context:
         grid = np.zeros(9, np.int32)
         self._check(lib().pcr_debug_voxel(self._h, _vp(keys), _vp(ok), _vp(oc), _vp(grid)))
         return dict(keys=keys[:n], out_keys=ok[:m], counts=oc[:m], grid=grid)
+
+    # -- submap assembly (MapManager::updateMap / loopFindNearKeyframes): transform + concat + downsample on the device;
+    # the result becomes the current target. clouds: list of (n, 8) float32 arrays that must stay alive (cached by pointer)
+    def submap_build(self, clouds, poses, leaf, want_points=True):
+        k = len(clouds)
+        arrs = [_cloud(cl) for cl in clouds]
+        ptrs = (ctypes.c_void_p * max(k, 1))(*[a.ctypes.data for a, _, _ in arrs])
+        counts = (ctypes.c_size_t * max(k, 1))(*[n for _, n, _ in arrs])
+        stride = arrs[0][2] if k else 32
+        assert all(st == stride for _, _, st in arrs), "all keyframe clouds must share one record stride"
+        P = np.ascontiguousarray(np.concatenate([_T_in(T) for T in poses]) if k else np.zeros(16))
+        total = int(sum(n for _, n, _ in arrs))
+        out = np.empty((max(total, 1), 8), np.float32) if want_points else None
+        m = ctypes.c_size_t(0)
+        self._check(lib().pcr_submap_build(self._h, ptrs, counts, ctypes.c_size_t(k), ctypes.c_size_t(stride), _vp(P), ctypes.c_float(leaf),
+                                           _vp(out), ctypes.c_size_t(total), ctypes.byref(m)))
+        return (out[:m.value].copy() if want_points else None), m.value
+
+    def submap_cache_clear(self):
+        self._check(lib().pcr_submap_cache_clear(self._h))
 
     # -- target blob (multi-GPU)
     def target_blob_size(self):

@@ -8,6 +8,8 @@
 #include "vgicp.cuh"
 #include "host_math.hpp"
 #include <cfloat>
+#include <map>
+#include <memory>
 #include <string>
 
 using namespace pcr;
@@ -44,6 +46,13 @@ struct pcr_ctx {
   LoamDriver loam;
   NdtDriver ndtd;
   VgicpDriver vgd;
+
+  // submap assembly: device copies of immutable keyframe clouds, keyed by (host pointer, count)
+  struct CachedCloud { DevBuf<float4> pts; size_t n = 0; };
+  std::map<std::pair<const void*, size_t>, std::unique_ptr<CachedCloud>> kf_cache;
+  DevBuf<float4> sub_concat;
+  DevBuf<unsigned char> sub_meta;
+  PinBuf<unsigned char> sub_meta_h;
 
   // VGICP: last registration (for getFitnessScore)
   size_t last_ns = 0;
@@ -432,6 +441,100 @@ extern "C" int pcr_voxel_downsample_device(pcr_ctx* c, const void* dev_pts, size
   PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   PCR_CUDA_CHECK(cudaGetLastError());
   return PCR_OK;
+  PCR_API_END(c)
+}
+
+// ---- submap assembly (MapManager::updateMap / loopFindNearKeyframes) ------------------------------------------------
+struct SubmapPart {
+  const float4* src;
+  unsigned long long offset;  // first output record of this cloud
+  unsigned long long n;
+  float T[12];                // rows of the float 3x4 [R | t]
+};
+
+__global__ void __launch_bounds__(256) submap_transform_kernel(const SubmapPart* __restrict__ parts, int n_parts, size_t total,
+                                                               float4* __restrict__ out) {
+  extern __shared__ unsigned long long s_off[];  // n_parts + 1 offsets
+  for (int k = threadIdx.x; k <= n_parts; k += blockDim.x) s_off[k] = k < n_parts ? parts[k].offset : (unsigned long long)total;
+  __syncthreads();
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  int lo = 0, hi = n_parts - 1;  // last part whose offset <= i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (s_off[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  const SubmapPart& pt = parts[lo];
+  const float4 p = __ldg(pt.src + (i - pt.offset));
+  // pcp::transformPointCloud: pto = tr * pfrom with tr = pose.cast<float>()  ->  ((r0 x + r1 y) + r2 z) + t, intensity kept
+  float4 o;
+  o.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pt.T[0], p.x), __fmul_rn(pt.T[1], p.y)), __fmul_rn(pt.T[2], p.z)), pt.T[3]);
+  o.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pt.T[4], p.x), __fmul_rn(pt.T[5], p.y)), __fmul_rn(pt.T[6], p.z)), pt.T[7]);
+  o.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(pt.T[8], p.x), __fmul_rn(pt.T[9], p.y)), __fmul_rn(pt.T[10], p.z)), pt.T[11]);
+  o.w = p.w;
+  out[i] = o;
+}
+
+extern "C" int pcr_submap_cache_clear(pcr_ctx* c) {
+  if (!c) return PCR_ERR_INVALID;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->kf_cache.clear();
+  return PCR_OK;
+}
+
+extern "C" int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const size_t* counts, size_t n_clouds, size_t stride,
+                                const double* poses, float leaf, void* out, size_t cap, size_t* m) {
+  PCR_API_BEGIN(c)
+  if (!m || !(leaf > 0.f) || stride < 12 || stride % 4 || (n_clouds && (!clouds || !counts || !poses))) return fail(c, PCR_ERR_INVALID, "bad arguments");
+  *m = 0;
+  SubmapPart* hp = reinterpret_cast<SubmapPart*>(c->sub_meta_h.ensure((n_clouds + 1) * sizeof(SubmapPart)));
+  size_t total = 0, np = 0;
+  for (size_t k = 0; k < n_clouds; k++) {
+    if (counts[k] == 0) continue;
+    if (!clouds[k]) return fail(c, PCR_ERR_INVALID, "null keyframe cloud");
+    auto key = std::make_pair(clouds[k], counts[k]);
+    auto it = c->kf_cache.find(key);
+    if (it == c->kf_cache.end()) {
+      std::unique_ptr<pcr_ctx::CachedCloud> cc(new pcr_ctx::CachedCloud());
+      cc->n = counts[k];
+      upload_points(c, clouds[k], counts[k], stride, c->raw_src, cc->pts);
+      // raw_src is reused by the next upload: the pack kernel of this one is already queued on the same stream
+      it = c->kf_cache.emplace(key, std::move(cc)).first;
+    }
+    SubmapPart& p = hp[np++];
+    p.src = it->second->pts.p;
+    p.offset = total;
+    p.n = counts[k];
+    const double* T = poses + k * 16;
+    for (int r = 0; r < 3; r++) {
+      p.T[r * 4 + 0] = float(T[r]); p.T[r * 4 + 1] = float(T[4 + r]); p.T[r * 4 + 2] = float(T[8 + r]); p.T[r * 4 + 3] = float(T[12 + r]);
+    }
+    total += counts[k];
+  }
+  c->has_target = false;
+  c->has_last = false;
+  c->n_target = 0;
+  if (total == 0) {  // empty submap: registered as an empty target
+    c->dst.ensure(1);
+    return build_target(c, c->dst.p, 0);
+  }
+  c->sub_meta.ensure(np * sizeof(SubmapPart));
+  PCR_CUDA_CHECK(cudaMemcpyAsync(c->sub_meta.p, hp, np * sizeof(SubmapPart), cudaMemcpyHostToDevice, c->stream));
+  c->sub_concat.ensure(total);
+  submap_transform_kernel<<<unsigned((total + 255) / 256), 256, (np + 1) * sizeof(unsigned long long), c->stream>>>(
+      reinterpret_cast<const SubmapPart*>(c->sub_meta.p), int(np), total, c->sub_concat.p);
+  c->ds_out.ensure(total * 32);
+  size_t mm = 0;
+  int rc = downsample_packed(c, c->sub_concat.p, total, leaf, c->ds_out.p, total, &mm);
+  if (rc) return rc;
+  if (out) {
+    if (mm > cap) return fail(c, PCR_ERR_INVALID, "output capacity too small");
+    PCR_CUDA_CHECK(cudaMemcpyAsync(out, c->ds_out.p, mm * 32, cudaMemcpyDeviceToHost, c->stream));
+  }
+  *m = mm;
+  const float4* d = adopt_points(c, c->ds_out.p, mm, 32, c->dst);
+  return build_target(c, d, mm);
   PCR_API_END(c)
 }
 

@@ -1,0 +1,221 @@
+"""Headless restatement of the callers either side of the PCR hot path, without ROS and
+without threads, over the C ABI:
+
+  * frontend::LidarOdometry::generateOdom      frontend/src/LidarOdometry.cpp:89-246
+  * frontend::MapManager::{setCurPose, putKeyFrame, updateMap}   frontend/src/MapManager.cpp:109-201
+  * geometry::trans::SixDof2Mobile             common/geometry/trans.hpp:68-86
+  * backend::LoopClosureManager::{loopFindNearKeyframes, lcHandler verification}   backend/src/LoopClosureManager.cpp:40-119
+
+The data-parallel work stays on the GPU: per-frame voxel downsample (pcr_voxel_downsample), submap assembly
+(pcr_submap_build: transform + concat + downsample on the device, the result IS the register's target, so the submap
+never crosses PCIe), registration (pcr_align against the resident submap), loop-closure VGICP + fitness.
+
+Threading model. The reference rebuilds the submap on its own thread whenever the pose moved more than 1 m
+(`notifyUpdateMap`) while the LO thread keeps registering against the old one; which frame first sees the new submap
+depends on thread timing. Here the rebuild runs synchronously at the end of the frame that requested it — the
+deterministic limit of the reference's behaviour (its offline `USE_BAG` mode with a fast map thread).
+Keyframe radius results are taken in ascending keyframe index (nanoflann's unsorted radius search returns tree order).
+"""
+import numpy as np
+from . import capi
+
+MIN_KF_GAP = 1.0          # MapManager::minKFGap / LidarOdometry::minKFGap (MapManager.hpp:67, LidarOdometry.hpp:52)
+SUBMAP_RADIUS = 8.0       # MapManager::mSurroundingKeyframeSearchRadius (MapManager.hpp:68)
+
+
+def rot_to_quat(R):
+    """Eigen::Quaternion(Matrix3) (w, x, y, z)"""
+    t = R[0, 0] + R[1, 1] + R[2, 2]
+    if t > 0:
+        s = np.sqrt(t + 1.0)
+        w = 0.5 * s
+        s = 0.5 / s
+        return np.array([w, (R[2, 1] - R[1, 2]) * s, (R[0, 2] - R[2, 0]) * s, (R[1, 0] - R[0, 1]) * s])
+    i = 0
+    if R[1, 1] > R[0, 0]:
+        i = 1
+    if R[2, 2] > R[i, i]:
+        i = 2
+    j, k = (i + 1) % 3, (i + 2) % 3
+    s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0)
+    q = np.zeros(4)
+    q[1 + i] = 0.5 * s
+    s = 0.5 / s
+    q[0] = (R[k, j] - R[j, k]) * s
+    q[1 + j] = (R[j, i] + R[i, j]) * s
+    q[1 + k] = (R[k, i] + R[i, k]) * s
+    return q
+
+
+def six_dof_to_mobile(T):
+    """geometry::trans::SixDof2Mobile (trans.hpp:68-86): keep x, y and the rotation about +-z (if the rotation axis is
+    within ~18 deg of z, else drop the rotation)."""
+    q = rot_to_quat(T[:3, :3])
+    n = np.linalg.norm(q[1:])
+    if n > 0:  # Eigen::AngleAxis(Quaternion)
+        angle = 2.0 * np.arctan2(n, abs(q[0]))
+        if q[0] < 0:
+            n = -n
+        axis = q[1:] / n
+    else:
+        angle, axis = 0.0, np.array([1.0, 0.0, 0.0])
+    res = np.eye(4)
+    res[:2, 3] = T[:2, 3]
+    tmp = axis[2]
+    if abs(tmp) > 0.95:
+        a = angle
+        sz = np.copysign(1.0, tmp)
+        c, s = np.cos(a), np.sin(a) * sz
+        res[:3, :3] = [[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]]
+    return res
+
+
+class MapManager:
+    """keyframes + submap (frontend/src/MapManager.cpp). The submap lives on the device as the register's target."""
+
+    def __init__(self, ctx, grid_size=0.5, is_mapping=True):
+        self.ctx = ctx
+        self.grid_size = float(grid_size)
+        self.is_mapping = is_mapping
+        self.keyframes = []          # list of (cloud (n, 8) float32 C-contiguous, pose 4x4)
+        self.closest_kf_idx = []
+        self.submap_idx = []
+        self.submap_size = 0
+        self.cur_pose = np.eye(4)
+        self.last_pose = np.eye(4)
+        self.update_requested = False
+        self.n_updates = 0
+
+    def isSubmapEmpty(self):
+        return len(self.submap_idx) == 0
+
+    def notifyUpdateMap(self):
+        self.update_requested = True
+
+    def setCurPose(self, p):  # MapManager.cpp:109-119
+        self.cur_pose = p.copy()
+        if np.linalg.norm(self.last_pose[:3, 3] - p[:3, 3]) > MIN_KF_GAP:
+            self.last_pose = p.copy()
+            self.notifyUpdateMap()
+
+    def putKeyFrame(self, cloud, pose):  # MapManager.cpp:122-149
+        if not self.is_mapping:
+            return False
+        cloud = np.ascontiguousarray(cloud, dtype=np.float32)
+        if not self.keyframes:
+            self.keyframes.append((cloud, pose.copy()))
+            return True
+        pos = np.array([kf[1][:3, 3] for kf in self.keyframes])
+        d2 = np.sum((pos - pose[:3, 3]) ** 2, axis=1)
+        k = int(np.argmin(d2))
+        if d2[k] > MIN_KF_GAP:  # the reference compares the SQUARED distance with minKFGap (:141)
+            self.keyframes.append((cloud, pose.copy()))
+            self.closest_kf_idx.append(k)
+            return True
+        return False
+
+    def updateMap(self):  # MapManager.cpp:151-201
+        self.update_requested = False
+        if not self.keyframes:
+            return
+        pos = np.array([kf[1][:3, 3] for kf in self.keyframes])
+        d2 = np.sum((pos - self.cur_pose[:3, 3]) ** 2, axis=1)
+        idx = [int(i) for i in np.nonzero(d2 < SUBMAP_RADIUS * SUBMAP_RADIUS)[0]]  # nanoflann radius search: d2 < r^2
+        self.submap_idx = idx
+        _, self.submap_size = self.ctx.submap_build([self.keyframes[i][0] for i in idx], [self.keyframes[i][1] for i in idx], self.grid_size,
+                                                    want_points=False)
+        self.n_updates += 1
+
+
+class LidarOdometry:
+    """frontend::LidarOdometry (frontend/src/LidarOdometry.cpp) fed frame by frame."""
+
+    def __init__(self, pcr_type="loam", grid_size=0.5, device=0, **params):
+        method = {"loam": capi.PCR_LOAM, "ndt": capi.PCR_NDT, "vgicp": capi.PCR_VGICP}.get(pcr_type)
+        if method is None:
+            raise RuntimeError("such pcr type(%s) is not exist, please implemented your self!" % pcr_type)
+        self.ctx = capi.Context(method, device=device, **params)
+        self.grid_size = float(grid_size)
+        self.map = MapManager(self.ctx, grid_size)
+        self.last_pos = np.zeros(3)
+        self.reloc_pose = np.eye(4)
+        self.reloc = False
+        self.global_odom = []        # list of (stamp, pose)
+        self.odom2map = np.eye(4)
+        self.odom2map_init = False
+        self.converged = []
+
+    def setRelocFlag(self, pose):
+        self.reloc_pose = pose.copy()
+        self.reloc = True
+
+    def generateOdom(self, scan, stamp, local_odom=None):
+        """one frame: raw scan (n, 8) float32, stamp (s), local odometry pose (4x4) or None. Returns the global pose."""
+        init_pose = self.reloc_pose.copy()
+        if self.reloc:
+            self.reloc = False
+            self.global_odom = []
+        elif local_odom is not None and self.odom2map_init:
+            init_pose = self.odom2map @ local_odom
+        else:
+            n = len(self.global_odom)
+            if n:  # Frontend::getClosestItem: walk back from the newest while the stamp distance shrinks
+                cidx, m = n - 1, abs(stamp - self.global_odom[-1][0])
+                for i in range(n - 2, -1, -1):
+                    t = abs(self.global_odom[i][0] - stamp)
+                    if t < m:
+                        m, cidx = t, i
+                    else:
+                        break
+                if cidx > 0:
+                    init_pose = self.global_odom[cidx][1].copy()
+        conv = True
+        if not self.map.isSubmapEmpty():
+            ds = self.ctx.voxel_downsample(scan, self.grid_size)       # mVoxelGrid.filter (:170-171)
+            init_pose, conv = self.ctx.align(ds, init_pose)            # mPcr->scan2Map against the resident submap (:184)
+        self.converged.append(bool(conv))
+        init_pose = six_dof_to_mobile(init_pose)                       # :211
+        self.map.setCurPose(init_pose)
+        if self.map.isSubmapEmpty():
+            self.map.putKeyFrame(scan, init_pose)
+            self.map.notifyUpdateMap()
+        else:  # selectKeyFrame (:81-87)
+            if np.linalg.norm(init_pose[:3, 3] - self.last_pos) > MIN_KF_GAP:
+                self.map.putKeyFrame(scan, init_pose)
+                self.last_pos = init_pose[:3, 3].copy()
+        self.global_odom.append((stamp, init_pose.copy()))
+        if local_odom is not None:
+            self.odom2map_init = True
+            self.odom2map = init_pose @ np.linalg.inv(local_odom)
+        if self.map.update_requested:   # the map thread, run synchronously (module docstring)
+            self.map.updateMap()
+        return init_pose
+
+    def close(self):
+        self.ctx.close()
+
+
+class LoopClosureVerifier:
+    """Verification half of backend::LoopClosureManager::lcHandler (LoopClosureManager.cpp:73-110): for a candidate pair
+    (oldKey, curKey) build the history submap of oldKey (+-range keyframes, transformed, 0.5 m downsample), register the
+    current keyframe's cloud with VGICP in loop-closure mode from its own pose, accept iff converged and fitness < thresh."""
+
+    def __init__(self, keyframes, context_pc_ds=0.5, history_submap_range=1, fitness_score=0.3, device=0):
+        self.keyframes = keyframes
+        self.ds = float(context_pc_ds)
+        self.range = int(history_submap_range)
+        self.thresh = float(fitness_score)
+        self.ctx = capi.Context(capi.PCR_VGICP, device=device)
+        self.ctx.init_for_lc()
+
+    def verify(self, old_key, cur_key):
+        n = len(self.keyframes)
+        near = [k for k in range(old_key - self.range, old_key + self.range + 1) if 0 <= k < n]
+        _, m = self.ctx.submap_build([self.keyframes[k][0] for k in near], [self.keyframes[k][1] for k in near], self.ds, want_points=False)
+        cloud, pose = self.keyframes[cur_key]
+        T, conv = self.ctx.align(cloud, pose)
+        fs = self.ctx.fitness()
+        return dict(old=old_key, cur=cur_key, converged=bool(conv), fitness=fs, accepted=bool(conv and fs < self.thresh), T=T, map_points=m)
+
+    def close(self):
+        self.ctx.close()

@@ -115,6 +115,40 @@ def c4_batched(method, downsample, n_scans, seed_offset=0, tiles=4, spacing=0.24
     return dict(name=name, method=method, dst=dst, scans=scans, truths=truths, guesses=guesses, raw_map_points=n_raw)
 
 
+def c5_sequence(n_frames, sensor="vlp16", speed=5.0, rate=10.0, seed_offset=0):
+    """C5 offline LIO sequence: a figure-8 (lemniscate, ~75 m lobes) driven at `speed` m/s and sampled at `rate` Hz through
+    the 2x2-tile world; per frame a raw scan in the sensor frame, a stamp, the ground-truth pose in the map frame (= first
+    sensor frame) and a local odometry pose (truth + accumulated wheel/IMU-like noise: 5 mm, 0.02 deg per step)."""
+    sc = synth.Scene(seed=SEED, tiles=(2, 2))
+    step = speed / rate
+    a = 75.0
+    # arc-length parametrisation by dense sampling of x = a cos t / (1 + sin^2 t), y = a sin t cos t / (1 + sin^2 t)
+    tt = np.linspace(0.0, 2 * np.pi, 200001)
+    px = 200.0 + a * np.cos(tt) / (1 + np.sin(tt) ** 2)
+    py = 200.0 + a * np.sin(tt) * np.cos(tt) / (1 + np.sin(tt) ** 2)
+    seg = np.concatenate([[0.0], np.cumsum(np.hypot(np.diff(px), np.diff(py)))])
+    total = seg[-1]
+    frames, T0inv, odom = [], None, np.eye(4)
+    rng = np.random.RandomState(77 + seed_offset)
+    prev_truth = None
+    for k in range(n_frames):
+        sdist = (k * step) % total
+        i = int(np.searchsorted(seg, sdist))
+        i = min(max(i, 1), len(tt) - 1)
+        yaw = np.arctan2(py[i] - py[i - 1], px[i] - px[i - 1])
+        T = sc.free_pose_near(px[i], py[i], 2.0, yaw, step=0.5)
+        if T0inv is None:
+            T0inv = np.linalg.inv(T)
+        truth = T0inv @ T
+        if prev_truth is not None:
+            noise = synth.se3_exp(np.concatenate([rng.normal(0, 0.005, 3) * [1, 1, 0], np.deg2rad(rng.normal(0, 0.02, 3)) * [0, 0, 1]]))
+            odom = odom @ (np.linalg.inv(prev_truth) @ truth) @ noise
+        prev_truth = truth
+        scan = np.ascontiguousarray(sc.scan(T, sensor, seed=20000 + k + 100000 * seed_offset))
+        frames.append(dict(scan=scan, stamp=k / rate, truth=truth, local_odom=odom.copy()))
+    return dict(name="C5 offline LIO mapping: %d-frame %s figure-8 at %.0f m/s, %.0f Hz" % (n_frames, sensor, speed, rate), frames=frames)
+
+
 def shard(n_items, rank, world):
     """contiguous block partition of n_items over `world` ranks (scans i -> contiguous blocks)"""
     base, rem = divmod(n_items, world)
