@@ -9,7 +9,7 @@ WLS=${2:-"c2_ndt c1_loam c3_vgicp c4_loam c4_ndt"}
 STEPS=${STEPS:-4}
 mkdir -p gpurun_out
 declare -A KERN=( [c2_ndt]=ndt_eval_kernel [c4_ndt]=ndt_eval_kernel [c1_loam]=loam_iter_kernel [c4_loam]=loam_iter_kernel [c3_vgicp]=gicp_knn_kernel )
-declare -A SKIP=( [c2_ndt]=40 [c4_ndt]=40 [c1_loam]=10 [c4_loam]=9 [c3_vgicp]=8 )
+declare -A SKIP=( [c2_ndt]=40 [c4_ndt]=40 [c1_loam]=10 [c4_loam]=10 [c3_vgicp]=8 )
 for wl in $WLS; do
   python bench.py --workload $wl --steps $STEPS --warmup 3 > gpurun_out/bench_${ROUND}_$wl.json 2> gpurun_out/bench_${ROUND}_$wl.err || { echo "bench $wl failed"; tail -5 gpurun_out/bench_${ROUND}_$wl.err; continue; }
   ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${ROUND}_$wl.csv \

@@ -43,12 +43,18 @@ __device__ __forceinline__ Cand cand_sel(bool p, const Cand& a, const Cand& b) {
 __constant__ signed char c_row_dy[25] = {0, 1, -1, 0, 0, 1, 1, -1, -1, 2, -2, 0, 0, 2, 2, -2, -2, 1, -1, 1, -1, 2, 2, -2, -2};
 __constant__ signed char c_row_dz[25] = {0, 0, 0, 1, -1, 1, -1, 1, -1, 0, 0, 2, -2, 1, -1, 1, -1, 2, 2, -2, -2, 2, -2, 2, -2};
 
-template <int LPQ, bool DEBUG>
-__global__ void __launch_bounds__(kLoamBlock, 2)
+// MODE 0: fused iteration (search + fit + solve) — small problems, one launch per iteration keeps the latency short.
+// MODE 1: search only: no shared-memory accumulators, half the registers -> twice the resident warps to hide the
+//         dependent load chains of the neighbour search; the five winners (+ counters) of every query go to `knn_buf`
+//         (seven int planes of `knn_stride` entries).   MODE 2: fit + solve from `knn_buf`. Large batches run 1 then 2.
+constexpr int kModeFused = 0, kModeSearch = 1, kModeFit = 2;
+
+template <int LPQ, bool DEBUG, int MODE>
+__global__ void __launch_bounds__(kLoamBlock, MODE == kModeSearch ? 4 : 2)
 loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, GridView grid, LoamParams prm,
                  LoamState* __restrict__ states, double* __restrict__ partials, int max_blocks,
                  pcr_loam_iter_log* __restrict__ logs, int apply_update, int tile, double slack, int max_ring,
-                 int32_t* __restrict__ dbg_knn, int32_t* __restrict__ dbg_status) {
+                 int32_t* __restrict__ dbg_knn, int32_t* __restrict__ dbg_status, int32_t* __restrict__ knn_buf, size_t knn_stride) {
   // LPQ = lanes co-operating on one query, G = 32 / LPQ queries searched concurrently by a warp.
   // `tile` (multiple of G, <= 32) = queries a warp owns per pass: 32 for throughput on large batches, smaller when there
   // are too few queries to fill the machine (a single scan), trading phase-2 lane utilisation for shorter latency chains.
@@ -68,8 +74,10 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
   __shared__ double stot[kNV];
   __shared__ int s_last;
   if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
+  if (MODE != kModeSearch) {
 #pragma unroll
-  for (int k = 0; k < kNV; k++) sacc[k * kLoamBlock + threadIdx.x] = 0.0;
+    for (int k = 0; k < kNV; k++) sacc[k * kLoamBlock + threadIdx.x] = 0.0;
+  }
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -107,9 +115,16 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     int wj[5] = {-1, -1, -1, -1, -1};  // cell-sorted positions of my query's five nearest neighbours
     int my_ncand = 0, my_nrows = 0;
 
+    if (MODE == kModeFit && have) {  // winners of the search kernel
+#pragma unroll
+      for (int q = 0; q < 5; q++) wj[q] = knn_buf[size_t(q) * knn_stride + i];
+      my_ncand = knn_buf[5 * knn_stride + i];
+      my_nrows = knn_buf[6 * knn_stride + i];
+    }
+
     // ---- phase 1: G queries of the tile are searched per round, LPQ lanes each
-    const unsigned todo = __ballot_sync(FULL, have && near);
-    const int rounds = (tile + G - 1) / G;
+    const unsigned todo = MODE == kModeFit ? 0u : __ballot_sync(FULL, have && near);
+    const int rounds = MODE == kModeFit ? 0 : (tile + G - 1) / G;
     for (int r = 0; r < rounds; r++) {
       const unsigned round_bits = (G == 32 ? todo : ((todo >> (r * G)) & ((1u << G) - 1u)));
       if (round_bits == 0) continue;  // warp-uniform
@@ -235,6 +250,16 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
       if (lane / G == r) { my_ncand = nc; my_nrows = nr; }
     }
 
+    if (MODE == kModeSearch) {
+      if (have) {
+#pragma unroll
+        for (int q = 0; q < 5; q++) knn_buf[size_t(q) * knn_stride + i] = wj[q];
+        knn_buf[5 * knn_stride + i] = my_ncand;
+        knn_buf[6 * knn_stride + i] = my_nrows;
+      }
+      continue;
+    }
+
     // ---- phase 2: one query per lane
     if (have) {
       int status = 0;
@@ -303,6 +328,8 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
       if (DEBUG && dbg_status) dbg_status[i] = status;
     }
   }
+
+  if (MODE == kModeSearch) return;
 
   // ---- block reduction straight out of shared memory, fixed order: warp w owns components w, w+8, ...
   __syncthreads();
@@ -425,7 +452,7 @@ __global__ void loam_finalize_kernel(LoamState* states, int n_scans) {
 
 template <int LPQ, bool DEBUG>
 static void opt_in_one() {
-  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<LPQ, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
+  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<LPQ, DEBUG, kModeFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
 }
 static void loam_opt_in_smem() {
   static bool done_dev[64] = {false};
@@ -435,6 +462,7 @@ static void loam_opt_in_smem() {
   if (done) return;
   opt_in_one<1, false>(); opt_in_one<2, false>(); opt_in_one<4, false>(); opt_in_one<8, false>();
   opt_in_one<1, true>(); opt_in_one<2, true>(); opt_in_one<4, true>(); opt_in_one<8, true>();
+  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<1, false, kModeFit>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
   done = true;
 }
 
@@ -461,9 +489,9 @@ template <bool DEBUG>
 static void launch_iter(int lpq, dim3 grid, cudaStream_t s, const float4* src, const uint32_t* offs, const GridView& view, const LoamParams& prm,
                         LoamState* states, double* partials, int max_blocks, pcr_loam_iter_log* logs, int apply, int tile, double slack,
                         int max_ring, int32_t* dbg_knn, int32_t* dbg_status) {
-#define PCR_LOAM_LAUNCH(L)                                                                                                          \
-  loam_iter_kernel<L, DEBUG><<<grid, kLoamBlock, kLoamDynSmem, s>>>(src, offs, view, prm, states, partials, max_blocks, logs, apply, tile, \
-                                                                    slack, max_ring, dbg_knn, dbg_status)
+#define PCR_LOAM_LAUNCH(L)                                                                                                                      \
+  loam_iter_kernel<L, DEBUG, kModeFused><<<grid, kLoamBlock, kLoamDynSmem, s>>>(src, offs, view, prm, states, partials, max_blocks, logs, apply, tile, \
+                                                                                slack, max_ring, dbg_knn, dbg_status, nullptr, 0)
   switch (lpq) {
     case 1: PCR_LOAM_LAUNCH(1); break;
     case 2: PCR_LOAM_LAUNCH(2); break;
@@ -532,10 +560,23 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     if (!ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
     PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
   }
+  // large batches (one lane per query, full tiles): search and fit as two kernels per iteration, see kModeSearch
+  const bool split = lpq == 1 && tile == 32 && env_int("PCR_LOAM_SPLIT", 1) != 0;
   if (grid.built && grid.has_start && max_pts > 0) {
+    if (split) knn_buf.ensure(7 * total_q);
+    const size_t search_pb = size_t(kLoamWarps) * 32;
+    const dim3 sgrid(unsigned((max_pts + search_pb - 1) / search_pb), unsigned(n_scans));
     for (int it = 0; it < prm.max_iters; it++) {
-      launch_iter<false>(lpq, gridDim, s, src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 1, tile, slack, grid.max_ring, nullptr, nullptr);
-      launches++;
+      if (split) {
+        loam_iter_kernel<1, false, kModeSearch><<<sgrid, kLoamBlock, 0, s>>>(src, offsets.p, view, prm, states.p, partials.p, int(sgrid.x), logs.p, 1, 32,
+                                                                            slack, grid.max_ring, nullptr, nullptr, knn_buf.p, total_q);
+        loam_iter_kernel<1, false, kModeFit><<<gridDim, kLoamBlock, kLoamDynSmem, s>>>(src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 1,
+                                                                                      32, slack, grid.max_ring, nullptr, nullptr, knn_buf.p, total_q);
+        launches += 2;
+      } else {
+        launch_iter<false>(lpq, gridDim, s, src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 1, tile, slack, grid.max_ring, nullptr, nullptr);
+        launches++;
+      }
       hot_launches++;
     }
   }

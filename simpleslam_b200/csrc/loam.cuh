@@ -32,6 +32,7 @@ struct LoamDriver {
   DevBuf<pcr_loam_iter_log> logs;
   DevBuf<uint32_t> offsets;
   DevBuf<int32_t> dbg_knn, dbg_status;
+  DevBuf<int32_t> knn_buf;  // split mode: 5 winners + 2 counters per query (seven planes)
   PinBuf<LoamState> h_states;
   PinBuf<uint32_t> h_offsets;
   PinBuf<pcr_loam_iter_log> h_logs;
