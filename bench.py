@@ -62,54 +62,99 @@ def algo_bytes_examined(method, point_evals, index_reads, pairs):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line), every 200 ms, through
+    NVML in a background thread (same counters as `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`;
+    an in-process NVML query disturbs the measured CUDA calls less than an nvidia-smi poller). Falls back to nvidia-smi."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, index):
-        self.rows = []
+    def __init__(self, index, enabled=True):
+        self.rows = []      # (sm_mhz, max_mhz, reasons bitmask)
         self.proc = None
+        self.mode = None
+        self._stop = threading.Event()
+        if not enabled:   # only rank 0 reports clocks; extra pollers just contend for the driver lock
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
+            self.mode = "smi"
+            self.t = threading.Thread(target=self._read_smi, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((sm, self.mx, rs))
+            except Exception:
+                pass
+            self._stop.wait(0.2)
 
-    def wait_samples(self, n=1, timeout=6.0):
-        """nvidia-smi needs ~1 s to emit its first row: block until n rows are in (or the timeout passes)"""
-        t0 = time.perf_counter()
-        while self.proc and len(self.rows) < n and time.perf_counter() - t0 < timeout:
-            time.sleep(0.05)
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+    def _read_smi(self):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm, mx = float(f[0]), float(f[1])
             except ValueError:
                 continue
+            rs = 0
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                    rs |= self.BITS[n]
+            self.rows.append((sm, mx, rs))
+
+    def wait_samples(self, n=1, timeout=6.0):
+        """the first sample takes a moment: block until n rows are in (or the timeout passes)"""
+        if not self.mode:
+            return
+        t0 = time.perf_counter()
+        while len(self.rows) < n and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
+    def stop(self):
+        if not self.mode:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable (not rank 0, or no NVML / nvidia-smi)"], "samples": 0}
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        bits = 0
+        for r in self.rows:
+            bits |= r[2]
+        reasons = sorted(n for n, b in self.BITS.items() if bits & b)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "source": self.mode}
 
 
 def build_workload(name, downsample, n_scans, seed_offset):
@@ -210,7 +255,7 @@ def run_c5(args, rank, world, local_rank):
     frames = seq["frames"]
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
     scans = [pin(f["scan"]) for f in frames]
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))
 
     def run_once(profile):
         lo = frontend.LidarOdometry(args.pcr, device=local_rank)
@@ -359,7 +404,7 @@ def run_ours(args, rank, world, local_rank):
         return Ts, convs, Tt
 
     ctx.set_profiling(True)
-    sampler = ClockSampler(local_rank)  # started before warm-up: nvidia-smi needs ~1 s to produce its first sample
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))  # started before warm-up: nvidia-smi needs ~1 s to produce its first sample
     for k in range(args.warmup):
         resident_step(k)
     sampler.wait_samples(1)
@@ -445,7 +490,7 @@ def run_ours(args, rank, world, local_rank):
                 ctx.align(hs, Tg)
                 e2e_cached_t.append(time.perf_counter() - t0)
     t_e2e = float(np.sum(e2e_t))
-    if len(sampler.rows) < 3:  # very short runs: keep the GPU busy with the same resident steps until three samples are in
+    if sampler.mode and len(sampler.rows) < 3:  # very short runs: keep the GPU busy with the same resident steps until three samples are in
         t_end = time.perf_counter() + 3.0
         while len(sampler.rows) < 3 and time.perf_counter() < t_end:
             resident_step(args.warmup)
