@@ -12,7 +12,7 @@ declare -A KERN=( [c2_ndt]=ndt_eval_kernel [c4_ndt]=ndt_eval_kernel [c1_loam]=lo
 declare -A SKIP=( [c2_ndt]=40 [c4_ndt]=40 [c1_loam]=10 [c4_loam]=10 [c3_vgicp]=8 )
 for wl in $WLS; do
   python bench.py --workload $wl --steps $STEPS --warmup 3 > gpurun_out/bench_${ROUND}_$wl.json 2> gpurun_out/bench_${ROUND}_$wl.err || { echo "bench $wl failed"; tail -5 gpurun_out/bench_${ROUND}_$wl.err; continue; }
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${ROUND}_$wl.csv \
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_${ROUND}_$wl.csv \
       python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_${ROUND}_$wl.log 2>&1
   k=${KERN[$wl]}
   ncu --set full --clock-control none --import-source on -k regex:$k --launch-skip ${SKIP[$wl]} --launch-count 1 -f \

@@ -30,7 +30,7 @@ ndt_leaf_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ key
   double cxx = 1, cxy = 0, cxz = 0, cyy = 1, cyz = 0, czz = 1;
   float fx = 0.f, fy = 0.f, fz = 0.f;
   for (uint32_t j = b; j < e; j++) {
-    const float4 p = __ldg(pts + vals[j]);
+    const float4 p = __ldg(pts + j);  // `pts` is gathered into key order: a leaf is one contiguous run
     const double x = p.x, y = p.y, z = p.z;
     sx += x; sy += y; sz += z;
     cxx += x * x; cxy += x * y; cxz += x * z; cyy += y * y; cyz += y * z; czz += z * z;  // exact products
@@ -135,7 +135,8 @@ int ndt_build_target(const float4* pts, size_t n, const pcr_params& prm, NdtTarg
   tgt.centroids.ensure(L);
   tgt.table.ensure(size_t(tgt.g.ncell));
   PCR_CUDA_CHECK(cudaMemsetAsync(tgt.table.p, 0xff, size_t(tgt.g.ncell) * sizeof(int32_t), s));
-  ndt_leaf_kernel<<<unsigned((L + 127) / 128), 128, 0, s>>>(pts, ks.keys, ks.vals, ks.seg_start.p, L, prm.ndt_min_points, prm.ndt_eig_mult,
+  gather_sorted(pts, ks, s);
+  ndt_leaf_kernel<<<unsigned((L + 127) / 128), 128, 0, s>>>(ks.sorted_pts.p, ks.keys, ks.vals, ks.seg_start.p, L, prm.ndt_min_points, prm.ndt_eig_mult,
                                                            tgt.recs.p, tgt.keys.p, tgt.npts.p, tgt.mean.p, tgt.cov.p, tgt.icov.p,
                                                            tgt.table.p, tgt.centroids.p);
   PCR_CUDA_CHECK(cudaGetLastError());

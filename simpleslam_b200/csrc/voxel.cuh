@@ -19,6 +19,7 @@ bool make_grid_spec(const float mn[3], const float mx[3], float leaf, GridSpec& 
 // (key, original index) pairs sorted by key, stable => ascending original index inside a voxel.
 struct KeySort {
   DevBuf<uint32_t> k0, k1, v0, v1, seg_start;
+  DevBuf<float4> sorted_pts;          // points gathered into key order (centroid pass)
   DevBuf<unsigned char> tmp;
   DevBuf<unsigned> d_count;
   PinBuf<unsigned> h_count;
@@ -37,7 +38,9 @@ struct KeySort {
 
 // pcl::VoxelGrid centroid per segment: float32 sums in ascending original index, / count.
 // out32: 32-byte PointXYZI records.
-void voxel_centroids(const float4* pts, const KeySort& ks, void* dev_out32, cudaStream_t s);
+void voxel_centroids(const float4* pts, KeySort& ks, void* dev_out32, cudaStream_t s);
+// ks.sorted_pts[i] = pts[ks.vals[i]]: the points in key order (ascending original index inside a voxel)
+void gather_sorted(const float4* pts, KeySort& ks, cudaStream_t s);
 
 // Uniform grid over a cloud for neighbour search.
 struct CellGrid {
