@@ -869,6 +869,7 @@ extern "C" int pcr_vgicp_evaluate(pcr_ctx* c, const void* src, size_t ns, size_t
   PCR_API_BEGIN(c)
   if (c->prm.method != PCR_VGICP || !c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no VGICP target");
   const float4* d = upload_points(c, src, ns, stride, c->raw_src, c->src);
+  c->has_last = false;  // c->src no longer holds the last aligned scan (getFitnessScore needs a new scan2Map)
   int rc = c->vgd.compute_source_covs(d, ns, c->prm.vgicp_k, c->ks, c->bw, c->stream);
   if (rc) return fail(c, rc, "source covariance build failed");
   uint32_t* ho = c->vgd.h_offsets.ensure(2);
