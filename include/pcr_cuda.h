@@ -156,6 +156,19 @@ int pcr_target_blob_size(pcr_ctx* c, size_t* bytes);
 int pcr_target_export(pcr_ctx* c, void* dev_blob, size_t cap);
 int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes);
 
+/* On-disk index cache: the built target index (the same blob pcr_target_export produces) written to /
+ * read from a file, so that the localisation mode (test/loc.cpp -> MapManager(pcd_file), frontend/src/MapManager.cpp:52-84)
+ * does not re-downsample and re-index its static map at every start. LOAM and NDT contexts. */
+int pcr_target_save(pcr_ctx* c, const char* path);
+int pcr_target_load(pcr_ctx* c, const char* path);
+/* Minimal PCD reader (pcp::loadPCDFile -> pcl::io::loadPCDFile<PointXYZI>, common/pcp/pcp.hpp:71-75): DATA ascii | binary,
+ * float32 fields x y z and optionally intensity (other fields skipped). Writes up to `cap` 32-byte PointXYZI records
+ * (x y z 1 | intensity 0 0 0) to the HOST buffer `out` (NULL: only count); *n = points in the file. Needs no GPU. */
+int pcr_read_pcd(const char* path, void* out, size_t cap, size_t* n);
+/* MapManager(pcd_file) in one call: read the PCD, voxel-downsample at `leaf` (pcp::voxelDownSample, MapManager.cpp:77) and
+ * register the result as the static target. *m = points of the downsampled map. */
+int pcr_static_map_load(pcr_ctx* c, const char* pcd_path, float leaf, size_t* m);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Parity / introspection entry points (used by tests/ to compare every intermediate with the oracle).
  * All output pointers are HOST pointers and may be NULL.

@@ -23,7 +23,7 @@ SYMBOLS = [
     "pcr_target_blob_size", "pcr_target_export", "pcr_target_import", "pcr_debug_voxel", "pcr_loam_linearize",
     "pcr_loam_get_logs", "pcr_ndt_num_leaves", "pcr_ndt_get_leaves", "pcr_ndt_derivatives", "pcr_ndt_hessian",
     "pcr_gicp_covariances", "pcr_vgicp_num_voxels", "pcr_vgicp_get_voxels", "pcr_vgicp_evaluate",
-    "pcr_submap_build", "pcr_submap_cache_clear",
+    "pcr_submap_build", "pcr_submap_cache_clear", "pcr_target_save", "pcr_target_load", "pcr_read_pcd", "pcr_static_map_load",
 ]
 
 
@@ -57,6 +57,35 @@ class Stats(ctypes.Structure):
 class LoamIterLog(ctypes.Structure):
     _fields_ = [("T_before", ctypes.c_double * 16), ("JtJ", ctypes.c_double * 36), ("JtE", ctypes.c_double * 6),
                 ("x", ctypes.c_double * 6), ("n", ctypes.c_int64), ("converged", ctypes.c_int32), ("pad", ctypes.c_int32)]
+
+
+def read_pcd(path):
+    """pcr_read_pcd: (n, 8) float32 PointXYZI records of a PCD file (host only, needs no GPU)"""
+    n = ctypes.c_size_t(0)
+    rc = lib().pcr_read_pcd(str(path).encode(), None, ctypes.c_size_t(0), ctypes.byref(n))
+    if rc != 0:
+        raise PcrError(rc, "cannot read PCD file %s" % path)
+    out = np.empty((max(n.value, 1), 8), np.float32)
+    rc = lib().pcr_read_pcd(str(path).encode(), _vp(out), ctypes.c_size_t(n.value), ctypes.byref(n))
+    if rc != 0:
+        raise PcrError(rc, "truncated PCD file %s" % path)
+    return out[:n.value]
+
+
+def write_pcd(path, pts, binary=True):
+    """test / bench utility: write (n, >=5) float32 PointXYZI records as a PCD v0.7 file (x y z intensity)"""
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    n = len(pts)
+    xyzi = np.ascontiguousarray(np.concatenate([pts[:, :3], pts[:, 4:5]], axis=1))
+    hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\nSIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\n"
+           "WIDTH %d\nHEIGHT 1\nVIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA %s\n" % (n, n, "binary" if binary else "ascii"))
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        if binary:
+            f.write(xyzi.tobytes())
+        else:
+            for r in xyzi:
+                f.write(("%.9g %.9g %.9g %.9g\n" % tuple(float(v) for v in r)).encode())
 
 
 class PcrError(RuntimeError):
@@ -259,6 +288,18 @@ class Context:
 
     def target_import(self, dev_ptr, nbytes):
         self._check(lib().pcr_target_import(self._h, _vp(dev_ptr), ctypes.c_size_t(nbytes)))
+
+    # -- on-disk index cache / static map
+    def target_save(self, path):
+        self._check(lib().pcr_target_save(self._h, str(path).encode()))
+
+    def target_load(self, path):
+        self._check(lib().pcr_target_load(self._h, str(path).encode()))
+
+    def static_map_load(self, pcd_path, leaf):
+        m = ctypes.c_size_t(0)
+        self._check(lib().pcr_static_map_load(self._h, str(pcd_path).encode(), ctypes.c_float(leaf), ctypes.byref(m)))
+        return m.value
 
     # -- parity / introspection
     def loam_linearize(self, src, T):

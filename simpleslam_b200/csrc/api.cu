@@ -8,6 +8,9 @@
 #include "vgicp.cuh"
 #include "host_math.hpp"
 #include <cfloat>
+#include <cstdio>
+#include <fstream>
+#include <sstream>
 #include <map>
 #include <memory>
 #include <string>
@@ -706,6 +709,148 @@ extern "C" int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes)
   PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->has_target = true;
   return PCR_OK;
+  PCR_API_END(c)
+}
+
+// ---- on-disk index cache + PCD reader -----------------------------------------------------------
+namespace {
+struct FileHeader {
+  char magic[8];       // "PCRIDX01"
+  uint64_t blob_bytes;
+};
+}  // namespace
+
+extern "C" int pcr_target_save(pcr_ctx* c, const char* path) {
+  PCR_API_BEGIN(c)
+  if (!path) return fail(c, PCR_ERR_INVALID, "null path");
+  size_t bytes = 0;
+  int rc = pcr_target_blob_size(c, &bytes);
+  if (rc) return rc;
+  DevBuf<unsigned char> blob;
+  blob.ensure(bytes);
+  rc = pcr_target_export(c, blob.p, bytes);
+  if (rc) return rc;
+  std::vector<unsigned char> host(bytes);
+  PCR_CUDA_CHECK(cudaMemcpy(host.data(), blob.p, bytes, cudaMemcpyDeviceToHost));
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return fail(c, PCR_ERR_INVALID, "cannot open index file for writing");
+  FileHeader h;
+  std::memcpy(h.magic, "PCRIDX01", 8);
+  h.blob_bytes = bytes;
+  const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(host.data(), 1, bytes, f) == bytes;
+  std::fclose(f);
+  if (!ok) return fail(c, PCR_ERR_INVALID, "short write of the index file");
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_target_load(pcr_ctx* c, const char* path) {
+  PCR_API_BEGIN(c)
+  if (!path) return fail(c, PCR_ERR_INVALID, "null path");
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return fail(c, PCR_ERR_INVALID, "cannot open index file");
+  FileHeader h;
+  if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "PCRIDX01", 8) != 0) { std::fclose(f); return fail(c, PCR_ERR_INVALID, "not an index file"); }
+  unsigned char* host = c->pin.ensure(h.blob_bytes);
+  const bool ok = std::fread(host, 1, h.blob_bytes, f) == h.blob_bytes;
+  std::fclose(f);
+  if (!ok) return fail(c, PCR_ERR_INVALID, "truncated index file");
+  DevBuf<unsigned char> blob;
+  blob.ensure(h.blob_bytes);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(blob.p, host, h.blob_bytes, cudaMemcpyHostToDevice, c->stream));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return pcr_target_import(c, blob.p, h.blob_bytes);
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_read_pcd(const char* path, void* out, size_t cap, size_t* n) {
+  if (!path || !n) return PCR_ERR_INVALID;
+  *n = 0;
+  std::ifstream in(path, std::ios::binary);
+  if (!in) return PCR_ERR_INVALID;
+  std::vector<std::string> fields, types;
+  std::vector<int> sizes, counts;
+  size_t points = 0;
+  std::string data_kind, line;
+  while (std::getline(in, line)) {  // header: "KEY v1 v2 ..." lines up to DATA
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty() || line[0] == '#') continue;
+    std::istringstream ls(line);
+    std::string key, tok;
+    ls >> key;
+    if (key == "FIELDS") { while (ls >> tok) fields.push_back(tok); }
+    else if (key == "SIZE") { while (ls >> tok) sizes.push_back(std::atoi(tok.c_str())); }
+    else if (key == "TYPE") { while (ls >> tok) types.push_back(tok); }
+    else if (key == "COUNT") { while (ls >> tok) counts.push_back(std::atoi(tok.c_str())); }
+    else if (key == "POINTS") { ls >> points; }
+    else if (key == "DATA") { ls >> data_kind; break; }
+  }
+  const size_t nf = fields.size();
+  if (!nf || sizes.size() != nf || types.size() != nf || (data_kind != "ascii" && data_kind != "binary")) return PCR_ERR_UNSUPPORTED;
+  if (counts.empty()) counts.assign(nf, 1);
+  int off[4] = {-1, -1, -1, -1}, col[4] = {-1, -1, -1, -1};  // byte offset / ascii column of x, y, z, intensity
+  int rec = 0, cols = 0;
+  for (size_t k = 0; k < nf; k++) {
+    const char* want[4] = {"x", "y", "z", "intensity"};
+    for (int w = 0; w < 4; w++)
+      if (fields[k] == want[w]) {
+        if (sizes[k] != 4 || types[k] != "F" || counts[k] != 1) return PCR_ERR_UNSUPPORTED;
+        off[w] = rec; col[w] = cols;
+      }
+    rec += sizes[k] * counts[k];
+    cols += counts[k];
+  }
+  if (off[0] < 0 || off[1] < 0 || off[2] < 0) return PCR_ERR_UNSUPPORTED;
+  *n = points;
+  if (!out) return PCR_OK;
+  float* o = static_cast<float*>(out);
+  const size_t take = std::min(points, cap);
+  if (data_kind == "binary") {
+    std::vector<unsigned char> buf(static_cast<size_t>(rec) * 4096, 0);
+    for (size_t base = 0; base < take; base += 4096) {
+      const size_t m = std::min<size_t>(4096, take - base);
+      in.read(reinterpret_cast<char*>(buf.data()), std::streamsize(m * size_t(rec)));
+      if (size_t(in.gcount()) != m * size_t(rec)) return PCR_ERR_INVALID;
+      for (size_t i = 0; i < m; i++) {
+        const unsigned char* r = buf.data() + i * size_t(rec);
+        float* q = o + (base + i) * 8;
+        std::memcpy(q + 0, r + off[0], 4); std::memcpy(q + 1, r + off[1], 4); std::memcpy(q + 2, r + off[2], 4);
+        q[3] = 1.0f;
+        q[4] = 0.0f;
+        if (off[3] >= 0) std::memcpy(q + 4, r + off[3], 4);
+        q[5] = q[6] = q[7] = 0.0f;
+      }
+    }
+  } else {
+    std::vector<double> v(static_cast<size_t>(cols), 0.0);
+    for (size_t i = 0; i < take; i++) {
+      for (int k = 0; k < cols; k++)
+        if (!(in >> v[size_t(k)])) return PCR_ERR_INVALID;
+      float* q = o + i * 8;
+      q[0] = float(v[size_t(col[0])]); q[1] = float(v[size_t(col[1])]); q[2] = float(v[size_t(col[2])]);
+      q[3] = 1.0f;
+      q[4] = col[3] >= 0 ? float(v[size_t(col[3])]) : 0.0f;
+      q[5] = q[6] = q[7] = 0.0f;
+    }
+  }
+  return PCR_OK;
+}
+
+extern "C" int pcr_static_map_load(pcr_ctx* c, const char* pcd_path, float leaf, size_t* m) {
+  PCR_API_BEGIN(c)
+  if (!pcd_path || !m || !(leaf > 0.f)) return fail(c, PCR_ERR_INVALID, "bad arguments");
+  size_t n = 0;
+  int rc = pcr_read_pcd(pcd_path, nullptr, 0, &n);
+  if (rc) return fail(c, rc, "can't load globalmap (unreadable or unsupported PCD)");  // MapManager.cpp:68-73
+  unsigned char* host = c->pin.ensure(std::max<size_t>(n, 1) * 32);
+  rc = pcr_read_pcd(pcd_path, host, n, &n);
+  if (rc) return fail(c, rc, "can't load globalmap (truncated PCD)");
+  const float4* d = upload_points(c, host, n, 32, c->raw_src, c->ds_in);
+  c->ds_out.ensure(std::max<size_t>(n, 1) * 32);
+  rc = downsample_packed(c, d, n, leaf, c->ds_out.p, n, m);   // pcp::voxelDownSample(mSubmap, mGridSize), MapManager.cpp:77
+  if (rc) return rc;
+  const float4* t = adopt_points(c, c->ds_out.p, *m, 32, c->dst);
+  return build_target(c, t, *m);
   PCR_API_END(c)
 }
 
