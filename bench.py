@@ -201,6 +201,25 @@ def run_reference(args, rank, world):
     from oracle import pyoracle as orc
     orc.build()
     cores = os.cpu_count() or 1
+    if args.workload == "c5_lio":  # the oracle's frontend loop over a bounded prefix of the same sequence
+        from oracle import pyfrontend as opf
+        from simpleslam_b200 import workloads
+        m = min(args.frames, 120)
+        seq = workloads.c5_sequence(m)
+        oo = opf.OracleOdometry(args.pcr, threads=cores)
+        t0 = time.perf_counter()
+        for f in seq["frames"]:
+            oo.step(f["scan"], f["stamp"], f["local_odom"])
+        tc = time.perf_counter() - t0
+        val = m / tc
+        print(json.dumps({
+            "impl": "reference", "metric": "offline LIO mapping frames/sec (%s frontend)" % args.pcr.upper(), "value": val, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": m, "warmup": 0, "ms_per_step": 1e3 * tc / m, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+f64", "data": "synthetic", "config": {"workload": seq["name"], "pcr": args.pcr},
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": "first %d frames through oracle/pyfrontend.py" % m},
+            "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "note": "reference frontend needs ROS + PCL + Eigen (absent): this arm times the CPU restatement"}))
+        return
     ds = lambda pts, leaf: orc.voxel_downsample(pts, leaf)["points"]  # noqa: E731
     wl = build_workload(args.workload, ds, min(64, args.steps + args.warmup), 0)
     method = wl["method"]
