@@ -169,6 +169,20 @@ int pcr_read_pcd(const char* path, void* out, size_t cap, size_t* n);
  * register the result as the static target. *m = points of the downsampled map. */
 int pcr_static_map_load(pcr_ctx* c, const char* pcd_path, float leaf, size_t* m);
 
+/* ScanContext place-recognition descriptor (backend/src/ScanContext.cpp). `pts`: n_clouds clouds
+ * concatenated, cloud i = records [offsets[i], offsets[i+1]) (HOST). Per cloud: desc 1200 doubles (20 rings x 60 sectors,
+ * row-major, maximum z + lidar_height per bin, radius <= 80 m; makeScanContext :152-196), ring_key 20 doubles (row means,
+ * :198-212), sector_key 60 doubles (column means, :215-230). Output pointers are HOST and may be NULL. */
+int pcr_scancontext_make(pcr_ctx* c, const void* pts, const size_t* offsets, size_t n_clouds, size_t stride, float lidar_height,
+                         double* desc, double* ring_key, double* sector_key);
+/* distanceBtnScanContext (:116-150) for a batch of descriptor pairs: descs = n_desc x 1200 doubles (HOST), pairs = 2 x
+ * n_pairs indices (i0 j0 i1 j1 ...); search_ratio as in the config (0.1). dist[p] = minimum columnwise cosine distance,
+ * shift[p] = the column shift of descriptor j that attains it. sector_key_align = 0 reproduces the reference, whose
+ * fastAlignUsingVkey only ever evaluates shift 0 (its sector key is a 60 x 1 matrix and the loop runs over cols(), :93,122);
+ * 1 = align over all 60 shifts of the sector key as the IROS'18 implementation intends. */
+int pcr_scancontext_distance(pcr_ctx* c, const double* descs, size_t n_desc, const int32_t* pairs, size_t n_pairs, float search_ratio,
+                             int32_t sector_key_align, double* dist, int32_t* shift);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Parity / introspection entry points (used by tests/ to compare every intermediate with the oracle).
  * All output pointers are HOST pointers and may be NULL.

@@ -24,6 +24,7 @@ SYMBOLS = [
     "pcr_loam_get_logs", "pcr_ndt_num_leaves", "pcr_ndt_get_leaves", "pcr_ndt_derivatives", "pcr_ndt_hessian",
     "pcr_gicp_covariances", "pcr_vgicp_num_voxels", "pcr_vgicp_get_voxels", "pcr_vgicp_evaluate",
     "pcr_submap_build", "pcr_submap_cache_clear", "pcr_target_save", "pcr_target_load", "pcr_read_pcd", "pcr_static_map_load",
+    "pcr_scancontext_make", "pcr_scancontext_distance",
 ]
 
 
@@ -288,6 +289,29 @@ class Context:
 
     def target_import(self, dev_ptr, nbytes):
         self._check(lib().pcr_target_import(self._h, _vp(dev_ptr), ctypes.c_size_t(nbytes)))
+
+    # -- ScanContext
+    def scancontext_make(self, clouds, lidar_height=2.0):
+        arrs = [_cloud(cl) for cl in clouds]
+        k = len(arrs)
+        if k == 0:
+            return np.zeros((0, 20, 60)), np.zeros((0, 20)), np.zeros((0, 60))
+        stride = arrs[0][2]
+        cat = np.ascontiguousarray(np.concatenate([a for a, _, _ in arrs]))
+        offs = np.concatenate([[0], np.cumsum([n for _, n, _ in arrs])]).astype(np.uint64)
+        desc = np.empty((k, 20, 60)); rk = np.empty((k, 20)); sk = np.empty((k, 60))
+        self._check(lib().pcr_scancontext_make(self._h, _vp(cat), _vp(offs), ctypes.c_size_t(k), ctypes.c_size_t(stride), ctypes.c_float(lidar_height),
+                                               _vp(desc), _vp(rk), _vp(sk)))
+        return desc, rk, sk
+
+    def scancontext_distance(self, descs, pairs, search_ratio=0.1, sector_key_align=False):
+        descs = np.ascontiguousarray(descs, dtype=np.float64).reshape(-1, 1200)
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        n = len(pairs)
+        dist = np.empty(max(n, 1)); shift = np.empty(max(n, 1), np.int32)
+        self._check(lib().pcr_scancontext_distance(self._h, _vp(descs), ctypes.c_size_t(len(descs)), _vp(pairs), ctypes.c_size_t(n),
+                                                   ctypes.c_float(search_ratio), ctypes.c_int32(int(sector_key_align)), _vp(dist), _vp(shift)))
+        return dist[:n], shift[:n]
 
     # -- on-disk index cache / static map
     def target_save(self, path):

@@ -6,8 +6,10 @@
 #include "loam.cuh"
 #include "ndt.cuh"
 #include "vgicp.cuh"
+#include "scancontext.cuh"
 #include "host_math.hpp"
 #include <cfloat>
+#include <cmath>
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -851,6 +853,61 @@ extern "C" int pcr_static_map_load(pcr_ctx* c, const char* pcd_path, float leaf,
   if (rc) return rc;
   const float4* t = adopt_points(c, c->ds_out.p, *m, 32, c->dst);
   return build_target(c, t, *m);
+  PCR_API_END(c)
+}
+
+// ---- ScanContext ---------------------------------------------------------------------------------
+extern "C" int pcr_scancontext_make(pcr_ctx* c, const void* pts, const size_t* offsets, size_t n_clouds, size_t stride, float lidar_height,
+                                    double* desc, double* ring_key, double* sector_key) {
+  PCR_API_BEGIN(c)
+  if (!offsets || stride < 12 || stride % 4) return fail(c, PCR_ERR_INVALID, "bad arguments");
+  if (n_clouds == 0) return PCR_OK;
+  const size_t n = offsets[n_clouds] - offsets[0];
+  if (n && !pts) return fail(c, PCR_ERR_INVALID, "null cloud");
+  const unsigned char* base = static_cast<const unsigned char*>(pts) + offsets[0] * stride;
+  const float4* d = upload_points(c, base, n, stride, c->raw_src, c->ds_in);
+  DevBuf<uint32_t> offs;
+  offs.ensure(n_clouds + 1);
+  std::vector<uint32_t> ho(n_clouds + 1);
+  for (size_t k = 0; k <= n_clouds; k++) ho[k] = uint32_t(offsets[k] - offsets[0]);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(offs.p, ho.data(), (n_clouds + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  DevBuf<double> out;
+  const size_t per = size_t(kScSize) + kScRings + kScSectors;
+  out.ensure(n_clouds * per);
+  double* dd = out.p;
+  double* dr = dd + n_clouds * kScSize;
+  double* dsk = dr + n_clouds * kScRings;
+  scancontext_make(d, offs.p, int(n_clouds), lidar_height, dd, dr, dsk, c->stream);
+  if (desc) PCR_CUDA_CHECK(cudaMemcpyAsync(desc, dd, n_clouds * kScSize * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (ring_key) PCR_CUDA_CHECK(cudaMemcpyAsync(ring_key, dr, n_clouds * kScRings * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (sector_key) PCR_CUDA_CHECK(cudaMemcpyAsync(sector_key, dsk, n_clouds * kScSectors * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  PCR_CUDA_CHECK(cudaGetLastError());
+  return PCR_OK;
+  PCR_API_END(c)
+}
+
+extern "C" int pcr_scancontext_distance(pcr_ctx* c, const double* descs, size_t n_desc, const int32_t* pairs, size_t n_pairs, float search_ratio,
+                                        int32_t sector_key_align, double* dist, int32_t* shift) {
+  PCR_API_BEGIN(c)
+  if (n_pairs == 0) return PCR_OK;
+  if (!descs || !pairs || !dist || !shift || n_desc == 0) return fail(c, PCR_ERR_INVALID, "bad arguments");
+  for (size_t k = 0; k < 2 * n_pairs; k++)
+    if (pairs[k] < 0 || size_t(pairs[k]) >= n_desc) return fail(c, PCR_ERR_INVALID, "pair index out of range");
+  const int radius = int(std::lround(0.5 * double(search_ratio) * double(kScSectors)));  // SEARCH_RADIUS (:127)
+  if (radius < 0 || radius > 30) return fail(c, PCR_ERR_INVALID, "search ratio out of range");
+  DevBuf<double> dd, ddist;
+  DevBuf<int2> dp;
+  DevBuf<int32_t> dshift;
+  dd.ensure(n_desc * kScSize); dp.ensure(n_pairs); ddist.ensure(n_pairs); dshift.ensure(n_pairs);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(dd.p, descs, n_desc * kScSize * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  PCR_CUDA_CHECK(cudaMemcpyAsync(dp.p, pairs, n_pairs * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+  scancontext_distance(dd.p, dp.p, int(n_pairs), radius, sector_key_align ? 1 : 0, ddist.p, dshift.p, c->stream);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(dist, ddist.p, n_pairs * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  PCR_CUDA_CHECK(cudaMemcpyAsync(shift, dshift.p, n_pairs * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  PCR_CUDA_CHECK(cudaGetLastError());
+  return PCR_OK;
   PCR_API_END(c)
 }
 

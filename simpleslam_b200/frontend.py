@@ -219,3 +219,48 @@ class LoopClosureVerifier:
 
     def close(self):
         self.ctx.close()
+
+
+class ScanContext:
+    """backend::context::ScanContext (backend/src/ScanContext.cpp): descriptors and descriptor distances on the GPU
+    (pcr_scancontext_make / pcr_scancontext_distance), the candidate bookkeeping of query() (:232-290) on the host.
+    Ring-key neighbours are taken in (d2, index) order; the ring-key set is refreshed with the reference's rule
+    (rebuilt when more than numExcludeRecent + buildTreeGap keys are missing)."""
+
+    def __init__(self, ctx, lidar_height=2.0, num_exclude_recent=40, build_tree_gap=10, num_candidates=10, search_ratio=0.1, dist_thres=0.4,
+                 sector_key_align=False):
+        self.ctx = ctx
+        self.lidar_height = float(lidar_height)
+        self.num_exclude_recent, self.build_tree_gap, self.num_candidates = int(num_exclude_recent), int(build_tree_gap), int(num_candidates)
+        self.search_ratio, self.dist_thres, self.sector_key_align = float(search_ratio), float(dist_thres), bool(sector_key_align)
+        self.polarcontexts, self.ringcontexts, self.sectorcontexts = [], [], []
+        self.ring_sub = 0
+
+    def size(self):
+        return len(self.polarcontexts)
+
+    def addContext(self, *clouds):
+        """one or more (already downsampled) keyframe clouds -> descriptors, one kernel launch for all of them"""
+        desc, rk, sk = self.ctx.scancontext_make(list(clouds), self.lidar_height)
+        for k in range(len(clouds)):
+            self.polarcontexts.append(desc[k]); self.ringcontexts.append(rk[k]); self.sectorcontexts.append(sk[k])
+
+    def query(self, idx):
+        """(matched keyframe or -1, yaw offset in rad) — ScanContext::query"""
+        if idx <= self.num_exclude_recent + self.num_candidates:
+            return -1, 0.0
+        if self.ring_sub == 0 or idx - self.ring_sub > self.num_exclude_recent + self.build_tree_gap:
+            self.ring_sub = idx - self.num_exclude_recent
+        sub = np.asarray(self.ringcontexts[: self.ring_sub])
+        d2 = np.sum((sub - self.ringcontexts[idx]) ** 2, axis=1)
+        cand = np.lexsort((np.arange(len(sub)), d2))[: self.num_candidates]
+        descs = np.stack([self.polarcontexts[idx]] + [self.polarcontexts[j] for j in cand])
+        pairs = [(0, k + 1) for k in range(len(cand))]
+        dist, shift = self.ctx.scancontext_distance(descs, pairs, self.search_ratio, self.sector_key_align)
+        best, arg, nn = np.inf, 0, 0
+        for k, j in enumerate(cand):
+            if dist[k] < best:
+                best, arg, nn = dist[k], int(shift[k]), int(j)
+        if best > self.dist_thres:
+            return -1, 0.0
+        return nn, float(np.float32(np.float32(360.0 / 60.0) * arg) * np.pi / 180.0)
