@@ -473,7 +473,8 @@ void NdtDriver::evaluate(const float4* src, const uint32_t* d_offs, size_t max_p
   // enough blocks to fill the machine a few times over, never more than one block per 128 points
   const int full_blocks = int((max_pts + kNdtBlock - 1) / kNdtBlock);
   // 5 blocks of 128 threads are resident per SM: one resident wave, points strided over it
-  int max_blocks = std::max(1, std::min(full_blocks, (kNumSMs * 5 + count - 1) / count));
+  // (floor, not ceil: every block does the same strided share of its request, so one block too many means a second wave)
+  int max_blocks = std::max(1, std::min(full_blocks, (kNumSMs * 5) / count));
   d_params.ensure(count);
   partials.ensure(size_t(count) * max_blocks * kNdtNV);
   if (tickets.cap < size_t(count)) {
