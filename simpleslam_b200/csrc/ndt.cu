@@ -4,6 +4,7 @@
 #include "host_math.hpp"
 #include <cfloat>
 #include <algorithm>
+#include <cstdlib>
 
 namespace pcr {
 
@@ -452,6 +453,8 @@ ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ off
 NdtDriver::~NdtDriver() {
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
+  if (ready) cudaEventDestroy(ready);
+  if (second_stream) { cudaStreamSynchronize(second_stream); cudaStreamDestroy(second_stream); }
   if (mapped_results) cudaFreeHost(mapped_results);
 }
 
@@ -467,6 +470,13 @@ static void launch_eval(bool double_path, dim3 grid, cudaStream_t s, const float
 // Requests h_params[0..count) must be ordered: all float-path (kind 0) requests first, then the double-path (kind 1) ones.
 void NdtDriver::evaluate(const float4* src, const uint32_t* d_offs, size_t max_pts, const NdtTarget& tgt, int search, int count,
                          bool profile, cudaStream_t s) {
+  launch(src, d_offs, max_pts, tgt, search, count, profile, s);
+  collect(count, profile, s);
+}
+
+void NdtDriver::launch(const float4* src, const uint32_t* d_offs, size_t max_pts, const NdtTarget& tgt, int search, int count, bool profile,
+                       cudaStream_t s) {
+  pending_run = false;
   if (count == 0) return;
   int n0 = 0;
   while (n0 < count && h_params.p[n0].kind == 0) n0++;
@@ -517,6 +527,12 @@ void NdtDriver::evaluate(const float4* src, const uint32_t* d_offs, size_t max_p
     }
     if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev1, s));
   }
+  pending_run = run;
+}
+
+void NdtDriver::collect(int count, bool profile, cudaStream_t s) {
+  if (count == 0) return;
+  const bool run = pending_run;
   PCR_CUDA_CHECK(cudaStreamSynchronize(s));
   PCR_CUDA_CHECK(cudaGetLastError());
   h_results.ensure(count);
@@ -723,34 +739,87 @@ static void fill_params(NdtEvalParams& ep, const float* T, const double* p, int 
   ep.pad = 0;
 }
 
+// One lane = one NdtDriver + one stream driving the state machines of a subset of the scans in lock-step.
+namespace {
+struct Lane {
+  NdtDriver* drv;
+  cudaStream_t stream;
+  std::vector<int> scans;    // scans of the batch owned by this lane
+  std::vector<int> active;   // scans with a request in flight (order of h_params)
+  bool in_flight = false;
+};
+
+// builds the lane's next round of requests; returns false when all of its scans are finished
+bool lane_launch(Lane& L, std::vector<ScanState>& st, const float4* src, size_t max_pts, const NdtTarget& tgt, const pcr_params& prm, bool profile) {
+  L.active.clear();
+  for (int i : L.scans)
+    if (st[size_t(i)].phase != ScanState::FINISHED) L.active.push_back(i);
+  L.in_flight = false;
+  if (L.active.empty()) return false;
+  std::stable_partition(L.active.begin(), L.active.end(), [&](int i) { return st[size_t(i)].eval_kind == 0; });
+  L.drv->h_params.ensure(L.active.size());
+  for (size_t k = 0; k < L.active.size(); k++) {
+    ScanState& ss = st[size_t(L.active[k])];
+    fill_params(L.drv->h_params.p[k], ss.eval_T, ss.eval_p, ss.eval_kind, ss.eval_hess, L.active[k]);
+  }
+  L.drv->launch(src, L.drv->offsets.p, max_pts, tgt, prm.ndt_search, int(L.active.size()), profile, L.stream);
+  L.in_flight = true;
+  return true;
+}
+}  // namespace
+
 int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, const NdtTarget& tgt, const pcr_params& prm, double* T,
                      int32_t* converged, int32_t* iters, double* trans_prob, bool profile, cudaStream_t s) {
   launches = 0; hot_ms = 0.f; hot_launches = 0; total_evals = 0; total_hess = 0; total_pairs = 0; point_evals = 0;
   if (n_scans == 0) return 0;
-  uint32_t* ho = h_offsets.ensure(n_scans + 1);
   size_t max_pts = 0;
-  for (size_t i = 0; i <= n_scans; i++) ho[i] = uint32_t(offs[i] - offs[0]);
   for (size_t i = 0; i < n_scans; i++) max_pts = std::max(max_pts, size_t(offs[i + 1] - offs[i]));
-  offsets.ensure(n_scans + 1);
-  PCR_CUDA_CHECK(cudaMemcpyAsync(offsets.p, ho, (n_scans + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   std::vector<ScanState> st(n_scans);
   NdtLogic logic{prm};
   for (size_t i = 0; i < n_scans; i++) logic.start(st[i], T + i * 16);
-  h_params.ensure(n_scans);
-  std::vector<int> active;
-  active.reserve(n_scans);
+
+  // Batches run as two lanes on two streams: while one lane's kernel runs, the host digests the other lane's results
+  // (Newton direction, More-Thuente bookkeeping, angle tables) and queues its next round, so the GPU does not idle
+  // between evaluation rounds. A single scan uses one lane.
+  const char* lanes_env = std::getenv("PCR_NDT_LANES");  // tuning / measurement knob: 1 = single lane (clean per-kernel timing)
+  const bool two = n_scans >= 4 && !(lanes_env && std::atoi(lanes_env) == 1);
+  if (two && !second) {
+    second.reset(new NdtDriver());
+    PCR_CUDA_CHECK(cudaStreamCreateWithFlags(&second_stream, cudaStreamNonBlocking));
+    PCR_CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  }
+  Lane lanes[2];
+  const int nl = two ? 2 : 1;
+  lanes[0].drv = this; lanes[0].stream = s;
+  if (two) {
+    lanes[1].drv = second.get(); lanes[1].stream = second_stream;
+    second->launches = 0; second->hot_ms = 0.f; second->hot_launches = 0; second->point_evals = 0;
+    PCR_CUDA_CHECK(cudaEventRecord(ready, s));                      // src was packed on the main stream
+    PCR_CUDA_CHECK(cudaStreamWaitEvent(second_stream, ready, 0));
+  }
+  for (size_t i = 0; i < n_scans; i++) lanes[two ? (i * 2 / n_scans) : 0].scans.push_back(int(i));
+  for (int l = 0; l < nl; l++) {
+    NdtDriver* d = lanes[l].drv;
+    uint32_t* ho = d->h_offsets.ensure(n_scans + 1);
+    for (size_t i = 0; i <= n_scans; i++) ho[i] = uint32_t(offs[i] - offs[0]);
+    d->offsets.ensure(n_scans + 1);
+    PCR_CUDA_CHECK(cudaMemcpyAsync(d->offsets.p, ho, (n_scans + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, lanes[l].stream));
+  }
+  for (int l = 0; l < nl; l++) lane_launch(lanes[l], st, src, max_pts, tgt, prm, profile);
   for (;;) {
-    active.clear();
-    for (size_t i = 0; i < n_scans; i++)
-      if (st[i].phase != ScanState::FINISHED) active.push_back(int(i));
-    if (active.empty()) break;
-    std::stable_partition(active.begin(), active.end(), [&](int i) { return st[i].eval_kind == 0; });
-    for (size_t k = 0; k < active.size(); k++) {
-      ScanState& ss = st[active[k]];
-      fill_params(h_params.p[k], ss.eval_T, ss.eval_p, ss.eval_kind, ss.eval_hess, active[k]);
+    bool any = false;
+    for (int l = 0; l < nl; l++) {
+      Lane& L = lanes[l];
+      if (!L.in_flight) continue;
+      any = true;
+      L.drv->collect(int(L.active.size()), profile, L.stream);
+      for (size_t k = 0; k < L.active.size(); k++) logic.on_result(st[size_t(L.active[k])], L.drv->h_results.p[k]);
+      lane_launch(L, st, src, max_pts, tgt, prm, profile);
     }
-    evaluate(src, offsets.p, max_pts, tgt, prm.ndt_search, int(active.size()), profile, s);
-    for (size_t k = 0; k < active.size(); k++) logic.on_result(st[active[k]], h_results.p[k]);
+    if (!any) break;
+  }
+  if (two) {
+    launches += second->launches; hot_ms += second->hot_ms; hot_launches += second->hot_launches; point_evals += second->point_evals;
   }
   for (size_t i = 0; i < n_scans; i++) {
     for (int q = 0; q < 16; q++) T[i * 16 + q] = double(st[i].final_T[q]);  // NdtRegister.cpp:28

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "voxel.cuh"
 #include "../../include/pcr_cuda.h"
+#include <memory>
 
 namespace pcr {
 
@@ -64,6 +65,14 @@ struct NdtDriver {
   size_t mapped_cap = 0;
   ~NdtDriver();
 
+  // second lane of a batched align (own buffers, own stream): see NdtDriver::align
+  std::unique_ptr<NdtDriver> second;
+  cudaStream_t second_stream = nullptr;
+  cudaEvent_t ready = nullptr;
+  bool pending_run = false;
+  // launch: queue one evaluation round (h_params[0..count)) on stream s; collect: wait for it -> h_results[0..count)
+  void launch(const float4* src, const uint32_t* d_offs, size_t max_pts, const NdtTarget& tgt, int search, int count, bool profile, cudaStream_t s);
+  void collect(int count, bool profile, cudaStream_t s);
   // evaluate `count` requests (h_params[0..count)) -> h_results[0..count). Blocking.
   void evaluate(const float4* src, const uint32_t* d_offs, size_t max_pts, const NdtTarget& tgt, int search, int count, bool profile,
                 cudaStream_t s);
