@@ -121,6 +121,31 @@ __device__ __forceinline__ void knn_scan_run(WarpKnn& st, const float4* __restri
       idx = __float_as_int(m.w);
       pass = d2 < st.td || (d2 == st.td && idx < st.ti);
     }
+    if (st.cnt == 0) {
+      // first chunk of a search: the list is empty, so instead of up to 32 serial insertions sort the chunk with a warp
+      // bitonic network on (d2, index) and adopt its k smallest (15 shuffle steps)
+      float d = j < hi ? d2 : INFINITY;
+      int id = j < hi ? idx : 0x7fffffff;
+#pragma unroll
+      for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+          const float od = __shfl_xor_sync(kFull, d, jj);
+          const int oi = __shfl_xor_sync(kFull, id, jj);
+          const bool keep_min = ((lane & jj) == 0) == ((lane & kk) == 0);
+          const bool other_less = od < d || (od == d && oi < id);
+          const bool other_more = od > d || (od == d && oi > id);
+          if (keep_min ? other_less : other_more) { d = od; id = oi; }
+        }
+      }
+      const int valid = min(hi - base, 32);
+      st.cnt = min(k, valid);
+      st.bd = lane < st.cnt ? d : INFINITY;
+      st.bi = lane < st.cnt ? id : 0x7fffffff;
+      st.td = __shfl_sync(kFull, st.bd, k - 1);
+      st.ti = __shfl_sync(kFull, st.bi, k - 1);
+      continue;
+    }
     unsigned mask = __ballot_sync(kFull, pass);
     while (mask) {
       const int s = __ffs(mask) - 1;
