@@ -74,7 +74,10 @@ class ClockSampler:
         self.proc = None
         self.mode = None
         self._stop = threading.Event()
-        if not enabled:   # only rank 0 reports clocks; extra pollers just contend for the driver lock
+        if not enabled or os.environ.get("PCR_BENCH_SAMPLER") == "off":   # only rank 0 reports clocks (extra pollers contend for the driver lock)
+            return
+        if os.environ.get("PCR_BENCH_SAMPLER") == "smi":
+            self._start_smi(index)
             return
         try:
             import pynvml
@@ -90,6 +93,9 @@ class ClockSampler:
             return
         except Exception:
             self.mode = None
+        self._start_smi(index)
+
+    def _start_smi(self, index):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)

@@ -9,7 +9,9 @@
 #include "scancontext.cuh"
 #include "host_math.hpp"
 #include <cfloat>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -493,6 +495,9 @@ extern "C" int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const siz
   PCR_API_BEGIN(c)
   if (!m || !(leaf > 0.f) || stride < 12 || stride % 4 || (n_clouds && (!clouds || !counts || !poses))) return fail(c, PCR_ERR_INVALID, "bad arguments");
   *m = 0;
+  static const bool trace = std::getenv("PCR_TRACE") != nullptr;  // stage timings on stderr (tuning aid)
+  auto now = [&]() { if (trace) cudaStreamSynchronize(c->stream); return std::chrono::steady_clock::now(); };
+  auto t_start = now();
   SubmapPart* hp = reinterpret_cast<SubmapPart*>(c->sub_meta_h.ensure((n_clouds + 1) * sizeof(SubmapPart)));
   size_t total = 0, np = 0;
   for (size_t k = 0; k < n_clouds; k++) {
@@ -524,11 +529,13 @@ extern "C" int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const siz
     c->dst.ensure(1);
     return build_target(c, c->dst.p, 0);
   }
+  auto t_up = now();
   c->sub_meta.ensure(np * sizeof(SubmapPart));
   PCR_CUDA_CHECK(cudaMemcpyAsync(c->sub_meta.p, hp, np * sizeof(SubmapPart), cudaMemcpyHostToDevice, c->stream));
   c->sub_concat.ensure(total);
   submap_transform_kernel<<<unsigned((total + 255) / 256), 256, (np + 1) * sizeof(unsigned long long), c->stream>>>(
       reinterpret_cast<const SubmapPart*>(c->sub_meta.p), int(np), total, c->sub_concat.p);
+  auto t_tr = now();
   c->ds_out.ensure(total * 32);
   size_t mm = 0;
   int rc = downsample_packed(c, c->sub_concat.p, total, leaf, c->ds_out.p, total, &mm);
@@ -538,8 +545,16 @@ extern "C" int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const siz
     PCR_CUDA_CHECK(cudaMemcpyAsync(out, c->ds_out.p, mm * 32, cudaMemcpyDeviceToHost, c->stream));
   }
   *m = mm;
+  auto t_ds = now();
   const float4* d = adopt_points(c, c->ds_out.p, mm, 32, c->dst);
-  return build_target(c, d, mm);
+  rc = build_target(c, d, mm);
+  if (trace) {
+    auto t_end = now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    std::fprintf(stderr, "[pcr trace] submap_build: %zu clouds, %zu pts -> %zu | upload %.3f transform %.3f downsample %.3f index %.3f ms (ncell %lld, ring %d)\n",
+                 np, total, mm, ms(t_start, t_up), ms(t_up, t_tr), ms(t_tr, t_ds), ms(t_ds, t_end), c->loam_grid.g.ncell, c->loam_grid.max_ring);
+  }
+  return rc;
   PCR_API_END(c)
 }
 

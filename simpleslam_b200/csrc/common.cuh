@@ -4,8 +4,11 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <stdexcept>
+#include <utility>
 #include <vector>
 
 namespace pcr {
@@ -22,26 +25,91 @@ struct CudaError : std::runtime_error {
                              std::to_string(__LINE__) + ")");                                                  \
   } while (0)
 
-// Grow-only device buffer.
+// Process-wide cache of device allocations, bucketed by size class and device. cudaMalloc / cudaFree cost milliseconds
+// (occasionally tens of milliseconds, and cudaFree synchronises the device): a register that rebuilds its index on every
+// scan2Map call, or a frontend whose submap grows frame by frame, would pay that inside the hot loop. Freed buffers are
+// parked here instead and handed out again to the next request of the same size class — also across contexts.
+class DevPool {
+ public:
+  static size_t size_class(size_t bytes) {
+    if (bytes <= 256) return 256;
+    if (bytes > (size_t(1) << 30)) return (bytes + (size_t(1) << 28) - 1) & ~((size_t(1) << 28) - 1);  // > 1 GiB: 256 MiB steps
+    size_t c = 256;
+    while (c < bytes) c <<= 1;
+    return c;
+  }
+  static void* alloc(size_t bytes, size_t& got) {
+    got = size_class(bytes);
+    int dev = 0;
+    PCR_CUDA_CHECK(cudaGetDevice(&dev));
+    {
+      std::lock_guard<std::mutex> lk(mu());
+      auto& lst = free_list()[std::make_pair(dev, got)];
+      if (!lst.empty()) { void* p = lst.back(); lst.pop_back(); return p; }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, got);
+    if (e == cudaErrorMemoryAllocation) {  // out of memory: give the parked buffers back to the driver and retry once
+      cudaGetLastError();
+      trim();
+      e = cudaMalloc(&p, got);
+    }
+    if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc(") + std::to_string(got) + " bytes) failed: " + cudaGetErrorString(e));
+    return p;
+  }
+  // the caller guarantees that no work touching p is still in flight
+  static void release(void* p, size_t got) {
+    if (!p) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaFree(p); return; }
+    std::lock_guard<std::mutex> lk(mu());
+    free_list()[std::make_pair(dev, got)].push_back(p);
+  }
+  static void trim() {
+    std::lock_guard<std::mutex> lk(mu());
+    for (auto& kv : free_list()) {
+      for (void* p : kv.second) cudaFree(p);
+      kv.second.clear();
+    }
+  }
+
+ private:
+  static std::mutex& mu() { static std::mutex m; return m; }
+  static std::map<std::pair<int, size_t>, std::vector<void*>>& free_list() {
+    static auto* m = new std::map<std::pair<int, size_t>, std::vector<void*>>();  // leaked on purpose: outlives the CUDA context teardown
+    return *m;
+  }
+};
+
+// Grow-only device buffer (allocations come from DevPool).
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
-  size_t cap = 0;
+  size_t cap = 0;        // elements
+  size_t bytes_ = 0;     // size class the allocation was taken from
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { release(); }
   T* ensure(size_t n) {
     if (n > cap) {
-      if (p) cudaFree(p);
-      p = nullptr;
-      size_t want = n + n / 4 + 64;
-      PCR_CUDA_CHECK(cudaMalloc(&p, want * sizeof(T)));
-      cap = want;
+      if (p) {
+        cudaDeviceSynchronize();  // the old buffer may still be read by queued work (what cudaFree's implicit sync used to cover)
+        DevPool::release(p, bytes_);
+        p = nullptr;
+        cap = 0;
+      }
+      const size_t want = n + n / 4 + 64;
+      p = static_cast<T*>(DevPool::alloc(want * sizeof(T), bytes_));
+      cap = bytes_ / sizeof(T);
     }
     return p;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() {
+    if (p) DevPool::release(p, bytes_);
+    p = nullptr;
+    cap = 0;
+  }
 };
 
 // Pinned host staging buffer.

@@ -110,13 +110,27 @@ vg_voxel_kernel(const float4* __restrict__ pts, const double* __restrict__ covs,
   if (v >= nseg) return;
   const uint32_t b = seg_start[v], e = seg_start[v + 1];
   double m[3] = {0, 0, 0}, c[6] = {0, 0, 0, 0, 0, 0};
-  for (uint32_t j = b + lane; j < e; j += 32) {
-    const uint32_t idx = vals[j];
-    const float4 p = __ldg(pts + idx);
-    m[0] += double(p.x); m[1] += double(p.y); m[2] += double(p.z);
-    const double* cp = covs + size_t(idx) * 6;
+  // a voxel next to the sensor holds thousands of points: the indices of four trips are fetched together so that four
+  // independent point / covariance gathers are in flight per lane (the summation order per lane is unchanged)
+  for (uint32_t j0 = b + lane; j0 < e; j0 += 128) {
+    uint32_t idx[4];
 #pragma unroll
-    for (int t = 0; t < 6; t++) c[t] += cp[t];
+    for (int u = 0; u < 4; u++) idx[u] = (j0 + 32 * u < e) ? vals[j0 + 32 * u] : 0xffffffffu;
+    float4 p[4];
+    double2 ca[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (idx[u] == 0xffffffffu) continue;
+      p[u] = __ldg(pts + idx[u]);
+      const double2* cp = reinterpret_cast<const double2*>(covs + size_t(idx[u]) * 6);
+      ca[u][0] = __ldg(cp); ca[u][1] = __ldg(cp + 1); ca[u][2] = __ldg(cp + 2);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (idx[u] == 0xffffffffu) continue;
+      m[0] += double(p[u].x); m[1] += double(p[u].y); m[2] += double(p[u].z);
+      c[0] += ca[u][0].x; c[1] += ca[u][0].y; c[2] += ca[u][1].x; c[3] += ca[u][1].y; c[4] += ca[u][2].x; c[5] += ca[u][2].y;
+    }
   }
 #pragma unroll
   for (int t = 0; t < 3; t++) m[t] = warp_sum(m[t]);
@@ -210,14 +224,14 @@ vgicp_eval_kernel(const float4* __restrict__ src, const double* __restrict__ src
   }
   __syncthreads();
   const uint32_t begin = offs[sp.scan], end = offs[sp.scan + 1];
-  const int nb = int((end - begin + kVgBlock - 1) / kVgBlock);
+  const int nb = min(int((end - begin + kVgBlock - 1) / kVgBlock), max_blocks);
   if (int(blockIdx.x) >= nb) return;
 
+  // points strided over one resident wave of blocks: the 29-value block reduction is paid once per thread, not per point
   double acc[kVgNV];
 #pragma unroll
   for (int k = 0; k < kVgNV; k++) acc[k] = 0.0;
-  const uint32_t i = begin + blockIdx.x * kVgBlock + threadIdx.x;
-  if (i < end) {
+  for (uint32_t i = begin + blockIdx.x * kVgBlock + threadIdx.x; i < end; i += uint32_t(nb) * kVgBlock) {
     const float4 p = __ldg(src + i);
     const double px = double(p.x), py = double(p.y), pz = double(p.z);
     double t0[3];
@@ -257,8 +271,8 @@ vgicp_eval_kernel(const float4* __restrict__ src, const double* __restrict__ src
         double Me[3];
 #pragma unroll
         for (int r = 0; r < 3; r++) Me[r] = (M[r][0] * e[0] + M[r][1] * e[1]) + M[r][2] * e[2];
-        acc[0] = wgt * ((e[0] * Me[0] + e[1] * Me[1]) + e[2] * Me[2]);
-        acc[28] = 1.0;
+        acc[0] += wgt * ((e[0] * Me[0] + e[1] * Me[1]) + e[2] * Me[2]);
+        acc[28] += 1.0;
         if (sp.want_hb) {
           // J = [ skew(T p) | -I ] : columns
           const double J[6][3] = {{0.0, tA[2], -tA[1]}, {-tA[2], 0.0, tA[0]}, {tA[1], -tA[0], 0.0}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}};
@@ -271,9 +285,9 @@ vgicp_eval_kernel(const float4* __restrict__ src, const double* __restrict__ src
 #pragma unroll
           for (int r = 0; r < 6; r++)
 #pragma unroll
-            for (int c = r; c < 6; c++) acc[k++] = wgt * ((J[r][0] * MJ[c][0] + J[r][1] * MJ[c][1]) + J[r][2] * MJ[c][2]);
+            for (int c = r; c < 6; c++) acc[k++] += wgt * ((J[r][0] * MJ[c][0] + J[r][1] * MJ[c][1]) + J[r][2] * MJ[c][2]);
 #pragma unroll
-          for (int r = 0; r < 6; r++) acc[22 + r] = wgt * ((J[r][0] * Me[0] + J[r][1] * Me[1]) + J[r][2] * Me[2]);
+          for (int r = 0; r < 6; r++) acc[22 + r] += wgt * ((J[r][0] * Me[0] + J[r][1] * Me[1]) + J[r][2] * Me[2]);
         }
       }
     }
@@ -307,7 +321,8 @@ VgicpDriver::~VgicpDriver() {
 void VgicpDriver::evaluate(const float4* src, const double* covs, const uint32_t* d_offs, size_t max_pts, const VgicpTarget& tgt, int count,
                            bool profile, cudaStream_t s) {
   if (count == 0) return;
-  int max_blocks = int((max_pts + kVgBlock - 1) / kVgBlock);
+  // 4 blocks of 128 threads are resident per SM (126 registers): one resident wave shared by the requests
+  int max_blocks = std::min(int((max_pts + kVgBlock - 1) / kVgBlock), std::max(1, (kNumSMs * 4) / count));
   if (max_blocks < 1) max_blocks = 1;
   d_params.ensure(count);
   d_results.ensure(count);
