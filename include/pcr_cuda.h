@@ -83,7 +83,7 @@ typedef struct pcr_stats {
   int64_t n_target;
   int64_t n_residuals;       /* LOAM: accepted residuals of the last linearisation; VGICP: correspondences */
   int64_t kernel_launches;   /* hand-written kernels launched by the last align/scan2map call */
-  int64_t n_pairs;           /* LOAM: map points examined by the 27-cell gather (sum over iterations and scans); NDT: (point, leaf)
+  int64_t n_pairs;           /* LOAM: map points examined by the pruned neighbour search (sum over iterations and scans); NDT: (point, leaf)
                                 pairs evaluated (sum over evaluations); VGICP: correspondences (sum over evaluations) */
   int64_t n_point_evals;     /* source points pushed through the hot kernel, summed over its launches (roofline numerator) */
   int64_t n_index_reads;     /* spatial-index entries read by the hot kernel: LOAM x-row lookups (2 x 4 B each), NDT voxel-table
