@@ -158,7 +158,7 @@ int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes);
 
 /* On-disk index cache: the built target index (the same blob pcr_target_export produces) written to /
  * read from a file, so that the localisation mode (test/loc.cpp -> MapManager(pcd_file), frontend/src/MapManager.cpp:52-84)
- * does not re-downsample and re-index its static map at every start. LOAM and NDT contexts. */
+ * does not re-downsample and re-index its static map at every start. */
 int pcr_target_save(pcr_ctx* c, const char* path);
 int pcr_target_load(pcr_ctx* c, const char* path);
 /* Minimal PCD reader (pcp::loadPCDFile -> pcl::io::loadPCDFile<PointXYZI>, common/pcp/pcp.hpp:71-75): DATA ascii | binary,

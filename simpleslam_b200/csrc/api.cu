@@ -596,10 +596,12 @@ struct BlobHeader {
   uint64_t n_target;
   uint64_t sizes[8];  // byte sizes of the sections that follow (each 256-byte aligned)
   GridSpec g;
-  double d[4];
-  int32_t i[8];
+  double d[8];
+  int32_t i[16];
+  float f[16];
+  uint64_t u[4];
 };
-constexpr uint64_t kMagic = 0x50435242323030ull;  // "PCRB200"
+constexpr uint64_t kMagic = 0x32505242323030ull;  // "PCRB200" v2
 size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct Section { const void* src; void* dst_holder; size_t bytes; };
@@ -638,6 +640,27 @@ int collect_sections(pcr_ctx* c, BlobHeader& h, const void* ptrs[8]) {
         ptrs[7] = c->ndt.centroids.p; h.sizes[7] = L * sizeof(float4);
       }
       break;
+    case PCR_VGICP: {
+      const VgicpTarget& t = c->vg;
+      const MortonGrid& mg = t.grid;
+      h.i[0] = t.built ? 1 : 0;
+      for (int a = 0; a < 3; a++) { h.i[1 + a] = t.cmin[a]; h.i[4 + a] = t.cdim[a]; h.i[7 + a] = mg.dim0[a]; h.f[a] = mg.mn[a]; h.f[3 + a] = mg.smax[a]; }
+      h.i[10] = mg.built ? 1 : 0;
+      h.f[6] = mg.h0; h.f[7] = mg.inv_h0;
+      h.d[0] = t.resolution; h.d[1] = mg.slack0;
+      h.u[0] = mg.cap; h.u[1] = mg.n; h.u[2] = uint64_t(t.ncell); h.u[3] = t.nvox;
+      if (mg.built && t.n) {
+        ptrs[0] = mg.pts.p; h.sizes[0] = mg.n * sizeof(float4);
+        ptrs[1] = mg.tables.p; h.sizes[1] = size_t(kKnnLevels) * mg.cap * sizeof(uint4);
+        ptrs[2] = t.covs.p; h.sizes[2] = t.n * 6 * sizeof(double);
+        if (t.nvox) {
+          ptrs[3] = t.vox.p; h.sizes[3] = t.nvox * sizeof(VoxelRec);
+          ptrs[4] = t.vox_key.p; h.sizes[4] = t.nvox * sizeof(int32_t);
+          ptrs[5] = t.table.p; h.sizes[5] = size_t(t.ncell) * sizeof(int32_t);
+        }
+      }
+      break;
+    }
     default:
       return PCR_ERR_UNSUPPORTED;
   }
@@ -652,7 +675,7 @@ extern "C" int pcr_target_blob_size(pcr_ctx* c, size_t* bytes) {
   BlobHeader h;
   const void* ptrs[8];
   int rc = collect_sections(c, h, ptrs);
-  if (rc) return fail(c, rc, "target export is implemented for loam and ndt");
+  if (rc) return fail(c, rc, "target export: unknown method");
   size_t total = align256(sizeof(BlobHeader));
   for (int k = 0; k < 8; k++) total += align256(h.sizes[k]);
   *bytes = total;
@@ -666,7 +689,7 @@ extern "C" int pcr_target_export(pcr_ctx* c, void* dev_blob, size_t cap) {
   BlobHeader h;
   const void* ptrs[8];
   int rc = collect_sections(c, h, ptrs);
-  if (rc) return fail(c, rc, "target export is implemented for loam and ndt");
+  if (rc) return fail(c, rc, "target export: unknown method");
   size_t off = align256(sizeof(BlobHeader));
   unsigned char* base = static_cast<unsigned char*>(dev_blob);
   for (int k = 0; k < 8; k++) {
@@ -720,8 +743,29 @@ extern "C" int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes)
       take(t.centroids.p, 7);
     }
     t.built = true;
+  } else if (h.method == PCR_VGICP) {
+    VgicpTarget& t = c->vg;
+    MortonGrid& mg = t.grid;
+    t.built = false;
+    t.n = size_t(h.n_target);
+    t.resolution = h.d[0];
+    mg.slack0 = h.d[1];
+    for (int a = 0; a < 3; a++) { t.cmin[a] = h.i[1 + a]; t.cdim[a] = h.i[4 + a]; mg.dim0[a] = h.i[7 + a]; mg.mn[a] = h.f[a]; mg.smax[a] = h.f[3 + a]; }
+    mg.h0 = h.f[6]; mg.inv_h0 = h.f[7];
+    mg.cap = uint32_t(h.u[0]); mg.n = size_t(h.u[1]); t.ncell = (long long)h.u[2]; t.nvox = size_t(h.u[3]);
+    mg.built = h.i[10] != 0;
+    if (h.sizes[0]) {
+      mg.pts.ensure(mg.n); mg.tables.ensure(size_t(kKnnLevels) * mg.cap); t.covs.ensure(t.n * 6);
+      take(mg.pts.p, 0); take(mg.tables.p, 1); take(t.covs.p, 2);
+      if (t.nvox) {
+        t.vox.ensure(t.nvox); t.vox_key.ensure(t.nvox); t.table.ensure(size_t(t.ncell));
+        take(t.vox.p, 3); take(t.vox_key.p, 4); take(t.table.p, 5);
+      }
+    }
+    t.built = h.i[0] != 0;
+    c->has_last = false;
   } else {
-    return fail(c, PCR_ERR_UNSUPPORTED, "target import is implemented for loam and ndt");
+    return fail(c, PCR_ERR_UNSUPPORTED, "unknown method in the target blob");
   }
   PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->has_target = true;

@@ -42,7 +42,7 @@ def test_batch_equals_singles(method, case_fn):
     c.close()
 
 
-@pytest.mark.parametrize("method,case_fn", [(capi.PCR_LOAM, data.loam_case), (capi.PCR_NDT, data.ndt_case)])
+@pytest.mark.parametrize("method,case_fn", [(capi.PCR_LOAM, data.loam_case), (capi.PCR_NDT, data.ndt_case), (capi.PCR_VGICP, data.vgicp_case)])
 def test_target_blob_roundtrip(method, case_fn):
     """export the built index into a device blob, import it into a second context: identical registrations"""
     case = case_fn()
@@ -57,6 +57,8 @@ def test_target_blob_roundtrip(method, case_fn):
     Ta, ca = a.align(case["src"], case["T_guess"])
     Tb, cb = b.align(case["src"], case["T_guess"])
     assert ca == cb and np.array_equal(Ta, Tb)
+    if method == capi.PCR_VGICP:  # the imported target also carries the kNN grid behind getFitnessScore
+        assert a.fitness() == b.fitness()
     a.close(); b.close()
 
 
