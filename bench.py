@@ -169,11 +169,18 @@ def build_workload(name, downsample, n_scans, seed_offset):
         return workloads.c2_ndt(downsample, n_scans, seed_offset=seed_offset)
     if name == "c1_loam":
         return workloads.c1_loam(downsample, n_scans, seed_offset=seed_offset)
-    if name == "c3_vgicp":
-        return workloads.c3_vgicp(n_scans, seed_offset=seed_offset)
+    if name in ("c3_vgicp", "c3_vgicp_gn"):
+        wl = workloads.c3_vgicp(n_scans, seed_offset=seed_offset)
+        if name.endswith("_gn"):  # BASELINE config wording: "20 Gauss-Newton iterations" (the reference's shipped default is LM, <= 64)
+            wl["name"] += ", Gauss-Newton capped at 20 iterations"
+            wl["vgicp"] = dict(optimizer="GN", max_iterations=20)
+        return wl
     if name in ("c4_loam", "c4_ndt"):
         return workloads.c4_batched(name[3:], downsample, n_scans, seed_offset=seed_offset)
     raise SystemExit("unknown workload " + name)
+
+
+VGICP_ORACLE_OPTS = {}   # set by the c3_vgicp_gn workload
 
 
 def oracle_register(method, src, dst, T, threads):
@@ -183,7 +190,7 @@ def oracle_register(method, src, dst, T, threads):
         return orc.Ndt(dst, 1.0).align(src, T, threads=threads)["T"]
     if method == "loam":
         return orc.loam_align(src, dst, T, threads=threads)["T"]
-    return orc.Vgicp(dst, 1.0, 20, threads=threads).align(src, T, threads=threads)["T"]
+    return orc.Vgicp(dst, 1.0, 20, threads=threads).align(src, T, threads=threads, **VGICP_ORACLE_OPTS)["T"]
 
 
 def step_inputs(wl, k):
@@ -229,6 +236,7 @@ def run_reference(args, rank, world):
     ds = lambda pts, leaf: orc.voxel_downsample(pts, leaf)["points"]  # noqa: E731
     wl = build_workload(args.workload, ds, min(64, args.steps + args.warmup), 0)
     method = wl["method"]
+    VGICP_ORACLE_OPTS.update(wl.get("vgicp", {}))
     for k in range(args.warmup):
         s, d, Tg, _ = step_inputs(wl, k)
         oracle_register(method, s, d, Tg, cores)
@@ -377,12 +385,13 @@ def run_ours(args, rank, world, local_rank):
         # NCCL writes its banner / debug lines to stdout: keep stdout for the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_bench_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
-    method_id = {"c2_ndt": capi.PCR_NDT, "c1_loam": capi.PCR_LOAM, "c3_vgicp": capi.PCR_VGICP, "c4_loam": capi.PCR_LOAM,
+    method_id = {"c2_ndt": capi.PCR_NDT, "c1_loam": capi.PCR_LOAM, "c3_vgicp": capi.PCR_VGICP, "c3_vgicp_gn": capi.PCR_VGICP, "c4_loam": capi.PCR_LOAM,
                  "c4_ndt": capi.PCR_NDT}[args.workload]
     static_map = args.workload.startswith("c4")  # loc.cpp mode: the map is registered once, e2e = batches of host scans
-    ctx = capi.Context(method_id, device=local_rank)
+    gn = args.workload == "c3_vgicp_gn"
+    ctx = capi.Context(method_id, device=local_rank, **(dict(vgicp_optimizer=capi.PCR_LSQ_GN, vgicp_max_iters=20) if gn else {}))
     ds = lambda pts, leaf: ctx.voxel_downsample(pts, leaf)  # noqa: E731
-    B = args.batch if args.batch > 0 else {"c2_ndt": 8, "c1_loam": 64, "c3_vgicp": 1, "c4_loam": 128, "c4_ndt": 16}[args.workload]
+    B = args.batch if args.batch > 0 else {"c2_ndt": 8, "c1_loam": 64, "c3_vgicp": 1, "c3_vgicp_gn": 1, "c4_loam": 128, "c4_ndt": 16}[args.workload]
     n_steps_all = args.steps + args.warmup
     n_unique = min(64, n_steps_all * B)
     t_gen = time.perf_counter()
@@ -391,6 +400,7 @@ def run_ours(args, rank, world, local_rank):
     method = wl["method"]
     if method == "vgicp":
         B = 1
+    VGICP_ORACLE_OPTS.update(wl.get("vgicp", {}))
 
     # ---- static map: rank 0 builds the index, broadcasts it once over NCCL; the others import it
     setup = {}
@@ -658,7 +668,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2_ndt", choices=["c2_ndt", "c1_loam", "c3_vgicp", "c4_loam", "c4_ndt", "c5_lio"])
+    ap.add_argument("--workload", default="c2_ndt", choices=["c2_ndt", "c1_loam", "c3_vgicp", "c3_vgicp_gn", "c4_loam", "c4_ndt", "c5_lio"])
     ap.add_argument("--frames", type=int, default=300, help="c5_lio: frames of the sequence (BASELINE config: 2000)")
     ap.add_argument("--pcr", default="loam", choices=["loam", "ndt", "vgicp"], help="c5_lio: frontend.pcr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
