@@ -111,3 +111,78 @@ def test_loam_jacobian_is_the_point_to_plane_derivative():
         assert np.median(err) < 0.02 and np.percentile(err, 95) < 0.25, (i, np.median(err), np.percentile(err, 95))
         worst = max(worst, float(np.median(err)))
     assert worst < 0.02
+
+
+def test_voxel_downsample_against_numpy():
+    """pcl::VoxelGrid semantics restated a second time in numpy: float32 key math, keys ascending, float32 centroid sums in
+    ascending original index (cumsum is sequential)"""
+    rng = np.random.RandomState(9)
+    pts = data.xyzi((rng.uniform(-20, 20, (5000, 3)) * [1, 1, 0.2]).astype(np.float32), rng.rand(5000).astype(np.float32))
+    leaf = np.float32(0.5)
+    o = orc.voxel_downsample(pts, float(leaf))
+    inv = np.float32(1.0) / leaf
+    xyz = pts[:, :3]
+    mn, mx = xyz.min(0), xyz.max(0)
+    min_b = np.floor(mn * inv).astype(np.int32)
+    max_b = np.floor(mx * inv).astype(np.int32)
+    div = max_b - min_b + 1
+    ijk = (np.floor(xyz * inv) - min_b.astype(np.float32)).astype(np.int32)
+    key = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+    assert np.array_equal(key, o["keys"])
+    order = np.argsort(key, kind="stable")
+    uk, start, cnt = np.unique(key[order], return_index=True, return_counts=True)
+    assert np.array_equal(uk, o["out_keys"]) and np.array_equal(cnt, o["counts"])
+    for v in rng.choice(len(uk), 200, replace=False):
+        sel = order[start[v]: start[v] + cnt[v]]
+        c = np.cumsum(pts[sel][:, [0, 1, 2, 4]], axis=0, dtype=np.float32)[-1] / np.float32(cnt[v])
+        assert np.array_equal(c.view(np.uint32), o["points"][v][[0, 1, 2, 4]].view(np.uint32))
+        assert o["points"][v][3] == 1.0
+
+
+def test_ndt_leaves_against_numpy():
+    tgt, _ = _ndt_case()
+    L = orc.Ndt(tgt, 1.0).leaves()
+    xyz = tgt[:, :3].astype(np.float64)
+    ijk = np.floor(tgt[:, :3] * np.float32(1.0)).astype(np.int64) - L["min_b"]
+    key = ijk[:, 0] + ijk[:, 1] * L["div_b"][0] + ijk[:, 2] * L["div_b"][0] * L["div_b"][1]
+    checked = 0
+    for j in np.random.RandomState(0).choice(len(L["keys"]), 60, replace=False):
+        p = xyz[key == L["keys"][j]]
+        n = len(p)
+        if L["npts"][j] < 6:
+            assert n == max(L["npts"][j], n)
+            continue
+        assert n == L["npts"][j]
+        mean = p.mean(0)
+        assert np.allclose(mean, L["mean"][j], rtol=0, atol=1e-12)
+        # single-pass form of voxel_grid_covariance_omp_impl.hpp:329-330 with cov_ started at Identity
+        cov = ((np.eye(3) + p.T @ p) - 2 * np.outer(p.sum(0), mean)) / n + np.outer(mean, mean)
+        cov *= (n - 1.0) / n
+        w, V = np.linalg.eigh(cov)
+        if w[0] < 0.01 * w[2]:
+            w[0] = 0.01 * w[2]
+            if w[1] < 0.01 * w[2]:
+                w[1] = 0.01 * w[2]
+            cov = V @ np.diag(w) @ np.linalg.inv(V)
+        assert np.allclose(cov, L["cov"][j], rtol=1e-9, atol=1e-12)
+        assert np.allclose(np.linalg.inv(cov), L["icov"][j], rtol=1e-7, atol=1e-9)
+        checked += 1
+    assert checked > 20
+
+
+def test_gicp_covariances_against_numpy():
+    rng = np.random.RandomState(4)
+    pts = data.xyzi((rng.uniform(-10, 10, (4000, 3)) * [1, 1, 0.05]).astype(np.float32))
+    covs, idx = orc.gicp_covariances(pts, 20, want_idx=True)
+    xyz = pts[:, :3].astype(np.float64)
+    tree = cKDTree(xyz)
+    for i in rng.choice(len(pts), 150, replace=False):
+        _, nn = tree.query(xyz[i], k=20)
+        if set(nn.tolist()) != set(idx[i].tolist()):
+            continue  # float-metric tie at the 20th neighbour
+        nb = xyz[idx[i]]
+        d = nb - nb.mean(0)
+        c = d.T @ d / 20.0
+        U, _, Vt = np.linalg.svd(c)
+        ref = U @ np.diag([1.0, 1.0, 1e-3]) @ Vt        # PLANE regularisation (fast_gicp_impl.hpp:272-293)
+        assert np.allclose(covs[i], ref, rtol=1e-6, atol=1e-9), i
