@@ -91,3 +91,26 @@ def test_loop_closure_verification(seq):
     far = v.verify(0, cur)
     assert not far["accepted"]
     v.close()
+
+
+def test_frontend_and_scancontext_against_golden():
+    """GPU loop and descriptors against the committed golden vectors (tests/golden/frontend_small.npz)"""
+    import os
+    g = np.load(os.path.join(data.GOLDEN, "frontend_small.npz"))
+    offs = g["scan_offsets"]
+    scans = [data.xyzi(g["scans"][offs[k]:offs[k + 1]]) for k in range(len(offs) - 1)]
+    lo = frontend.LidarOdometry("loam")
+    for k, s in enumerate(scans):
+        P = lo.generateOdom(s, float(g["stamps"][k]), g["local_odom"][k])
+        dt, dr = data.pose_err(P, g["poses"][k])
+        assert dt < 1e-4 and dr < 1e-4, (k, dt, dr)
+    assert lo.converged == [bool(x) for x in g["converged"]] and len(lo.map.keyframes) == int(g["n_keyframes"])
+    assert lo.map.submap_size == int(g["submap_sizes"][-1])
+    ds = [lo.ctx.voxel_downsample(s, 0.5) for s in scans[:4]]
+    desc, _, _ = lo.ctx.scancontext_make(ds, 2.0)
+    assert np.array_equal(desc, g["sc_desc"])
+    dist, shift = lo.ctx.scancontext_distance(desc, [(0, 1)], 0.1, False)
+    assert abs(dist[0] - g["sc_dist"][0]) < 1e-12 and shift[0] == g["sc_shift"][0]
+    dist, shift = lo.ctx.scancontext_distance(desc, [(0, 3)], 0.1, True)
+    assert abs(dist[0] - g["sc_dist"][1]) < 1e-12 and shift[0] == g["sc_shift"][1]
+    lo.close()

@@ -38,3 +38,26 @@ def test_oracle_odometry_tracks_truth_and_builds_keyframes():
     f = seq["frames"][-1]
     P2 = o.step(f["scan"], f["stamp"] + 0.1, None)
     assert np.linalg.norm(P2[:2, 3] - P[:2, 3]) < 0.05
+
+
+def test_frontend_and_scancontext_golden():
+    """the oracle's frontend loop and ScanContext reproduce the frozen vectors of tests/golden/frontend_small.npz"""
+    import os
+    from oracle import pyoracle as orc
+    from oracle import pyscancontext as osc
+    import data
+    g = np.load(os.path.join(data.GOLDEN, "frontend_small.npz"))
+    offs = g["scan_offsets"]
+    scans = [data.xyzi(g["scans"][offs[k]:offs[k + 1]]) for k in range(len(offs) - 1)]
+    oo = opf.OracleOdometry("loam", threads=4)
+    for k, s in enumerate(scans):
+        P = oo.step(s, float(g["stamps"][k]), g["local_odom"][k])
+        assert np.allclose(P, g["poses"][k], rtol=0, atol=1e-9), k
+    assert list(g["converged"]) == oo.converged and int(g["n_keyframes"]) == len(oo.kfs)
+    assert np.array_equal(g["submap_sizes"], [len(s) for s in oo.submaps])
+    for k in range(4):
+        assert np.array_equal(osc.make_scancontext(orc.voxel_downsample(scans[k], 0.5)["points"], 2.0), g["sc_desc"][k])
+    d01 = osc.distance(g["sc_desc"][0], g["sc_desc"][1])
+    d03 = osc.distance(g["sc_desc"][0], g["sc_desc"][3], sector_key_align=True)
+    assert abs(d01[0] - g["sc_dist"][0]) < 1e-12 and d01[1] == g["sc_shift"][0]
+    assert abs(d03[0] - g["sc_dist"][1]) < 1e-12 and d03[1] == g["sc_shift"][1]
