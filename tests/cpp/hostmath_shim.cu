@@ -1,0 +1,41 @@
+// Host-side shim over the PRODUCT's small dense linear algebra (simpleslam_b200/csrc/dev_linalg.cuh is __host__ __device__,
+// host_math.hpp is plain C++), so that tests/test_product_linalg.py can exercise it on the CPU — no GPU needed — against
+// numpy / scipy and against the oracle's independent restatement.
+#include "../../simpleslam_b200/csrc/dev_linalg.cuh"
+#include "../../simpleslam_b200/csrc/host_math.hpp"
+#include <cstring>
+
+extern "C" {
+void shim_cpqr5x3(const double* A, const double* b, double* x) {
+  double a[5][3], bb[5], xx[3];
+  for (int r = 0; r < 5; r++) { bb[r] = b[r]; for (int c = 0; c < 3; c++) a[r][c] = A[r * 3 + c]; }
+  pcr::cpqr5x3_solve(a, bb, xx);
+  for (int c = 0; c < 3; c++) x[c] = xx[c];
+}
+void shim_ldlt6(const double* A, const double* b, double* x) { pcr::ldlt6_solve(A, b, x); }
+void shim_se3_exp(const double* k, double* E) { pcr::se3_exp(k, E); }
+void shim_t2se3(double* T) { pcr::t2se3(T); }
+void shim_mat4_mul(const double* A, const double* B, double* C) { pcr::mat4_mul(A, B, C); }
+void shim_eig_sym3(const double* A, double* w, double* V) {
+  double a[3][3], ww[3], vv[3][3];
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) a[r][c] = A[r * 3 + c];
+  pcr::eig_sym3(a, ww, vv);
+  for (int r = 0; r < 3; r++) { w[r] = ww[r]; for (int c = 0; c < 3; c++) V[r * 3 + c] = vv[r][c]; }
+}
+void shim_inv3(const double* A, double* O) {
+  double a[3][3], o[3][3];
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) a[r][c] = A[r * 3 + c];
+  pcr::inv3(a, o);
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) O[r * 3 + c] = o[r][c];
+}
+void shim_svd6(const double* A, const double* b, double* x) { pcr::hm::svd6_solve(A, b, x); }
+void shim_ndt_pose(const double* p, float* M) { pcr::hm::ndt_pose_matrix_f32(p, M); }
+void shim_euler(const float* R, float* e) { pcr::hm::euler_xyz_f32(R, e); }
+void shim_so3_exp(const double* om, double* R) { pcr::hm::so3_exp_matrix(om, R); }
+void shim_angle_tables(const double* p, float* jf, float* hf, double* jd, double* hd) {
+  float j[8][3], h[15][3];
+  double jdd[8][3], hdd[15][3];
+  pcr::hm::ndt_angle_tables(p, j, h, jdd, hdd);
+  std::memcpy(jf, j, sizeof(j)); std::memcpy(hf, h, sizeof(h)); std::memcpy(jd, jdd, sizeof(jdd)); std::memcpy(hd, hdd, sizeof(hdd));
+}
+}
