@@ -151,3 +151,20 @@ def verify_loop(kfs, old_key, cur_key, ds=0.5, rng=1, thresh=0.3, threads=8):
     _, d2 = orc.knn(target, q.astype(np.float64), 1, metric_float=True, cell=1.0, threads=threads)
     fs = float(d2.mean())
     return dict(converged=bool(r["converged"]), fitness=fs, accepted=bool(r["converged"] and fs < thresh), T=r["T"], map_points=len(target))
+
+
+def loop_closure_pass(kfs, ds=0.5, rng=1, thresh=0.3, lidar_height=2.0, threads=8, **sc_params):
+    """LoopClosureManager::addContext + lcHandler over all keyframes: ScanContext candidates -> VGICP verification"""
+    from . import pyscancontext as osc
+    sc = osc.OracleScanContext(lidar_height=lidar_height, **sc_params)
+    for cloud, _ in kfs:
+        sc.add(orc.voxel_downsample(cloud, ds)["points"])
+    loops, checked = [], []
+    for i in range(len(kfs)):
+        old, _ = sc.query(i)
+        if old >= 0:
+            r = verify_loop(kfs, old, i, ds, rng, thresh, threads)
+            checked.append(dict(r, old=old, cur=i))
+            if r["accepted"]:
+                loops.append((old, i, np.linalg.inv(kfs[old][1]) @ kfs[i][1]))
+    return loops, checked

@@ -264,3 +264,41 @@ class ScanContext:
         if best > self.dist_thres:
             return -1, 0.0
         return nn, float(np.float32(np.float32(360.0 / 60.0) * arg) * np.pi / 180.0)
+
+
+class LoopClosureManager:
+    """backend::LoopClosureManager (backend/src/LoopClosureManager.cpp:28-119) without threads: addContext() turns every new
+    keyframe into a ScanContext (0.5 m downsample first, :31-35), lcHandler() queries each new context and verifies the
+    candidates with VGICP in loop-closure mode + the fitness gate. Returns the accepted loops as (oldKey, curKey,
+    old_pose^-1 * cur_pose) — the reference stores the relative pose of the CURRENT keyframe poses, not the refined one
+    (:106-108)."""
+
+    def __init__(self, keyframes, context_pc_ds=0.5, history_submap_range=1, fitness_score=0.3, lidar_height=2.0, device=0, **sc_params):
+        self.keyframes = keyframes   # the MapManager's list of (cloud, pose): shared, grows as mapping proceeds
+        self.ds = float(context_pc_ds)
+        self.verifier = LoopClosureVerifier(keyframes, context_pc_ds, history_submap_range, fitness_score, device=device)
+        self.ctb = ScanContext(self.verifier.ctx, lidar_height=lidar_height, **sc_params)
+        self.n_contexts = 0
+        self.lc_size = 0
+        self.loops = []
+        self.checked = []            # every verified candidate: dict of LoopClosureVerifier.verify
+
+    def addContext(self):
+        new = self.keyframes[self.n_contexts:]
+        if new:
+            self.ctb.addContext(*[self.verifier.ctx.voxel_downsample(kf[0], self.ds) for kf in new])
+            self.n_contexts = len(self.keyframes)
+
+    def lcHandler(self):
+        for i in range(self.lc_size, self.ctb.size()):
+            old, _yaw = self.ctb.query(i)
+            if old >= 0:
+                r = self.verifier.verify(old, i)
+                self.checked.append(r)
+                if r["accepted"]:
+                    self.loops.append((old, i, np.linalg.inv(self.keyframes[old][1]) @ self.keyframes[i][1]))
+        self.lc_size = self.ctb.size()
+        return self.loops
+
+    def close(self):
+        self.verifier.close()

@@ -114,3 +114,28 @@ def test_frontend_and_scancontext_against_golden():
     dist, shift = lo.ctx.scancontext_distance(desc, [(0, 3)], 0.1, True)
     assert abs(dist[0] - g["sc_dist"][1]) < 1e-12 and shift[0] == g["sc_shift"][1]
     lo.close()
+
+
+def test_loop_closure_manager_pipeline():
+    """ScanContext candidate -> history submap -> VGICP (LC mode) -> fitness gate, GPU pipeline against the CPU restatement"""
+    seq = workloads.c5_sequence(60, speed=30.0)
+    kfs = [(np.ascontiguousarray(f["scan"]), f["truth"]) for f in seq["frames"]]
+    kfs.append((kfs[7][0].copy(), kfs[7][1] @ synth_exp([0.1, -0.05, 0.0, 0, 0, np.deg2rad(0.5)])))   # a revisit of keyframe 7 with drift
+    lcm = frontend.LoopClosureManager(kfs)
+    lcm.addContext()
+    loops = lcm.lcHandler()
+    oloops, ochecked = opf.loop_closure_pass(kfs)
+    assert [(a, b) for a, b, _ in loops] == [(a, b) for a, b, _ in oloops]
+    assert len(lcm.checked) == len(ochecked) >= 1
+    for g, o in zip(lcm.checked, ochecked):
+        assert (g["old"], g["cur"]) == (o["old"], o["cur"]) and g["converged"] == o["converged"] and g["accepted"] == o["accepted"]
+        dt, dr = data.pose_err(g["T"], o["T"])
+        assert dt < 1e-4 and dr < 1e-4 and abs(g["fitness"] - o["fitness"]) <= 1e-6 * max(o["fitness"], 1e-12)
+    assert (7, len(kfs) - 1) in [(a, b) for a, b, _ in loops]
+    assert lcm.addContext() is None and lcm.lcHandler() == loops      # nothing new: idempotent
+    lcm.close()
+
+
+def synth_exp(x):
+    from simpleslam_b200 import synth
+    return synth.se3_exp(x)
