@@ -8,7 +8,7 @@
  *   PCR::VgicpRegister  (PCR/src/VgicpRegister.cpp:21-45    -> fast_gicp::FastVGICP)
  * plus the frontend's voxel downsample (common/pcp/pcp.hpp:15-28, frontend/src/LidarOdometry.cpp:170-171)
  * need from a GPU. Plain pointers and sizes only; no C++/torch/PCL/Eigen types cross this boundary.
- * The header-only C++ adaptor simpleslam_b200/cpp/PCR/*.hpp re-creates the reference's class interface on top.
+ * The header-only C++ adaptor simpleslam_b200/cpp/PCR/ (one .hpp per register) re-creates the reference's class interface on top.
  *
  * Conventions
  *  - Clouds: array of records, `stride` bytes apart, float x,y,z at byte offset 0 and (if stride >= 20)
