@@ -204,6 +204,10 @@ typedef struct pcr_loam_iter_log {
  * failed before 5 were found), status[ns] (0 gate, 1 plane invalid, 2 weight, 3 accepted), JtJ[36], JtE[6], n */
 int pcr_loam_linearize(pcr_ctx* c, const void* src, size_t ns, size_t stride, const double T[16], int32_t* knn_idx,
                        int32_t* status, double JtJ[36], double JtE[6], int64_t* n_acc);
+/* kernel shape the last pcr_align / pcr_batch_align / pcr_loam_linearize of a LOAM context ran with: shape[0] = lanes per query
+ * (1, 2, 4, 8), shape[1] = queries per warp pass, shape[2] = 1 when the iteration ran as the search kernel + the fit kernel
+ * (large batches), 0 for the fused kernel. Lets the parity tests assert WHICH kernel variant they compared with the oracle. */
+int pcr_loam_last_shape(pcr_ctx* c, int32_t shape[3]);
 /* logs of the last pcr_align (scan 0 of a batch): returns count in *n */
 int pcr_loam_get_logs(pcr_ctx* c, pcr_loam_iter_log* logs, int32_t cap, int32_t* n);
 

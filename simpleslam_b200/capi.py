@@ -24,7 +24,7 @@ SYMBOLS = [
     "pcr_loam_get_logs", "pcr_ndt_num_leaves", "pcr_ndt_get_leaves", "pcr_ndt_derivatives", "pcr_ndt_hessian",
     "pcr_gicp_covariances", "pcr_vgicp_num_voxels", "pcr_vgicp_get_voxels", "pcr_vgicp_evaluate",
     "pcr_submap_build", "pcr_submap_cache_clear", "pcr_target_save", "pcr_target_load", "pcr_read_pcd", "pcr_static_map_load",
-    "pcr_scancontext_make", "pcr_scancontext_distance",
+    "pcr_scancontext_make", "pcr_scancontext_distance", "pcr_loam_last_shape",
 ]
 
 
@@ -334,6 +334,11 @@ class Context:
         self._check(lib().pcr_loam_linearize(self._h, _vp(a), ctypes.c_size_t(n), ctypes.c_size_t(st), _vp(Tb), _vp(idx), _vp(status), _vp(JtJ),
                                              _vp(JtE), ctypes.byref(nacc)))
         return dict(knn_idx=idx[:n], status=status[:n], JtJ=JtJ.reshape(6, 6), JtE=JtE, n=nacc.value)
+
+    def loam_last_shape(self):
+        sh = np.zeros(3, np.int32)
+        self._check(lib().pcr_loam_last_shape(self._h, _vp(sh)))
+        return dict(lpq=int(sh[0]), tile=int(sh[1]), split=bool(sh[2]))
 
     def loam_logs(self, cap=64):
         logs = (LoamIterLog * cap)()

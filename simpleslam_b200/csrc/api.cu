@@ -981,6 +981,12 @@ extern "C" int pcr_loam_linearize(pcr_ctx* c, const void* src, size_t ns, size_t
   PCR_API_END(c)
 }
 
+extern "C" int pcr_loam_last_shape(pcr_ctx* c, int32_t shape[3]) {
+  if (!c || !shape) return PCR_ERR_INVALID;
+  shape[0] = c->loam.last_lpq; shape[1] = c->loam.last_tile; shape[2] = c->loam.last_split ? 1 : 0;
+  return PCR_OK;
+}
+
 extern "C" int pcr_loam_get_logs(pcr_ctx* c, pcr_loam_iter_log* logs, int32_t cap, int32_t* n) {
   if (!c || !n) return PCR_ERR_INVALID;
   int cnt = std::min(c->loam.last_log_count, cap);

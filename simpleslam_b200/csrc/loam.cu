@@ -463,6 +463,7 @@ static void loam_opt_in_smem() {
   opt_in_one<1, false>(); opt_in_one<2, false>(); opt_in_one<4, false>(); opt_in_one<8, false>();
   opt_in_one<1, true>(); opt_in_one<2, true>(); opt_in_one<4, true>(); opt_in_one<8, true>();
   PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<1, false, kModeFit>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
+  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<1, true, kModeFit>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
   done = true;
 }
 
@@ -562,6 +563,7 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
   }
   // large batches (one lane per query, full tiles): search and fit as two kernels per iteration, see kModeSearch
   const bool split = lpq == 1 && tile == 32 && env_int("PCR_LOAM_SPLIT", 1) != 0;
+  last_lpq = lpq; last_tile = tile; last_split = split;
   if (grid.built && grid.has_start && max_pts > 0) {
     if (split) knn_buf.ensure(7 * total_q);
     const size_t search_pb = size_t(kLoamWarps) * 32;
@@ -613,6 +615,9 @@ int LoamDriver::linearize(const float4* src, size_t ns, const CellGrid& grid, co
   for (int q = 0; q < 16; q++) hs->T[q] = T[q];
   int tile = 32, lpq = 1;
   pick_shape(ns, lpq, tile);
+  // the same kernel selection as align(): with one lane per query and full tiles (large batches, or forced through the
+  // PCR_LOAM_LPQ / PCR_LOAM_TILE knobs) the linearisation runs as the search kernel followed by the fit kernel
+  const bool split = lpq == 1 && tile == 32 && env_int("PCR_LOAM_SPLIT", 1) != 0;
   const double slack = grid_slack_cells(grid.g);
   const size_t per_block = size_t(kLoamWarps) * tile;
   int max_blocks = int((ns + per_block - 1) / per_block);
@@ -624,11 +629,24 @@ int LoamDriver::linearize(const float4* src, size_t ns, const CellGrid& grid, co
   PCR_CUDA_CHECK(cudaMemcpyAsync(states.p, hs, sizeof(LoamState), cudaMemcpyHostToDevice, s));
   PCR_CUDA_CHECK(cudaMemcpyAsync(offsets.p, ho, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   PCR_CUDA_CHECK(cudaMemsetAsync(logs.p, 0, sizeof(pcr_loam_iter_log), s));
+  last_split = false;
   if (ns > 0 && grid.built && grid.has_start) {
     GridView view = make_view(grid);
-    launch_iter<true>(lpq, dim3(max_blocks, 1), s, src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 0, tile, slack,
-                      grid.max_ring, dbg_knn.p, dbg_status.p);
+    if (split) {
+      knn_buf.ensure(7 * ns);
+      const size_t search_pb = size_t(kLoamWarps) * 32;
+      const dim3 sgrid(unsigned((ns + search_pb - 1) / search_pb), 1);
+      loam_iter_kernel<1, false, kModeSearch><<<sgrid, kLoamBlock, 0, s>>>(src, offsets.p, view, prm, states.p, partials.p, int(sgrid.x), logs.p, 0, 32, slack,
+                                                                          grid.max_ring, nullptr, nullptr, knn_buf.p, ns);
+      loam_iter_kernel<1, true, kModeFit><<<dim3(max_blocks, 1), kLoamBlock, kLoamDynSmem, s>>>(src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p,
+                                                                                               0, 32, slack, grid.max_ring, dbg_knn.p, dbg_status.p, knn_buf.p, ns);
+      last_split = true;
+    } else {
+      launch_iter<true>(lpq, dim3(max_blocks, 1), s, src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 0, tile, slack,
+                        grid.max_ring, dbg_knn.p, dbg_status.p);
+    }
   }
+  last_lpq = lpq; last_tile = tile;
   pcr_loam_iter_log* hl = h_logs.ensure(size_t(prm.max_iters));
   PCR_CUDA_CHECK(cudaMemcpyAsync(hl, logs.p, sizeof(pcr_loam_iter_log), cudaMemcpyDeviceToHost, s));
   PCR_CUDA_CHECK(cudaStreamSynchronize(s));

@@ -43,6 +43,8 @@ struct LoamDriver {
   long long pt_evals = 0;
   float hot_ms = 0.f;
   int hot_launches = 0;
+  int last_lpq = 0, last_tile = 0;  // kernel shape of the last align / linearize call (introspection: pcr_loam_last_shape)
+  bool last_split = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
   ~LoamDriver();
