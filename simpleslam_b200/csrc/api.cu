@@ -1024,18 +1024,14 @@ static int ndt_eval_one(pcr_ctx* c, const void* src, size_t ns, size_t stride, c
                         NdtEvalResult& out) {
   if (c->prm.method != PCR_NDT || !c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no NDT target");
   const float4* d = upload_points(c, src, ns, stride, c->raw_src, c->src);
-  uint32_t* ho = c->ndtd.h_offsets.ensure(2);
-  ho[0] = 0; ho[1] = uint32_t(ns);
-  c->ndtd.offsets.ensure(2);
-  PCR_CUDA_CHECK(cudaMemcpyAsync(c->ndtd.offsets.p, ho, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  NdtEvalParams* ep = c->ndtd.h_params.ensure(1);
+  NdtEvalParams ep;
+  memset(&ep, 0, sizeof(ep));
   float Tm[16];
   if (Tf) memcpy(Tm, Tf, sizeof(Tm)); else hm::ndt_pose_matrix_f32(p, Tm);
-  memcpy(ep->Tf, Tm, sizeof(Tm));
-  hm::ndt_angle_tables(p, ep->j_ang, ep->h_ang, ep->j_ang_d, ep->h_ang_d);
-  ep->compute_hessian = hess; ep->kind = kind; ep->scan = 0; ep->pad = 0;
-  c->ndtd.evaluate(d, c->ndtd.offsets.p, ns, c->ndt, c->prm.ndt_search, 1, false, c->stream);
-  out = c->ndtd.h_results.p[0];
+  memcpy(ep.Tf, Tm, sizeof(Tm));
+  hm::ndt_angle_tables(p, ep.j_ang, ep.h_ang, ep.j_ang_d, ep.h_ang_d);
+  ep.compute_hessian = hess; ep.kind = kind; ep.scan = 0; ep.pad = 0;
+  c->ndtd.evaluate_one(d, ns, c->ndt, c->prm.ndt_search, ep, out, c->stream);
   return PCR_OK;
 }
 

@@ -2,6 +2,7 @@
 #include "ndt.cuh"
 #include "dev_linalg.cuh"
 #include "host_math.hpp"
+#include <cstdlib>
 #include <cfloat>
 #include <algorithm>
 #include <cstdlib>
@@ -149,8 +150,8 @@ int ndt_build_target(const float4* pts, size_t n, const pcr_params& prm, NdtTarg
 // N2 + N3 + N4. Source points are strided over the threads of a request's blocks. Per point: float transform,
 // DIRECT{7,1,26} voxel lookups (all table loads issued up front), then per valid leaf the FP32 score / gradient /
 // Hessian terms of updateDerivatives, accumulated in FP64 registers (leaf records software-prefetched one ahead).
-// Deterministic warp-shuffle + block + last-block reduction; the last block writes the 29 sums straight into
-// host-mapped pinned memory, so one kernel launch + one stream sync is the whole evaluation.
+// Deterministic warp-shuffle + block + last-block reduction; the last block of a request then advances the scan's
+// Newton / More-Thuente state machine on the device (ndt_round_kernel below).
 // ================================================================================================================
 struct NdtTargetView {
   const NdtLeafRec* recs;
@@ -301,535 +302,450 @@ __device__ __forceinline__ void ndt_pair_f64(const NdtTargetView& tgt, int id, c
     }
 }
 
+// ================================================================================================================
+// One evaluation ROUND for every scan that is waiting for this kind of evaluation (float computeDerivatives or
+// double-path computeHessian). Flat 1-D grid = one resident wave. Every block
+//   1. compacts the list of scans whose stamp says "evaluate me in this round" (deterministic order, no atomics),
+//   2. takes its share of the (request, sub-block) items: the wave is re-partitioned among the ACTIVE scans every round,
+//   3. evaluates its points (FP32 pair math, FP64 shared-memory accumulators), writes its partial sums,
+//   4. and, if it is the last block of its request, sums the partials in fixed order and advances the scan's Newton /
+//      More-Thuente state machine (ndt_logic.cuh) by this result: the next evaluation's transform and angle tables are
+//      written to the scan's state and its stamp is set for the kernel that has to serve it (the double-path kernel of
+//      the same round, or the float kernel of the next round).
+// Stamps are only ever written for LATER kernels, so every block of a launch sees the same request list.
+// ================================================================================================================
+constexpr int kNdtMaxBatch = 2048;  // scans per driver chunk (request list lives in shared memory)
+
+__device__ __noinline__ void ndt_state_step(NdtScanState* st, const double* totals, NdtCfg cfg) { ndt_logic::on_result(*st, totals, cfg); }
+
 template <int SEARCH, bool DOUBLE_PATH>
 __global__ void __launch_bounds__(kNdtBlock, DOUBLE_PATH ? 2 : 5)
-ndt_eval_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, NdtTargetView tgt,
-                const NdtEvalParams* __restrict__ params, NdtEvalResult* __restrict__ results, double* __restrict__ partials,
-                unsigned* __restrict__ tickets, int max_blocks, int req_base) {
+ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, NdtTargetView tgt, NdtScanState* __restrict__ states,
+                 NdtScanOut* __restrict__ outs, int32_t* __restrict__ float_round, int32_t* __restrict__ hess_round, int n_scans, int round,
+                 int step, NdtCfg cfg, double* __restrict__ partials, unsigned* __restrict__ tickets, NdtProgress* progress,
+                 NdtCounters* __restrict__ counters) {
   constexpr int NNB = NbTraits<SEARCH>::N;
-  const int req = req_base + blockIdx.y;
-  __shared__ NdtEvalParams sp;
+  __shared__ __align__(16) NdtScanState s_state;
   __shared__ double sacc[kNdtNV * kNdtBlock];
+  __shared__ double s_tot[kNdtNV + 1];
+  __shared__ unsigned short s_list[kNdtMaxBatch];
+  __shared__ int s_warp_cnt[kNdtBlock / 32];
   __shared__ int s_last;
-  {
-    const int nwords = sizeof(NdtEvalParams) / 4;
-    const int* gp = reinterpret_cast<const int*>(params + req);
-    int* spw = reinterpret_cast<int*>(&sp);
-    for (int k = threadIdx.x; k < nwords; k += kNdtBlock) spw[k] = gp[k];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // ---- 1. request list of this launch
+  const int32_t* stamps = DOUBLE_PATH ? hess_round : float_round;
+  const int per = (n_scans + kNdtBlock - 1) / kNdtBlock;
+  const int lo = min(tid * per, n_scans), hi = min(lo + per, n_scans);
+  int cnt = 0;
+  for (int k = lo; k < hi; k++) cnt += (stamps[k] == round) ? 1 : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
   }
+  if (lane == 31) s_warp_cnt[warp] = incl;
   __syncthreads();
-  const uint32_t begin = offs[sp.scan], end = offs[sp.scan + 1];
-  const int nb = min(int((end - begin + kNdtBlock - 1) / kNdtBlock), max_blocks);  // blocks working on this request
-  if (int(blockIdx.x) >= nb) return;
-
-  SmemAcc acc{sacc + threadIdx.x};
+  int base = 0, n_active = 0;
 #pragma unroll
-  for (int k = 0; k < kNdtNV; k++) sacc[k * kNdtBlock + threadIdx.x] = 0.0;
+  for (int w = 0; w < kNdtBlock / 32; w++) {
+    if (w < warp) base += s_warp_cnt[w];
+    n_active += s_warp_cnt[w];
+  }
+  int pos = base + incl - cnt;
+  for (int k = lo; k < hi; k++)
+    if (stamps[k] == round) s_list[pos++] = (unsigned short)k;
+  if (blockIdx.x == 0 && tid == 0) {
+    if (!DOUBLE_PATH && progress) progress->round = round;
+    if (n_active > 0) atomicAdd(&counters->work_launches, 1);
+  }
+  if (n_active == 0) return;
+  __syncthreads();
+
+  // ---- 2. my items
+  const int bpr = max(1, int(gridDim.x) / n_active);  // blocks per request
+  const int n_items = n_active * bpr;
   const GridSpec& g = tgt.g;
-  const bool hess = sp.compute_hessian != 0;
+  SmemAcc acc{sacc + tid};
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int req = item / bpr, sub = item - req * bpr;
+    const int scan = s_list[req];
+    const uint32_t begin = offs[scan], end = offs[scan + 1];
+    const int nb = max(1, min(int((end - begin + kNdtBlock - 1) / kNdtBlock), bpr));  // blocks working on this request
+    if (sub >= nb) continue;  // block-uniform
+    {
+      const int nwords = sizeof(NdtScanState) / 16;
+      const uint4* gp = reinterpret_cast<const uint4*>(states + scan);
+      uint4* sp4 = reinterpret_cast<uint4*>(&s_state);
+      for (int k = tid; k < nwords; k += kNdtBlock) sp4[k] = gp[k];
+    }
+#pragma unroll
+    for (int k = 0; k < kNdtNV; k++) sacc[k * kNdtBlock + tid] = 0.0;
+    __syncthreads();
+    const NdtEvalParams& sp = s_state.next;
+    const bool hess = sp.compute_hessian != 0;
 
-  for (uint32_t i = begin + blockIdx.x * kNdtBlock + threadIdx.x; i < end; i += uint32_t(nb) * kNdtBlock) {
-    const float4 po = __ldg(src + i);
-    // pcl::transformPointCloud (float): ((m00 x + m01 y) + m02 z) + m03
-    float pt[3];
+    for (uint32_t i = begin + sub * kNdtBlock + tid; i < end; i += uint32_t(nb) * kNdtBlock) {
+      const float4 po = __ldg(src + i);
+      // pcl::transformPointCloud (float): ((m00 x + m01 y) + m02 z) + m03
+      float pt[3];
 #pragma unroll
-    for (int r = 0; r < 3; r++)
-      pt[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(sp.Tf[r], po.x), __fmul_rn(sp.Tf[4 + r], po.y)), __fmul_rn(sp.Tf[8 + r], po.z)),
-                        sp.Tf[12 + r]);
-    // voxel of the transformed point: floor(p / leaf)  (voxel_grid_covariance_omp_impl.hpp:379-381)
-    float fi[3];
-    bool ok = true;
+      for (int r = 0; r < 3; r++)
+        pt[r] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(sp.Tf[r], po.x), __fmul_rn(sp.Tf[4 + r], po.y)), __fmul_rn(sp.Tf[8 + r], po.z)),
+                          sp.Tf[12 + r]);
+      // voxel of the transformed point: floor(p / leaf)  (voxel_grid_covariance_omp_impl.hpp:379-381)
+      float fi[3];
+      bool ok = true;
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-      fi[a] = floorf(__fdiv_rn(pt[a], g.leaf[a]));
-      if (!(fabsf(fi[a]) < 1.0e9f)) ok = false;
-    }
-    if (!ok) continue;
-    const int ijk[3] = {int(fi[0]), int(fi[1]), int(fi[2])};
-    // ---- phase 1: all neighbourhood table lookups in flight at once
-    int ids[NNB];
-#pragma unroll
-    for (int ni = 0; ni < NNB; ni++) {
-      int ox, oy, oz;
-      nb_offset<SEARCH>(ni, ox, oy, oz);
-      const int cx = ijk[0] + ox, cy = ijk[1] + oy, cz = ijk[2] + oz;
-      const bool inb = cx >= g.min_b[0] && cx <= g.max_b[0] && cy >= g.min_b[1] && cy <= g.max_b[1] && cz >= g.min_b[2] && cz <= g.max_b[2];
-      const long long key = (long long)(cx - g.min_b[0]) * g.mul[0] + (long long)(cy - g.min_b[1]) * g.mul[1] +
-                            (long long)(cz - g.min_b[2]) * g.mul[2];
-      ids[ni] = inb ? __ldg(tgt.table + key) : -1;
-    }
-    if (SEARCH == PCR_NDT_KDTREE) {
-      // N6: VoxelGridCovariance::radiusSearch — leaves of the centroid cloud whose float centroid is within `resolution`
-      // of the point: FLANN L2_Simple<float> metric (x->y->z float accumulate), strict d2 < r^2
+      for (int a = 0; a < 3; a++) {
+        fi[a] = floorf(__fdiv_rn(pt[a], g.leaf[a]));
+        if (!(fabsf(fi[a]) < 1.0e9f)) ok = false;
+      }
+      if (!ok) continue;
+      const int ijk[3] = {int(fi[0]), int(fi[1]), int(fi[2])};
+      // all neighbourhood table lookups in flight at once
+      int ids[NNB];
 #pragma unroll
       for (int ni = 0; ni < NNB; ni++) {
-        int id = ids[ni];
-        if (id <= -2) id = -2 - id;
-        if (id >= 0) {
-          const float4 c = __ldg(tgt.centroids + id);
-          const float dx = __fsub_rn(pt[0], c.x), dy = __fsub_rn(pt[1], c.y), dz = __fsub_rn(pt[2], c.z);
-          const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-          if (!(d2 < tgt.radius2)) id = -1;
-        }
-        ids[ni] = id;
+        int ox, oy, oz;
+        nb_offset<SEARCH>(ni, ox, oy, oz);
+        const int cx = ijk[0] + ox, cy = ijk[1] + oy, cz = ijk[2] + oz;
+        const bool inb = cx >= g.min_b[0] && cx <= g.max_b[0] && cy >= g.min_b[1] && cy <= g.max_b[1] && cz >= g.min_b[2] && cz <= g.max_b[2];
+        const long long key = (long long)(cx - g.min_b[0]) * g.mul[0] + (long long)(cy - g.min_b[1]) * g.mul[1] +
+                              (long long)(cz - g.min_b[2]) * g.mul[2];
+        ids[ni] = inb ? __ldg(tgt.table + key) : -1;
       }
-    }
-    unsigned mask = 0;
+      if (SEARCH == PCR_NDT_KDTREE) {
+        // N6: VoxelGridCovariance::radiusSearch — leaves of the centroid cloud whose float centroid is within `resolution`
+        // of the point: FLANN L2_Simple<float> metric (x->y->z float accumulate), strict d2 < r^2
 #pragma unroll
-    for (int ni = 0; ni < NNB; ni++) mask |= (ids[ni] >= 0) ? (1u << ni) : 0u;
-    if (!mask) continue;
-    auto pick = [&](int k) {
-      int v = ids[0];
-#pragma unroll
-      for (int ni = 1; ni < NNB; ni++) v = (k == ni) ? ids[ni] : v;
-      return v;
-    };
-    if (!DOUBLE_PATH) {
-      float xj[8], xh[15];
-#pragma unroll
-      for (int r = 0; r < 8; r++) xj[r] = (sp.j_ang[r][0] * po.x + sp.j_ang[r][1] * po.y) + sp.j_ang[r][2] * po.z;
-#pragma unroll
-      for (int r = 0; r < 15; r++) xh[r] = hess ? (sp.h_ang[r][0] * po.x + sp.h_ang[r][1] * po.y) + sp.h_ang[r][2] * po.z : 0.f;
-      // ---- phase 2: neighbours in reference order, next leaf record prefetched while the current one is evaluated
-      int k = __ffs(mask) - 1;
-      mask &= mask - 1;
-      LeafRegs cur = load_leaf(tgt.recs, pick(k));
-      while (true) {
-        LeafRegs nxt = cur;
-        const bool more = mask != 0;
-        if (more) {
-          k = __ffs(mask) - 1;
-          mask &= mask - 1;
-          nxt = load_leaf(tgt.recs, pick(k));
+        for (int ni = 0; ni < NNB; ni++) {
+          int id = ids[ni];
+          if (id <= -2) id = -2 - id;
+          if (id >= 0) {
+            const float4 c = __ldg(tgt.centroids + id);
+            const float dx = __fsub_rn(pt[0], c.x), dy = __fsub_rn(pt[1], c.y), dz = __fsub_rn(pt[2], c.z);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (!(d2 < tgt.radius2)) id = -1;
+          }
+          ids[ni] = id;
         }
-        ndt_pair_f32(cur, pt, xj, xh, hess, tgt.d2f, tgt.d1, acc);
-        if (!more) break;
-        cur = nxt;
       }
-    } else {
-      const double x[3] = {double(po.x), double(po.y), double(po.z)};
-      double xj[8], xh[15];
+      unsigned mask = 0;
 #pragma unroll
-      for (int r = 0; r < 8; r++) xj[r] = x[0] * sp.j_ang_d[r][0] + x[1] * sp.j_ang_d[r][1] + x[2] * sp.j_ang_d[r][2];
+      for (int ni = 0; ni < NNB; ni++) mask |= (ids[ni] >= 0) ? (1u << ni) : 0u;
+      if (!mask) continue;
+      auto pick = [&](int k) {
+        int v = ids[0];
 #pragma unroll
-      for (int r = 0; r < 15; r++) xh[r] = x[0] * sp.h_ang_d[r][0] + x[1] * sp.h_ang_d[r][1] + x[2] * sp.h_ang_d[r][2];
-      while (mask) {
-        const int k = __ffs(mask) - 1;
+        for (int ni = 1; ni < NNB; ni++) v = (k == ni) ? ids[ni] : v;
+        return v;
+      };
+      if (!DOUBLE_PATH) {
+        float xj[8], xh[15];
+#pragma unroll
+        for (int r = 0; r < 8; r++) xj[r] = (sp.j_ang[r][0] * po.x + sp.j_ang[r][1] * po.y) + sp.j_ang[r][2] * po.z;
+#pragma unroll
+        for (int r = 0; r < 15; r++) xh[r] = hess ? (sp.h_ang[r][0] * po.x + sp.h_ang[r][1] * po.y) + sp.h_ang[r][2] * po.z : 0.f;
+        // neighbours in reference order, next leaf record prefetched while the current one is evaluated
+        int k = __ffs(mask) - 1;
         mask &= mask - 1;
-        ndt_pair_f64(tgt, pick(k), pt, xj, xh, acc);
+        LeafRegs cur = load_leaf(tgt.recs, pick(k));
+        while (true) {
+          LeafRegs nxt = cur;
+          const bool more = mask != 0;
+          if (more) {
+            k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            nxt = load_leaf(tgt.recs, pick(k));
+          }
+          ndt_pair_f32(cur, pt, xj, xh, hess, tgt.d2f, tgt.d1, acc);
+          if (!more) break;
+          cur = nxt;
+        }
+      } else {
+        const double x[3] = {double(po.x), double(po.y), double(po.z)};
+        double xj[8], xh[15];
+#pragma unroll
+        for (int r = 0; r < 8; r++) xj[r] = x[0] * sp.j_ang_d[r][0] + x[1] * sp.j_ang_d[r][1] + x[2] * sp.j_ang_d[r][2];
+#pragma unroll
+        for (int r = 0; r < 15; r++) xh[r] = x[0] * sp.h_ang_d[r][0] + x[1] * sp.h_ang_d[r][1] + x[2] * sp.h_ang_d[r][2];
+        while (mask) {
+          const int k = __ffs(mask) - 1;
+          mask &= mask - 1;
+          ndt_pair_f64(tgt, pick(k), pt, xj, xh, acc);
+        }
       }
     }
-  }
 
-  // fixed-order block reduction straight out of shared memory: warp w owns components w, w+4, ...
-  __syncthreads();
-  {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- 3. fixed-order block reduction straight out of shared memory: warp w owns components w, w+4, ...
+    __syncthreads();
     for (int k = warp; k < kNdtNV; k += kNdtBlock / 32) {
       const double* col = sacc + k * kNdtBlock;
       double v = ((col[lane] + col[lane + 32]) + col[lane + 64]) + col[lane + 96];
       v = warp_sum(v);
-      if (lane == 0) partials[(size_t(req) * max_blocks + blockIdx.x) * kNdtNV + k] = v;
+      if (lane == 0) partials[size_t(item) * kNdtNV + k] = v;
     }
     if (lane == 0) __threadfence();  // one fence per writer warp, after all of its partial sums
+    __syncthreads();
+    if (tid == 0) {
+      unsigned t = atomicAdd(tickets + scan, 1u);
+      s_last = (t == unsigned(nb - 1));
+    }
+    __syncthreads();
+    if (!s_last) continue;  // block-uniform
+    // ---- 4. last block of the request: totals, then the scan's state machine
+    __threadfence();
+    if (tid < kNdtNV) {
+      const double* pb = partials + size_t(req) * bpr * kNdtNV + tid;
+      double tsum = 0.0;
+      for (int b = 0; b < nb; b++) tsum += __ldcg(pb + size_t(b) * kNdtNV);
+      s_tot[tid] = tsum;
+    }
+    __syncthreads();
+    if (tid < 30) outs[scan].v[tid] = tid < kNdtNV ? s_tot[tid] : 0.0;
+    if (tid == 0) {
+      tickets[scan] = 0;
+      atomicAdd(reinterpret_cast<unsigned long long*>(&counters->point_evals), (unsigned long long)(end - begin));
+      if (step) ndt_state_step(&s_state, s_tot, cfg);
+    }
+    __syncthreads();
+    if (step) {
+      const int nwords = sizeof(NdtScanState) / 16;
+      uint4* gp = reinterpret_cast<uint4*>(states + scan);
+      const uint4* sp4 = reinterpret_cast<const uint4*>(&s_state);
+      for (int k = tid; k < nwords; k += kNdtBlock) gp[k] = sp4[k];
+      if (tid == 0) {
+        if (s_state.pend == NDT_PEND_FLOAT) float_round[scan] = round + 1;
+        else if (s_state.pend == NDT_PEND_DOUBLE) hess_round[scan] = round;  // served by the double-path kernel of this round
+      }
+      if (s_state.pend == NDT_PEND_NONE) {
+        NdtScanOut* o = outs + scan;
+        if (tid < 16) o->final_T[tid] = s_state.final_T[tid];
+        if (tid == 0) {
+          o->converged = s_state.converged; o->nr_iterations = s_state.nr_iterations;
+          o->n_evals = s_state.n_evals; o->n_hess = s_state.n_hess; o->n_pairs = s_state.n_pairs; o->score = s_state.score;
+          const int f = atomicAdd(&counters->finished, 1) + 1;
+          if (f == n_scans && progress) { __threadfence_system(); progress->all_done = 1; }
+        }
+      }
+    }
+    __syncthreads();  // s_state / s_tot are reused by the next item
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned t = atomicAdd(tickets + req, 1u);
-    s_last = (t == unsigned(nb - 1));
+}
+
+// start of a registration: one thread per scan runs ndt_logic::start (guess -> p, first request). Empty scans and an
+// empty target evaluate to all-zero sums (no block would contribute), which the state machine digests right here.
+__global__ void ndt_init_kernel(const double* __restrict__ guesses, const uint32_t* __restrict__ offs, NdtScanState* __restrict__ states,
+                                NdtScanOut* __restrict__ outs, int32_t* __restrict__ float_round, int32_t* __restrict__ hess_round, int n_scans,
+                                int no_target, NdtCfg cfg, NdtProgress* progress, NdtCounters* __restrict__ counters) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_scans) return;
+  NdtScanState st;
+  ndt_logic::start(st, guesses + size_t(s) * 16, s);
+  hess_round[s] = -1;
+  if (no_target || offs[s + 1] == offs[s]) {
+    double zeros[kNdtNV];
+    for (int k = 0; k < kNdtNV; k++) zeros[k] = 0.0;
+    while (st.pend != NDT_PEND_NONE) ndt_logic::on_result(st, zeros, cfg);
   }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x < kNdtNV) {
-    const double* base = partials + size_t(req) * max_blocks * kNdtNV + threadIdx.x;
-    double tsum = 0.0;
-    for (int b = 0; b < nb; b++) tsum += __ldcg(base + size_t(b) * kNdtNV);
-    results[req].v[threadIdx.x] = tsum;  // host-mapped pinned memory
+  states[s] = st;
+  if (st.pend == NDT_PEND_NONE) {
+    float_round[s] = -1;
+    NdtScanOut* o = outs + s;
+    for (int q = 0; q < 16; q++) o->final_T[q] = st.final_T[q];
+    o->converged = st.converged; o->nr_iterations = st.nr_iterations; o->n_evals = st.n_evals; o->n_hess = st.n_hess;
+    o->n_pairs = st.n_pairs; o->score = st.score;
+    const int f = atomicAdd(&counters->finished, 1) + 1;
+    if (f == n_scans && progress) { __threadfence_system(); progress->all_done = 1; }
+  } else {
+    float_round[s] = 0;
   }
-  if (threadIdx.x == 0) tickets[req] = 0;
 }
 
 NdtDriver::~NdtDriver() {
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
-  if (ready) cudaEventDestroy(ready);
-  if (second_stream) { cudaStreamSynchronize(second_stream); cudaStreamDestroy(second_stream); }
-  if (mapped_results) cudaFreeHost(mapped_results);
+  if (progress) cudaFreeHost(progress);
+}
+
+void NdtDriver::ensure_progress() {
+  if (!progress) PCR_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&progress), sizeof(NdtProgress), cudaHostAllocMapped));
+}
+
+void NdtDriver::prepare(size_t n_scans, int grid_blocks, cudaStream_t s) {
+  ensure_progress();
+  states.ensure(n_scans); outs.ensure(n_scans); stamps.ensure(2 * n_scans);
+  partials.ensure(std::max<size_t>(size_t(grid_blocks), n_scans) * kNdtNV);
+  counters.ensure(1);
+  if (tickets.cap < n_scans) {
+    tickets.ensure(n_scans);
+    PCR_CUDA_CHECK(cudaMemsetAsync(tickets.p, 0, tickets.cap * sizeof(unsigned), s));
+  }
+  PCR_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, sizeof(NdtCounters), s));
+  progress->round = -1;
+  progress->all_done = 0;
+}
+
+static NdtTargetView make_view(const NdtTarget& tgt) {
+  NdtTargetView v;
+  v.recs = tgt.recs.p; v.mean = tgt.mean.p; v.icov = tgt.icov.p; v.table = tgt.table.p; v.g = tgt.g;
+  v.centroids = tgt.centroids.p;
+  v.d1 = tgt.d1; v.d2 = tgt.d2; v.d2f = float(tgt.d2);
+  v.radius2 = float(double(tgt.resolution) * double(tgt.resolution));  // KdTreeFLANN::radiusSearch: (float)(radius * radius)
+  return v;
 }
 
 template <int SEARCH>
-static void launch_eval(bool double_path, dim3 grid, cudaStream_t s, const float4* src, const uint32_t* offs, const NdtTargetView& v,
-                        const NdtEvalParams* params, NdtEvalResult* results, double* partials, unsigned* tickets, int max_blocks, int base) {
-  if (double_path)
-    ndt_eval_kernel<SEARCH, true><<<grid, kNdtBlock, 0, s>>>(src, offs, v, params, results, partials, tickets, max_blocks, base);
+static void launch_round_t(bool dbl, int grid, cudaStream_t s, const float4* src, const uint32_t* offs, const NdtTargetView& v, NdtScanState* states,
+                           NdtScanOut* outs, int32_t* fr, int32_t* hr, int n, int round, int step, const NdtCfg& cfg, double* partials,
+                           unsigned* tickets, NdtProgress* prog, NdtCounters* cnt) {
+  if (dbl)
+    ndt_round_kernel<SEARCH, true><<<grid, kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt);
   else
-    ndt_eval_kernel<SEARCH, false><<<grid, kNdtBlock, 0, s>>>(src, offs, v, params, results, partials, tickets, max_blocks, base);
+    ndt_round_kernel<SEARCH, false><<<grid, kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt);
 }
 
-// Requests h_params[0..count) must be ordered: all float-path (kind 0) requests first, then the double-path (kind 1) ones.
-void NdtDriver::evaluate(const float4* src, const uint32_t* d_offs, size_t max_pts, const NdtTarget& tgt, int search, int count,
-                         bool profile, cudaStream_t s) {
-  launch(src, d_offs, max_pts, tgt, search, count, profile, s);
-  collect(count, profile, s);
-}
-
-void NdtDriver::launch(const float4* src, const uint32_t* d_offs, size_t max_pts, const NdtTarget& tgt, int search, int count, bool profile,
-                       cudaStream_t s) {
-  pending_run = false;
-  if (count == 0) return;
-  int n0 = 0;
-  while (n0 < count && h_params.p[n0].kind == 0) n0++;
-  // enough blocks to fill the machine a few times over, never more than one block per 128 points
-  const int full_blocks = int((max_pts + kNdtBlock - 1) / kNdtBlock);
-  // 5 blocks of 128 threads are resident per SM: one resident wave, points strided over it
-  // (floor, not ceil: every block does the same strided share of its request, so one block too many means a second wave)
-  int max_blocks = std::max(1, std::min(full_blocks, (kNumSMs * 5) / count));
-  d_params.ensure(count);
-  partials.ensure(size_t(count) * max_blocks * kNdtNV);
-  if (tickets.cap < size_t(count)) {
-    tickets.ensure(count);
-    PCR_CUDA_CHECK(cudaMemsetAsync(tickets.p, 0, tickets.cap * sizeof(unsigned), s));
-  }
-  if (mapped_cap < size_t(count)) {
-    if (mapped_results) cudaFreeHost(mapped_results);
-    mapped_cap = size_t(count) + 64;
-    PCR_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&mapped_results), mapped_cap * sizeof(NdtEvalResult), cudaHostAllocMapped));
-  }
-  memset(mapped_results, 0, size_t(count) * sizeof(NdtEvalResult));  // requests over empty scans launch no block
-  NdtEvalResult* dev_results = nullptr;
-  PCR_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_results), mapped_results, 0));
-  PCR_CUDA_CHECK(cudaMemcpyAsync(d_params.p, h_params.p, size_t(count) * sizeof(NdtEvalParams), cudaMemcpyHostToDevice, s));
-  const bool run = !tgt.overflow && tgt.nleaves > 0 && max_pts > 0;
-  if (run) {
-    for (int q = 0; q < count; q++) point_evals += h_offsets.p[h_params.p[q].scan + 1] - h_offsets.p[h_params.p[q].scan];
-    NdtTargetView v;
-    v.recs = tgt.recs.p; v.mean = tgt.mean.p; v.icov = tgt.icov.p; v.table = tgt.table.p; v.g = tgt.g;
-    v.centroids = tgt.centroids.p;
-    v.d1 = tgt.d1; v.d2 = tgt.d2; v.d2f = float(tgt.d2);
-    v.radius2 = float(double(tgt.resolution) * double(tgt.resolution));  // KdTreeFLANN::radiusSearch: (float)(radius * radius)
-    if (profile) {
-      if (!ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
-      PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
+void NdtDriver::launch_round(const float4* src, const NdtTarget& tgt, int search, int n, int round, int step, const NdtCfg& cfg, int grid_blocks,
+                             bool float_kernel, bool double_kernel, cudaStream_t s) {
+  const NdtTargetView v = make_view(tgt);
+  NdtProgress* dprog = nullptr;
+  PCR_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dprog), progress, 0));
+  int32_t* fr = stamps.p;
+  int32_t* hr = stamps.p + n;
+  for (int part = 0; part < 2; part++) {
+    if (part == 0 ? !float_kernel : !double_kernel) continue;
+    const bool dbl = part == 1;
+    switch (search) {
+      case PCR_NDT_DIRECT1: launch_round_t<PCR_NDT_DIRECT1>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p); break;
+      case PCR_NDT_DIRECT26: launch_round_t<PCR_NDT_DIRECT26>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p); break;
+      case PCR_NDT_KDTREE: launch_round_t<PCR_NDT_KDTREE>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p); break;
+      default: launch_round_t<PCR_NDT_DIRECT7>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p); break;
     }
-    for (int part = 0; part < 2; part++) {
-      const int base = part == 0 ? 0 : n0, n = part == 0 ? n0 : count - n0;
-      if (n == 0) continue;
-      dim3 grid(max_blocks, n);
-      switch (search) {
-        case PCR_NDT_DIRECT1: launch_eval<PCR_NDT_DIRECT1>(part == 1, grid, s, src, d_offs, v, d_params.p, dev_results, partials.p, tickets.p, max_blocks, base); break;
-        case PCR_NDT_DIRECT26: launch_eval<PCR_NDT_DIRECT26>(part == 1, grid, s, src, d_offs, v, d_params.p, dev_results, partials.p, tickets.p, max_blocks, base); break;
-        case PCR_NDT_KDTREE: launch_eval<PCR_NDT_KDTREE>(part == 1, grid, s, src, d_offs, v, d_params.p, dev_results, partials.p, tickets.p, max_blocks, base); break;
-        default: launch_eval<PCR_NDT_DIRECT7>(part == 1, grid, s, src, d_offs, v, d_params.p, dev_results, partials.p, tickets.p, max_blocks, base); break;
-      }
-      launches++;
-      hot_launches++;
-    }
-    if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev1, s));
+    launches++;
   }
-  pending_run = run;
 }
 
-void NdtDriver::collect(int count, bool profile, cudaStream_t s) {
-  if (count == 0) return;
-  const bool run = pending_run;
+static int wave_blocks(size_t n_scans, size_t max_pts) {
+  // one resident wave (5 blocks of 128 threads per SM), never more than one block per 128 points
+  const size_t full = (max_pts + kNdtBlock - 1) / kNdtBlock;
+  return int(std::max<size_t>(1, std::min<size_t>(size_t(kNumSMs) * 5, full * n_scans)));
+}
+
+void NdtDriver::evaluate_one(const float4* src, size_t ns, const NdtTarget& tgt, int search, const NdtEvalParams& ep, NdtEvalResult& out,
+                             cudaStream_t s) {
+  for (int k = 0; k < 30; k++) out.v[k] = 0.0;
+  if (tgt.overflow || tgt.nleaves == 0 || ns == 0) return;  // no block would contribute
+  const int grid = wave_blocks(1, ns);
+  prepare(1, grid, s);
+  uint32_t* ho = h_offsets.ensure(2);
+  ho[0] = 0; ho[1] = uint32_t(ns);
+  offsets.ensure(2);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(offsets.p, ho, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  NdtScanState* hs = h_state.ensure(1);
+  memset(hs, 0, sizeof(NdtScanState));
+  hs->next = ep;
+  hs->next.scan = 0;
+  PCR_CUDA_CHECK(cudaMemcpyAsync(states.p, hs, sizeof(NdtScanState), cudaMemcpyHostToDevice, s));
+  // stamps: the scan wants exactly this kind of evaluation in round 0
+  int32_t* hst = reinterpret_cast<int32_t*>(h_counters.ensure(1));
+  hst[0] = ep.kind == 0 ? 0 : -1;
+  hst[1] = ep.kind == 0 ? -1 : 0;
+  PCR_CUDA_CHECK(cudaMemcpyAsync(stamps.p, hst, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  NdtCfg cfg{};
+  launch_round(src, tgt, search, 1, 0, 0, cfg, grid, ep.kind == 0, ep.kind != 0, s);
+  NdtScanOut* ho_out = h_outs.ensure(1);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(ho_out, outs.p, sizeof(NdtScanOut), cudaMemcpyDeviceToHost, s));
   PCR_CUDA_CHECK(cudaStreamSynchronize(s));
   PCR_CUDA_CHECK(cudaGetLastError());
-  h_results.ensure(count);
-  memcpy(h_results.p, mapped_results, size_t(count) * sizeof(NdtEvalResult));
-  if (profile && run) {
-    float ms = 0.f;
-    PCR_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
-    hot_ms += ms;
-  }
+  for (int k = 0; k < 30; k++) out.v[k] = ho_out->v[k];
 }
 
 // ================================================================================================================
-// N5. Newton + More-Thuente driver (ndt_omp_impl.hpp:81-171, 773-932) as a per-scan state machine, so that a batch
-// of independent scans advances in lock-step with ONE kernel launch per round.
+// N5. Registration driver: the host only queues evaluation rounds. Each round = the float-path kernel followed by the
+// double-path kernel (which serves the computeHessian requests raised by the float kernel's tails in the same round).
+// How many rounds a batch needs is decided on the device; the host keeps a small number of rounds queued ahead of the
+// GPU (it reads the round counter and the all-done flag from host-mapped memory, never synchronising the stream) and
+// stops queueing when the last scan has finished. Kernels of rounds queued past that point find no request and return.
 // ================================================================================================================
-namespace {
-struct ScanState {
-  enum Phase { INIT_EVAL, LS_FIRST, LS_LOOP, LS_HESSIAN, FINISHED } phase = INIT_EVAL;
-  double p[6];
-  double score = 0;
-  double g[6];
-  double H[36];
-  float final_T[16];
-  float eval_T[16];
-  double eval_p[6];
-  int eval_kind = 0, eval_hess = 1;
-  int nr_iterations = 0;
-  bool converged = false;
-  // line search
-  double step_dir[6], phi_0, d_phi_0, a_l, f_l, g_l, a_u, f_u, g_u, a_t, x_t[6], phi_t, d_phi_t, psi_t, d_psi_t;
-  bool interval_converged, open_interval;
-  int step_iterations;
-  int n_evals = 0, n_hess = 0;
-  long long n_pairs = 0;
-};
-
-struct NdtLogic {
-  const pcr_params& prm;
-  static constexpr double mu = 1.e-4, nu = 0.9;
-  static constexpr int max_step_iterations = 10;
-
-  void request_deriv(ScanState& st, const float* T, const double* p, bool hess) {
-    std::memcpy(st.eval_T, T, sizeof(float) * 16);
-    std::memcpy(st.eval_p, p, sizeof(double) * 6);
-    st.eval_kind = 0;
-    st.eval_hess = hess ? 1 : 0;
-  }
-  void start(ScanState& st, const double* Tguess) {
-    float guess[16];
-    bool ident = true;
-    for (int i = 0; i < 16; i++) {
-      guess[i] = static_cast<float>(Tguess[i]);  // NdtRegister.cpp:27 res.matrix().cast<float>()
-      if (guess[i] != ((i % 5 == 0) ? 1.f : 0.f)) ident = false;
-    }
-    for (int i = 0; i < 16; i++) st.final_T[i] = (i % 5 == 0) ? 1.f : 0.f;
-    if (!ident) std::memcpy(st.final_T, guess, sizeof(guess));  // ndt_omp_impl.hpp:95-101
-    float Rm[9], eul[3];
-    for (int r = 0; r < 3; r++)
-      for (int c = 0; c < 3; c++) Rm[r * 3 + c] = st.final_T[c * 4 + r];
-    hm::euler_xyz_f32(Rm, eul);  // :103-111
-    st.p[0] = st.final_T[12]; st.p[1] = st.final_T[13]; st.p[2] = st.final_T[14];
-    st.p[3] = eul[0]; st.p[4] = eul[1]; st.p[5] = eul[2];
-    st.nr_iterations = 0;
-    st.converged = false;
-    st.phase = ScanState::INIT_EVAL;
-    request_deriv(st, st.final_T, st.p, true);
-  }
-  void take(ScanState& st, const NdtEvalResult& r, bool with_hessian) {
-    st.score = r.v[0];
-    for (int i = 0; i < 6; i++) st.g[i] = r.v[1 + i];
-    int k = 7;
-    for (int a = 0; a < 6; a++)
-      for (int b = a; b < 6; b++) { st.H[a * 6 + b] = with_hessian ? r.v[k] : 0.0; st.H[b * 6 + a] = st.H[a * 6 + b]; k++; }
-  }
-  void set_trial(ScanState& st) {
-    st.a_t = std::min(st.a_t, prm.ndt_step_size);
-    st.a_t = std::max(st.a_t, prm.ndt_trans_eps / 2);
-    for (int i = 0; i < 6; i++) st.x_t[i] = st.p[i] + st.step_dir[i] * st.a_t;
-    hm::ndt_pose_matrix_f32(st.x_t, st.final_T);
-  }
-  void begin_outer(ScanState& st) {
-    double b[6], delta_p[6];
-    for (int i = 0; i < 6; i++) b[i] = -st.g[i];
-    hm::svd6_solve(st.H, b, delta_p);  // :127-129
-    double nrm = 0;
-    for (int i = 0; i < 6; i++) nrm += delta_p[i] * delta_p[i];
-    nrm = std::sqrt(nrm);
-    if (nrm == 0 || nrm != nrm) {  // :134-139
-      st.converged = nrm == nrm;
-      st.phase = ScanState::FINISHED;
-      return;
-    }
-    for (int i = 0; i < 6; i++) st.step_dir[i] = delta_p[i] / nrm;
-    // computeStepLengthMT :773-
-    st.phi_0 = -st.score;
-    double d = 0;
-    for (int i = 0; i < 6; i++) d += st.g[i] * st.step_dir[i];
-    st.d_phi_0 = -d;
-    if (st.d_phi_0 >= 0) {
-      if (st.d_phi_0 == 0) { end_outer(st, 0.0); return; }
-      st.d_phi_0 *= -1;
-      for (int i = 0; i < 6; i++) st.step_dir[i] *= -1;
-    }
-    st.step_iterations = 0;
-    st.a_l = 0; st.a_u = 0;
-    st.f_l = hm::mt_psi(st.a_l, st.phi_0, st.phi_0, st.d_phi_0, mu);
-    st.g_l = hm::mt_dpsi(st.d_phi_0, st.d_phi_0, mu);
-    st.f_u = hm::mt_psi(st.a_u, st.phi_0, st.phi_0, st.d_phi_0, mu);
-    st.g_u = hm::mt_dpsi(st.d_phi_0, st.d_phi_0, mu);
-    st.interval_converged = (prm.ndt_step_size - prm.ndt_trans_eps / 2) < 0;
-    st.open_interval = true;
-    st.a_t = nrm;
-    set_trial(st);
-    st.phase = ScanState::LS_FIRST;
-    request_deriv(st, st.final_T, st.x_t, true);
-  }
-  void after_eval(ScanState& st) {
-    st.phi_t = -st.score;
-    double d = 0;
-    for (int i = 0; i < 6; i++) d += st.g[i] * st.step_dir[i];
-    st.d_phi_t = -d;
-    st.psi_t = hm::mt_psi(st.a_t, st.phi_t, st.phi_0, st.d_phi_0, mu);
-    st.d_psi_t = hm::mt_dpsi(st.d_phi_t, st.d_phi_0, mu);
-  }
-  void ls_continue(ScanState& st) {
-    if (!st.interval_converged && st.step_iterations < max_step_iterations && !(st.psi_t <= 0 && st.d_phi_t <= -nu * st.d_phi_0)) {
-      if (st.open_interval) st.a_t = hm::mt_trial_value(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, st.psi_t, st.d_psi_t);
-      else st.a_t = hm::mt_trial_value(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, st.phi_t, st.d_phi_t);
-      set_trial(st);
-      st.phase = ScanState::LS_LOOP;
-      request_deriv(st, st.final_T, st.x_t, false);
-      return;
-    }
-    if (st.step_iterations) {  // :928-929 computeHessian
-      st.phase = ScanState::LS_HESSIAN;
-      std::memcpy(st.eval_T, st.final_T, sizeof(float) * 16);
-      std::memcpy(st.eval_p, st.x_t, sizeof(double) * 6);
-      st.eval_kind = 1;
-      st.eval_hess = 1;
-      return;
-    }
-    end_outer(st, st.a_t);
-  }
-  void end_outer(ScanState& st, double a) {
-    for (int i = 0; i < 6; i++) st.p[i] += st.step_dir[i] * a;
-    if (st.nr_iterations > prm.ndt_max_iters || (st.nr_iterations && (std::fabs(a) < prm.ndt_trans_eps))) st.converged = true;  // :158-162
-    st.nr_iterations++;
-    if (st.converged) { st.phase = ScanState::FINISHED; return; }
-    begin_outer(st);
-  }
-  void on_result(ScanState& st, const NdtEvalResult& r) {
-    st.n_pairs += (long long)(r.v[28] + 0.5);
-    switch (st.phase) {
-      case ScanState::INIT_EVAL:
-        st.n_evals++;
-        take(st, r, true);
-        begin_outer(st);
-        break;
-      case ScanState::LS_FIRST:
-        st.n_evals++;
-        take(st, r, true);
-        after_eval(st);
-        ls_continue(st);
-        break;
-      case ScanState::LS_LOOP: {
-        st.n_evals++;
-        take(st, r, false);
-        after_eval(st);
-        if (st.open_interval && (st.psi_t <= 0 && st.d_psi_t >= 0)) {
-          st.open_interval = false;
-          st.f_l = st.f_l + st.phi_0 - mu * st.d_phi_0 * st.a_l;
-          st.g_l = st.g_l + mu * st.d_phi_0;
-          st.f_u = st.f_u + st.phi_0 - mu * st.d_phi_0 * st.a_u;
-          st.g_u = st.g_u + mu * st.d_phi_0;
-        }
-        if (st.open_interval)
-          st.interval_converged = hm::mt_update_interval(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, st.psi_t, st.d_psi_t);
-        else
-          st.interval_converged = hm::mt_update_interval(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, st.phi_t, st.d_phi_t);
-        st.step_iterations++;
-        ls_continue(st);
-        break;
-      }
-      case ScanState::LS_HESSIAN: {
-        st.n_hess++;
-        int k = 7;
-        for (int a = 0; a < 6; a++)
-          for (int b = a; b < 6; b++) { st.H[a * 6 + b] = r.v[k]; st.H[b * 6 + a] = r.v[k]; k++; }
-        end_outer(st, st.a_t);
-        break;
-      }
-      default: break;
-    }
-  }
-};
-}  // namespace
-
-static void fill_params(NdtEvalParams& ep, const float* T, const double* p, int kind, int hess, int scan) {
-  std::memcpy(ep.Tf, T, sizeof(float) * 16);
-  hm::ndt_angle_tables(p, ep.j_ang, ep.h_ang, ep.j_ang_d, ep.h_ang_d);
-  ep.compute_hessian = hess;
-  ep.kind = kind;
-  ep.scan = scan;
-  ep.pad = 0;
-}
-
-// One lane = one NdtDriver + one stream driving the state machines of a subset of the scans in lock-step.
-namespace {
-struct Lane {
-  NdtDriver* drv;
-  cudaStream_t stream;
-  std::vector<int> scans;    // scans of the batch owned by this lane
-  std::vector<int> active;   // scans with a request in flight (order of h_params)
-  bool in_flight = false;
-};
-
-// builds the lane's next round of requests; returns false when all of its scans are finished
-bool lane_launch(Lane& L, std::vector<ScanState>& st, const float4* src, size_t max_pts, const NdtTarget& tgt, const pcr_params& prm, bool profile) {
-  L.active.clear();
-  for (int i : L.scans)
-    if (st[size_t(i)].phase != ScanState::FINISHED) L.active.push_back(i);
-  L.in_flight = false;
-  if (L.active.empty()) return false;
-  std::stable_partition(L.active.begin(), L.active.end(), [&](int i) { return st[size_t(i)].eval_kind == 0; });
-  L.drv->h_params.ensure(L.active.size());
-  for (size_t k = 0; k < L.active.size(); k++) {
-    ScanState& ss = st[size_t(L.active[k])];
-    fill_params(L.drv->h_params.p[k], ss.eval_T, ss.eval_p, ss.eval_kind, ss.eval_hess, L.active[k]);
-  }
-  L.drv->launch(src, L.drv->offsets.p, max_pts, tgt, prm.ndt_search, int(L.active.size()), profile, L.stream);
-  L.in_flight = true;
-  return true;
-}
-}  // namespace
-
 int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, const NdtTarget& tgt, const pcr_params& prm, double* T,
                      int32_t* converged, int32_t* iters, double* trans_prob, bool profile, cudaStream_t s) {
-  launches = 0; hot_ms = 0.f; hot_launches = 0; total_evals = 0; total_hess = 0; total_pairs = 0; point_evals = 0;
+  launches = 0; hot_ms = 0.f; hot_launches = 0; total_evals = 0; total_hess = 0; total_pairs = 0; point_evals = 0; rounds = 0;
   if (n_scans == 0) return 0;
-  size_t max_pts = 0;
-  for (size_t i = 0; i < n_scans; i++) max_pts = std::max(max_pts, size_t(offs[i + 1] - offs[i]));
-  std::vector<ScanState> st(n_scans);
-  NdtLogic logic{prm};
-  for (size_t i = 0; i < n_scans; i++) logic.start(st[i], T + i * 16);
+  NdtCfg cfg{};
+  cfg.step_size = prm.ndt_step_size;
+  cfg.trans_eps = prm.ndt_trans_eps;
+  cfg.max_iters = prm.ndt_max_iters;
+  const int no_target = (tgt.overflow || tgt.nleaves == 0) ? 1 : 0;
+  static const int lookahead = [] { const char* v = std::getenv("PCR_NDT_LOOKAHEAD"); return v ? std::max(1, std::atoi(v)) : 3; }();
+  // every outer iteration costs at most 1 + kMaxStepIterations float evaluations (+ 1 double-path Hessian in the same round)
+  const int max_rounds = (prm.ndt_max_iters + 3) * (ndt_logic::kMaxStepIterations + 2) + 2;
+  if (profile && !ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
 
-  // Batches run as two lanes on two streams: while one lane's kernel runs, the host digests the other lane's results
-  // (Newton direction, More-Thuente bookkeeping, angle tables) and queues its next round, so the GPU does not idle
-  // between evaluation rounds. A single scan uses one lane.
-  const char* lanes_env = std::getenv("PCR_NDT_LANES");  // tuning / measurement knob: 1 = single lane (clean per-kernel timing)
-  const bool two = n_scans >= 4 && !(lanes_env && std::atoi(lanes_env) == 1);
-  if (two && !second) {
-    second.reset(new NdtDriver());
-    PCR_CUDA_CHECK(cudaStreamCreateWithFlags(&second_stream, cudaStreamNonBlocking));
-    PCR_CUDA_CHECK(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-  }
-  Lane lanes[2];
-  const int nl = two ? 2 : 1;
-  lanes[0].drv = this; lanes[0].stream = s;
-  if (two) {
-    lanes[1].drv = second.get(); lanes[1].stream = second_stream;
-    second->launches = 0; second->hot_ms = 0.f; second->hot_launches = 0; second->point_evals = 0;
-    PCR_CUDA_CHECK(cudaEventRecord(ready, s));                      // src was packed on the main stream
-    PCR_CUDA_CHECK(cudaStreamWaitEvent(second_stream, ready, 0));
-  }
-  for (size_t i = 0; i < n_scans; i++) lanes[two ? (i * 2 / n_scans) : 0].scans.push_back(int(i));
-  for (int l = 0; l < nl; l++) {
-    NdtDriver* d = lanes[l].drv;
-    uint32_t* ho = d->h_offsets.ensure(n_scans + 1);
-    for (size_t i = 0; i <= n_scans; i++) ho[i] = uint32_t(offs[i] - offs[0]);
-    d->offsets.ensure(n_scans + 1);
-    PCR_CUDA_CHECK(cudaMemcpyAsync(d->offsets.p, ho, (n_scans + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, lanes[l].stream));
-  }
-  for (int l = 0; l < nl; l++) lane_launch(lanes[l], st, src, max_pts, tgt, prm, profile);
-  for (;;) {
-    bool any = false;
-    for (int l = 0; l < nl; l++) {
-      Lane& L = lanes[l];
-      if (!L.in_flight) continue;
-      any = true;
-      L.drv->collect(int(L.active.size()), profile, L.stream);
-      for (size_t k = 0; k < L.active.size(); k++) logic.on_result(st[size_t(L.active[k])], L.drv->h_results.p[k]);
-      lane_launch(L, st, src, max_pts, tgt, prm, profile);
+  for (size_t c0 = 0; c0 < n_scans; c0 += kNdtMaxBatch) {  // chunks of scans (request list size); normally a single chunk
+    const size_t n = std::min<size_t>(kNdtMaxBatch, n_scans - c0);
+    size_t max_pts = 0;
+    for (size_t i = 0; i < n; i++) max_pts = std::max(max_pts, size_t(offs[c0 + i + 1] - offs[c0 + i]));
+    const int grid = wave_blocks(n, std::max<size_t>(max_pts, 1));
+    prepare(n, grid, s);
+    uint32_t* ho = h_offsets.ensure(n + 1);
+    double* hg = h_guesses.ensure(n * 16);
+    for (size_t i = 0; i <= n; i++) ho[i] = uint32_t(offs[c0 + i] - offs[0]);
+    memcpy(hg, T + c0 * 16, n * 16 * sizeof(double));
+    offsets.ensure(n + 1);
+    guesses.ensure(n * 16);
+    PCR_CUDA_CHECK(cudaMemcpyAsync(offsets.p, ho, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    PCR_CUDA_CHECK(cudaMemcpyAsync(guesses.p, hg, n * 16 * sizeof(double), cudaMemcpyHostToDevice, s));
+    NdtProgress* dprog = nullptr;
+    PCR_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dprog), progress, 0));
+    ndt_init_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(guesses.p, offsets.p, states.p, outs.p, stamps.p, stamps.p + n, int(n), no_target, cfg,
+                                                              dprog, counters.p);
+    launches++;
+    if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
+    int r = 0;
+    unsigned spins = 0;
+    bool stream_idle = false;
+    while (r < max_rounds) {
+      // throttle: at most `lookahead` rounds queued ahead of the round the GPU is working on
+      while (!progress->all_done && progress->round < r - lookahead) {
+        if ((++spins & 0xfff) == 0) {  // safety net: the stream drained (or failed) without the expected progress
+          const cudaError_t q = cudaStreamQuery(s);
+          if (q == cudaSuccess) { stream_idle = true; break; }
+          if (q != cudaErrorNotReady) PCR_CUDA_CHECK(q);
+        }
+      }
+      if (progress->all_done || stream_idle) break;
+      launch_round(src, tgt, prm.ndt_search, int(n), r, 1, cfg, grid, true, true, s);
+      r++;
     }
-    if (!any) break;
-  }
-  if (two) {
-    launches += second->launches; hot_ms += second->hot_ms; hot_launches += second->hot_launches; point_evals += second->point_evals;
-  }
-  for (size_t i = 0; i < n_scans; i++) {
-    for (int q = 0; q < 16; q++) T[i * 16 + q] = double(st[i].final_T[q]);  // NdtRegister.cpp:28
-    if (converged) converged[i] = st[i].converged ? 1 : 0;
-    if (iters) iters[i] = st[i].nr_iterations;
-    const size_t ns = offs[i + 1] - offs[i];
-    if (trans_prob) trans_prob[i] = st[i].score / double(ns);
-    total_evals += st[i].n_evals;
-    total_hess += st[i].n_hess;
-    total_pairs += st[i].n_pairs;
+    if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev1, s));
+    NdtScanOut* hout = h_outs.ensure(n);
+    NdtCounters* hc = h_counters.ensure(1);
+    PCR_CUDA_CHECK(cudaMemcpyAsync(hout, outs.p, n * sizeof(NdtScanOut), cudaMemcpyDeviceToHost, s));
+    PCR_CUDA_CHECK(cudaMemcpyAsync(hc, counters.p, sizeof(NdtCounters), cudaMemcpyDeviceToHost, s));
+    PCR_CUDA_CHECK(cudaStreamSynchronize(s));
+    PCR_CUDA_CHECK(cudaGetLastError());
+    if (hc->finished != int(n)) throw CudaError("NDT: the evaluation rounds ended before every scan finished");
+    if (profile) {
+      float ms = 0.f;
+      PCR_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+      hot_ms += ms;
+    }
+    hot_launches += hc->work_launches;
+    point_evals += hc->point_evals;
+    rounds += r;
+    for (size_t i = 0; i < n; i++) {
+      const NdtScanOut& o = hout[i];
+      for (int q = 0; q < 16; q++) T[(c0 + i) * 16 + q] = double(o.final_T[q]);  // NdtRegister.cpp:28
+      if (converged) converged[c0 + i] = o.converged ? 1 : 0;
+      if (iters) iters[c0 + i] = o.nr_iterations;
+      const size_t ns = offs[c0 + i + 1] - offs[c0 + i];
+      if (trans_prob) trans_prob[c0 + i] = o.score / double(ns);
+      total_evals += o.n_evals;
+      total_hess += o.n_hess;
+      total_pairs += o.n_pairs;
+    }
   }
   return 0;
 }

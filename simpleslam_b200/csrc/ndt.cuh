@@ -1,10 +1,11 @@
 // pclomp NDT on the GPU: voxel-covariance target build (N1), neighbourhood lookup (N2/N6), derivative kernels (N3/N4)
-// and the host-side Newton + More-Thuente driver (N5), batched over independent scans.
+// and the Newton + More-Thuente control flow (N5) as a device-side state machine (ndt_logic.cuh), batched over
+// independent scans: a registration is a stream of evaluation rounds with no host round trip in between.
 #pragma once
 #include "common.cuh"
 #include "voxel.cuh"
+#include "ndt_logic.cuh"
 #include "../../include/pcr_cuda.h"
-#include <memory>
 
 namespace pcr {
 
@@ -30,55 +31,64 @@ struct NdtTarget {
   CellGrid cgrid;
 };
 
-struct NdtEvalParams {  // per scan, per evaluation
-  float Tf[16];         // cloud transform (column-major float)
-  float j_ang[8][3];
-  float h_ang[15][3];
-  double j_ang_d[8][3];
-  double h_ang_d[15][3];
-  int compute_hessian;
-  int kind;             // 0 = computeDerivatives (float path), 1 = computeHessian (double path)
-  int scan;             // which scan of the batch
-  int pad;
-};
-
 struct NdtEvalResult { double v[30]; };  // score, g[6], H upper-triangular 21 (row-major order r<=c), pairs, pad
 
+struct NdtScanOut {  // per scan, written by the tail that finishes the scan (or by a single evaluation without state step)
+  float final_T[16];
+  int converged, nr_iterations, n_evals, n_hess;
+  long long n_pairs;
+  double score;
+  double v[30];      // sums of the last evaluation (introspection entry points)
+};
+
+struct NdtProgress {  // host-mapped pinned memory: the only thing the host looks at while a registration runs
+  volatile int round;     // round whose float kernel has started
+  volatile int all_done;  // set by the tail that finishes the last scan
+  int pad[14];
+};
+
+struct NdtCounters {  // device
+  int finished;
+  int work_launches;      // kernel launches that had at least one request
+  long long point_evals;  // source points pushed through the evaluation kernels
+};
+
 struct NdtDriver {
-  DevBuf<NdtEvalParams> d_params;
-  DevBuf<NdtEvalResult> d_results;
+  DevBuf<NdtScanState> states;
+  DevBuf<NdtScanOut> outs;
+  DevBuf<int32_t> stamps;  // [2][n]: round in which a scan wants a float evaluation / a double-path Hessian
   DevBuf<double> partials;
   DevBuf<unsigned> tickets;
   DevBuf<uint32_t> offsets;
-  PinBuf<NdtEvalParams> h_params;
-  PinBuf<NdtEvalResult> h_results;
+  DevBuf<double> guesses;
+  DevBuf<NdtCounters> counters;
+  PinBuf<NdtScanOut> h_outs;
+  PinBuf<NdtScanState> h_state;
   PinBuf<uint32_t> h_offsets;
-  size_t partial_cap_blocks = 0;
+  PinBuf<double> h_guesses;
+  PinBuf<NdtCounters> h_counters;
+  NdtProgress* progress = nullptr;  // mapped
   long long launches = 0;
   float hot_ms = 0.f;
   int hot_launches = 0;
+  int rounds = 0;
   int total_evals = 0, total_hess = 0;
   long long total_pairs = 0;
   long long point_evals = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  NdtEvalResult* mapped_results = nullptr;  // host-mapped pinned memory the last block writes into
-  size_t mapped_cap = 0;
   ~NdtDriver();
 
-  // second lane of a batched align (own buffers, own stream): see NdtDriver::align
-  std::unique_ptr<NdtDriver> second;
-  cudaStream_t second_stream = nullptr;
-  cudaEvent_t ready = nullptr;
-  bool pending_run = false;
-  // launch: queue one evaluation round (h_params[0..count)) on stream s; collect: wait for it -> h_results[0..count)
-  void launch(const float4* src, const uint32_t* d_offs, size_t max_pts, const NdtTarget& tgt, int search, int count, bool profile, cudaStream_t s);
-  void collect(int count, bool profile, cudaStream_t s);
-  // evaluate `count` requests (h_params[0..count)) -> h_results[0..count). Blocking.
-  void evaluate(const float4* src, const uint32_t* d_offs, size_t max_pts, const NdtTarget& tgt, int search, int count, bool profile,
-                cudaStream_t s);
+  // one evaluation with explicit parameters (introspection: pcr_ndt_derivatives / pcr_ndt_hessian). Blocking.
+  void evaluate_one(const float4* src, size_t ns, const NdtTarget& tgt, int search, const NdtEvalParams& ep, NdtEvalResult& out, cudaStream_t s);
   // full registration of n_scans scans (offs: host offsets, n_scans+1)
   int align(const float4* src, const size_t* offs, size_t n_scans, const NdtTarget& tgt, const pcr_params& prm, double* T,
             int32_t* converged, int32_t* iters, double* trans_prob, bool profile, cudaStream_t s);
+
+ private:
+  void ensure_progress();
+  void prepare(size_t n_scans, int grid_blocks, cudaStream_t s);
+  void launch_round(const float4* src, const NdtTarget& tgt, int search, int n, int round, int step, const NdtCfg& cfg, int grid_blocks,
+                    bool float_kernel, bool double_kernel, cudaStream_t s);
 };
 
 int ndt_build_target(const float4* pts, size_t n, const pcr_params& prm, NdtTarget& tgt, KeySort& ks, BBoxWork& bw, cudaStream_t s);

@@ -22,7 +22,8 @@ def _p(a):
 
 @pytest.fixture(scope="module")
 def shim():
-    deps = [SRC, os.path.join(ROOT, "simpleslam_b200", "csrc", "dev_linalg.cuh"), os.path.join(ROOT, "simpleslam_b200", "csrc", "host_math.hpp")]
+    deps = [SRC, os.path.join(ROOT, "simpleslam_b200", "csrc", "dev_linalg.cuh"), os.path.join(ROOT, "simpleslam_b200", "csrc", "host_math.hpp"),
+            os.path.join(ROOT, "simpleslam_b200", "csrc", "ndt_logic.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         nvcc = "/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc"
         cmd = [nvcc, "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, SRC]
