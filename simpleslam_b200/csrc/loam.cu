@@ -13,6 +13,7 @@
 // Restates PCR/src/LoamRegister.cpp:99-223 (reference CPU path: nanoflann kd-tree + OpenMP + omp critical).
 #include "loam.cuh"
 #include "dev_linalg.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include <cfloat>
 #include <algorithm>
 #include <cstdlib>
@@ -54,7 +55,8 @@ __global__ void __launch_bounds__(kLoamBlock, MODE == kModeSearch ? 4 : 2)
 loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, GridView grid, LoamParams prm,
                  LoamState* __restrict__ states, double* __restrict__ partials, int max_blocks,
                  pcr_loam_iter_log* __restrict__ logs, int apply_update, int tile, double slack, int max_ring,
-                 int32_t* __restrict__ dbg_knn, int32_t* __restrict__ dbg_status, int32_t* __restrict__ knn_buf, size_t knn_stride) {
+                 int32_t* __restrict__ dbg_knn, int32_t* __restrict__ dbg_status, int32_t* __restrict__ knn_buf, size_t knn_stride,
+                 const uint32_t* __restrict__ qperm) {
   // LPQ = lanes co-operating on one query, G = 32 / LPQ queries searched concurrently by a warp.
   // `tile` (multiple of G, <= 32) = queries a warp owns per pass: 32 for throughput on large batches, smaller when there
   // are too few queries to fill the machine (a single scan), trading phase-2 lane utilisation for shorter latency chains.
@@ -274,14 +276,36 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
       }
       double d5 = DBL_MAX;
       if (five) {
-        const double dx = q0 - double(nx[4]), dyy = q1 - double(ny[4]), dzz = q2 - double(nz[4]);
-        d5 = dx * dx + dyy * dyy + dzz * dzz;
+        if (MODE == kModeFit) {
+          // the search kernel selects the five winners on the FP32 metric (the SET is exact, see loam_search_kernel): order
+          // them here by the exact FP64 (d2, original index) key, the order nanoflann returns them in
+          unsigned long long ek[5];
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            const double dx = q0 - double(nx[k]), dyy = q1 - double(ny[k]), dzz = q2 - double(nz[k]);
+            ek[k] = (unsigned long long)__double_as_longlong(dx * dx + dyy * dyy + dzz * dzz);
+          }
+          auto cswap = [&](int a, int b) {  // compare-exchange, a < b
+            const bool sw = ek[b] < ek[a] || (ek[b] == ek[a] && nidx[b] < nidx[a]);
+            const unsigned long long te = sw ? ek[a] : ek[b]; ek[a] = sw ? ek[b] : ek[a]; ek[b] = te;
+            const float tx = sw ? nx[a] : nx[b]; nx[a] = sw ? nx[b] : nx[a]; nx[b] = tx;
+            const float ty = sw ? ny[a] : ny[b]; ny[a] = sw ? ny[b] : ny[a]; ny[b] = ty;
+            const float tz = sw ? nz[a] : nz[b]; nz[a] = sw ? nz[b] : nz[a]; nz[b] = tz;
+            const int ti = sw ? nidx[a] : nidx[b]; nidx[a] = sw ? nidx[b] : nidx[a]; nidx[b] = ti;
+          };
+          cswap(0, 1); cswap(3, 4); cswap(2, 4); cswap(2, 3); cswap(0, 3); cswap(0, 2); cswap(1, 4); cswap(1, 3); cswap(1, 2);  // 9-exchange network
+          d5 = __longlong_as_double((long long)ek[4]);
+        } else {
+          const double dx = q0 - double(nx[4]), dyy = q1 - double(ny[4]), dzz = q2 - double(nz[4]);
+          d5 = dx * dx + dyy * dyy + dzz * dzz;
+        }
       }
       // LoamRegister.cpp:59 gate: squared distance of the 5th neighbour < 1.0
       const bool gate = five && (d5 < prm.max_knn_d2);
+      const uint32_t iq = qperm ? __ldg(qperm + i) : i;  // original position of this query (queries may be spatially re-ordered)
       if (DEBUG && dbg_knn) {
 #pragma unroll
-        for (int k = 0; k < 5; k++) dbg_knn[size_t(i) * 5 + k] = gate ? nidx[k] : -1;
+        for (int k = 0; k < 5; k++) dbg_knn[size_t(iq) * 5 + k] = gate ? nidx[k] : -1;
       }
       if (gate) {
         status = 1;
@@ -325,7 +349,7 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
       }
       acc[28 * kLoamBlock] += double(my_ncand);
       acc[29 * kLoamBlock] += double(my_nrows);
-      if (DEBUG && dbg_status) dbg_status[i] = status;
+      if (DEBUG && dbg_status) dbg_status[iq] = status;
     }
   }
 
@@ -440,6 +464,216 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
   (void)update;
 }
 
+// ================================================================================================================
+// Batched search kernel (one lane per query, queries in Morton order of their scan-frame position so that the 32 lanes of
+// a warp walk neighbouring rows of the map: similar trip counts, shared cache lines).
+// Selection runs on the FP32 metric f (|f - e| <= 3e-7 e against the exact FP64 metric e of the reference, both taken on
+// the same float coordinates): a lane keeps its five smallest (f, position) pairs and the smallest f that was looked at but
+// is NOT among them (f_out). Candidates and rows are pruned against thr = 1.00001 * min(gate, current 5th f), so whatever
+// is dropped unseen is farther than the final 5th by a margin of 1e-5 >> 2 * 3e-7. If f_out > 5th f * (1 + 9.5e-7) the five
+// kept candidates are exactly the reference's five nearest (as a set; the fit kernel orders them by the exact (e, index)
+// key). Otherwise — a near tie between the 5th and the 6th, e.g. on quantised clouds — the query is searched again by
+// exact_search_one with the FP64 (e, index) order throughout.
+// ================================================================================================================
+struct RowGeom {  // per-query constants of the row walk (cells; same float key math as the build)
+  int cx, cy, cz;
+  float fx, fy, fz, h2, slk, ax2, ring2_min2;
+};
+__device__ __forceinline__ RowGeom row_geom(const GridSpec& g, float qf0, float qf1, float qf2, double leaf, double slack) {
+  RowGeom r;
+  const float sx = __fmul_rn(qf0, g.inv_leaf[0]), sy = __fmul_rn(qf1, g.inv_leaf[1]), sz = __fmul_rn(qf2, g.inv_leaf[2]);
+  const float flx = floorf(sx), fly = floorf(sy), flz = floorf(sz);
+  r.cx = int(__fsub_rn(flx, float(g.min_b[0]))); r.cy = int(__fsub_rn(fly, float(g.min_b[1]))); r.cz = int(__fsub_rn(flz, float(g.min_b[2])));
+  r.fx = sx - flx; r.fy = sy - fly; r.fz = sz - flz;
+  r.h2 = float(leaf * leaf) * 0.99999f;
+  r.slk = float(slack);
+  // distance (cells) from the query to the cells at x-offset +-2: below it one x-cell either side is enough
+  r.ax2 = fmaxf(1.f + fminf(r.fx, 1.f - r.fx) - r.slk, 0.f);
+  // every row of ring 2 is at least this far (squared): once the bound is below it the second ring is skipped as a whole
+  const float ring2 = fmaxf(1.f + fminf(fminf(r.fy, 1.f - r.fy), fminf(r.fz, 1.f - r.fz)) - r.slk, 0.f);
+  r.ring2_min2 = ring2 * ring2 * r.h2;
+  return r;
+}
+// x-run of row k of the neighbourhood that can still hold a point closer than thr: [lo, hi) in the cell-sorted map
+__device__ __forceinline__ bool row_run(const GridView& grid, const RowGeom& q, int k, float thr, int max_ring, int& lo, int& hi) {
+  const GridSpec& g = grid.g;
+  const int dy = c_row_dy[k], dz = c_row_dz[k];
+  // squared distance from the query to the row's (y, z) slab, shrunk by the cell-assignment slack
+  const float ay = fmaxf((dy == 0 ? 0.f : (dy > 0 ? float(dy) - q.fy : q.fy + float(-dy - 1))) - q.slk, 0.f);
+  const float az = fmaxf((dz == 0 ? 0.f : (dz > 0 ? float(dz) - q.fz : q.fz + float(-dz - 1))) - q.slk, 0.f);
+  const float row2 = (ay * ay + az * az) * q.h2;
+  if (row2 > thr) return false;  // every point of this row is farther than the current bound
+  const int y = q.cy + dy, z = q.cz + dz;
+  if (y < 0 || y >= g.div_b[1] || z < 0 || z >= g.div_b[2]) return false;
+  const int rx = (max_ring > 1 && thr < row2 + q.ax2 * q.ax2 * q.h2) ? 1 : max_ring;
+  const int x0 = max(q.cx - rx, 0), x1 = min(q.cx + rx, g.div_b[0] - 1);
+  if (x0 > x1) return false;
+  // a row is ONE contiguous run of the cell-sorted map: two loads of the dense start table
+  const long long key0 = (long long)x0 + (long long)y * g.mul[1] + (long long)z * g.mul[2];
+  lo = __ldg(grid.start + key0);
+  hi = __ldg(grid.start + key0 + (x1 - x0) + 1);
+  return true;
+}
+
+// exact path for one query (rare): FP64 (d2, index) order throughout, as the fused kernel does
+__device__ __noinline__ void exact_search_one(const GridView& grid, float qf0, float qf1, float qf2, double leaf, double slack, int max_ring,
+                                              float gate_thr, int (&wj)[5], int& ncand, int& nrows) {
+  const RowGeom q = row_geom(grid.g, qf0, qf1, qf2, leaf, slack);
+  const double q0 = double(qf0), q1 = double(qf1), q2 = double(qf2);
+  Cand best[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) { best[k].key = ~0ull; best[k].idx = 0x7fffffff; best[k].j = -1; }
+  float thr = gate_thr;
+  const int NR = (2 * max_ring + 1) * (2 * max_ring + 1);
+#pragma unroll 1
+  for (int k = 0; k < NR; k++) {
+    if (k >= 9 && thr < q.ring2_min2) break;
+    int lo, hi;
+    if (!row_run(grid, q, k, thr, max_ring, lo, hi)) continue;
+    ncand += hi - lo;
+    nrows++;
+#pragma unroll 1
+    for (int j = lo; j < hi; j++) {
+      const float4 m = __ldg(grid.pts + j);
+      const float ax = qf0 - m.x, ay = qf1 - m.y, az = qf2 - m.z;
+      if (!(fmaf(az, az, fmaf(ay, ay, ax * ax)) <= thr)) continue;
+      const double dx = q0 - double(m.x), dyy = q1 - double(m.y), dzz = q2 - double(m.z);
+      Cand cnd;
+      cnd.key = (unsigned long long)__double_as_longlong(dx * dx + dyy * dyy + dzz * dzz); cnd.idx = __float_as_int(m.w); cnd.j = j;
+      if (cand_less(cnd, best[4])) {
+        const bool l0 = cand_less(best[0], cnd), l1 = cand_less(best[1], cnd), l2 = cand_less(best[2], cnd), l3 = cand_less(best[3], cnd);
+        best[4] = cand_sel(l3, cnd, best[3]);
+        best[3] = cand_sel(l3, best[3], cand_sel(l2, cnd, best[2]));
+        best[2] = cand_sel(l2, best[2], cand_sel(l1, cnd, best[1]));
+        best[1] = cand_sel(l1, best[1], cand_sel(l0, cnd, best[0]));
+        best[0] = cand_sel(l0, best[0], cnd);
+        if (best[4].j >= 0) thr = fminf(thr, __double2float_ru(__longlong_as_double((long long)best[4].key)) * 1.00001f);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; k++) wj[k] = best[k].j;
+}
+
+__global__ void __launch_bounds__(kLoamBlock, 4)
+loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, GridView grid, LoamParams prm,
+                   const LoamState* __restrict__ states, double slack, int max_ring, int32_t* __restrict__ knn_buf, size_t knn_stride) {
+  const int scan = blockIdx.y;
+  const uint32_t begin = offs[scan], end = offs[scan + 1];
+  const LoamState* st = states + scan;
+  if (st->done) return;
+  __shared__ double sT[16];
+  if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
+  __syncthreads();
+  const GridSpec& g = grid.g;
+  const double leaf = double(g.leaf[0]);
+  const float gate_thr = float(prm.max_knn_d2) * 1.00001f;
+  const int NR = (2 * max_ring + 1) * (2 * max_ring + 1);
+  for (uint32_t i = begin + blockIdx.x * kLoamBlock + threadIdx.x; i < end; i += gridDim.x * kLoamBlock) {
+    const float4 po = __ldg(src + i);
+    // LoamRegister.cpp:128-130: ori = res * ori (double, ((R0 x + R1 y) + R2 z) + t*1), pointInMap = ori.cast<float>()
+    const double ox = double(po.x), oy = double(po.y), oz = double(po.z);
+    float pmf[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sT[r], ox), __dmul_rn(sT[4 + r], oy)), __dmul_rn(sT[8 + r], oz)), sT[12 + r]);
+      pmf[r] = __double2float_rn(v);
+    }
+    bool near = true;  // range-check in float so the int conversion cannot overflow
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const float fc = __fsub_rn(floorf(__fmul_rn(pmf[a], g.inv_leaf[a])), float(g.min_b[a]));
+      if (!(fc >= float(-max_ring) && fc <= float(g.div_b[a] - 1 + max_ring))) near = false;  // the rings would not touch the grid
+    }
+    int wj[5] = {-1, -1, -1, -1, -1};
+    int ncand = 0, nrows = 0;
+    if (near) {
+      const float qf0 = pmf[0], qf1 = pmf[1], qf2 = pmf[2];
+      const RowGeom q = row_geom(g, qf0, qf1, qf2, leaf, slack);
+      float bf[5] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};  // five smallest f, ascending
+      int bj[5] = {-1, -1, -1, -1, -1};
+      float f_out = INFINITY;  // smallest f that was examined but is not among the five
+      float thr = gate_thr;
+      auto consider = [&](const float4& m, int j) {
+        const float ax = qf0 - m.x, ay = qf1 - m.y, az = qf2 - m.z;
+        const float f = fmaf(az, az, fmaf(ay, ay, ax * ax));
+        if (f <= thr) {
+          if (f < bf[4]) {  // branch-free sorted insertion; the old 5th drops out
+            f_out = fminf(f_out, bf[4]);
+            const bool p3 = f < bf[3], p2 = f < bf[2], p1 = f < bf[1], p0 = f < bf[0];
+            bf[4] = p3 ? bf[3] : f;                   bj[4] = p3 ? bj[3] : j;
+            bf[3] = p3 ? (p2 ? bf[2] : f) : bf[3];    bj[3] = p3 ? (p2 ? bj[2] : j) : bj[3];
+            bf[2] = p2 ? (p1 ? bf[1] : f) : bf[2];    bj[2] = p2 ? (p1 ? bj[1] : j) : bj[2];
+            bf[1] = p1 ? (p0 ? bf[0] : f) : bf[1];    bj[1] = p1 ? (p0 ? bj[0] : j) : bj[1];
+            bf[0] = p0 ? f : bf[0];                   bj[0] = p0 ? j : bj[0];
+            thr = fminf(thr, bf[4] * 1.00001f);       // stays at the gate bound until five candidates are in (bf[4] = inf)
+          } else {
+            f_out = fminf(f_out, f);
+          }
+        }
+      };
+#pragma unroll 1
+      for (int k = 0; k < NR; k++) {
+        if (k >= 9 && thr < q.ring2_min2) break;
+        int lo, hi;
+        if (!row_run(grid, q, k, thr, max_ring, lo, hi)) continue;
+        ncand += hi - lo;
+        nrows++;
+#pragma unroll 1
+        for (int j = lo; j < hi; j += 4) {  // four independent float4 loads in flight
+          const int rem = hi - j;
+          const float4 far = make_float4(INFINITY, 0.f, 0.f, 0.f);  // f = inf: never considered
+          const float4 m0 = __ldg(grid.pts + j);
+          const float4 m1 = rem > 1 ? __ldg(grid.pts + j + 1) : far;
+          const float4 m2 = rem > 2 ? __ldg(grid.pts + j + 2) : far;
+          const float4 m3 = rem > 3 ? __ldg(grid.pts + j + 3) : far;
+          consider(m0, j); consider(m1, j + 1); consider(m2, j + 2); consider(m3, j + 3);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 5; k++) wj[k] = bj[k];
+      // a 6th candidate within 1e-6 (relative) of the 5th: the FP32 metric cannot tell which of them the reference keeps
+      if (bj[4] >= 0 && !(f_out > bf[4] * 1.000001f)) {
+        ncand = 0; nrows = 0;
+        exact_search_one(grid, qf0, qf1, qf2, leaf, slack, max_ring, gate_thr, wj, ncand, nrows);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) knn_buf[size_t(k) * knn_stride + i] = wj[k];
+    knn_buf[5 * knn_stride + i] = ncand;
+    knn_buf[6 * knn_stride + i] = nrows;
+  }
+}
+
+// ---- query re-ordering: Morton code of the scan-frame position (0.25 m cells, +-128 m), scan index on top -----------
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {  // 10 bits -> every third bit
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__global__ void __launch_bounds__(256) loam_query_key_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs,
+                                                             unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int scan = blockIdx.y;
+  const uint32_t begin = offs[scan], end = offs[scan + 1];
+  for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(src + i);
+    const int qx = min(max(int(floorf(fminf(fmaxf(p.x, -1000.f), 1000.f) * 4.f)) + 512, 0), 1023);
+    const int qy = min(max(int(floorf(fminf(fmaxf(p.y, -1000.f), 1000.f) * 4.f)) + 512, 0), 1023);
+    const int qz = min(max(int(floorf(fminf(fmaxf(p.z, -1000.f), 1000.f) * 4.f)) + 512, 0), 1023);
+    const uint32_t mc = spread10(uint32_t(qx)) | (spread10(uint32_t(qy)) << 1) | (spread10(uint32_t(qz)) << 2);
+    keys[i] = ((unsigned long long)scan << 30) | mc;
+    vals[i] = i;
+  }
+}
+__global__ void __launch_bounds__(256) loam_query_gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ vals, size_t n,
+                                                                float4* __restrict__ out) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = __ldg(src + vals[i]);
+}
+
 // T2SE3 on every scan's pose (LoamRegister.cpp:220), also for non-converged / aborted scans.
 __global__ void loam_finalize_kernel(LoamState* states, int n_scans) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -492,7 +726,7 @@ static void launch_iter(int lpq, dim3 grid, cudaStream_t s, const float4* src, c
                         int max_ring, int32_t* dbg_knn, int32_t* dbg_status) {
 #define PCR_LOAM_LAUNCH(L)                                                                                                                      \
   loam_iter_kernel<L, DEBUG, kModeFused><<<grid, kLoamBlock, kLoamDynSmem, s>>>(src, offs, view, prm, states, partials, max_blocks, logs, apply, tile, \
-                                                                                slack, max_ring, dbg_knn, dbg_status, nullptr, 0)
+                                                                                slack, max_ring, dbg_knn, dbg_status, nullptr, 0, nullptr)
   switch (lpq) {
     case 1: PCR_LOAM_LAUNCH(1); break;
     case 2: PCR_LOAM_LAUNCH(2); break;
@@ -525,6 +759,23 @@ LoamDriver::~LoamDriver() {
 }
 
 static GridView make_view(const CellGrid& grid) { return view_of(grid); }
+
+const float4* LoamDriver::sort_queries(const float4* src, const uint32_t* d_offs, size_t n_scans, size_t total_q, size_t max_pts, const uint32_t** perm,
+                                       cudaStream_t s) {
+  q_keys0.ensure(total_q); q_keys1.ensure(total_q); q_vals0.ensure(total_q); q_vals1.ensure(total_q); q_sorted.ensure(total_q);
+  const unsigned bx = unsigned(std::min<size_t>((max_pts + 255) / 256, 64));
+  loam_query_key_kernel<<<dim3(bx, unsigned(n_scans)), 256, 0, s>>>(src, d_offs, q_keys0.p, q_vals0.p);
+  int bits = 30;
+  while ((size_t(1) << (bits - 30)) < n_scans) bits++;
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, q_keys0.p, q_keys1.p, q_vals0.p, q_vals1.p, int(total_q), 0, bits, s);
+  q_tmp.ensure(bytes);
+  PCR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(q_tmp.p, bytes, q_keys0.p, q_keys1.p, q_vals0.p, q_vals1.p, int(total_q), 0, bits, s));
+  loam_query_gather_kernel<<<unsigned((total_q + 255) / 256), 256, 0, s>>>(src, q_vals1.p, total_q, q_sorted.p);
+  launches += 3;
+  *perm = q_vals1.p;
+  return q_sorted.p;
+}
 
 int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, const CellGrid& grid, const LoamParams& prm,
                       double* T, int32_t* converged, int32_t* iters_out, int64_t* n_last_out, bool profile, cudaStream_t s) {
@@ -565,15 +816,19 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
   const bool split = lpq == 1 && tile == 32 && env_int("PCR_LOAM_SPLIT", 1) != 0;
   last_lpq = lpq; last_tile = tile; last_split = split;
   if (grid.built && grid.has_start && max_pts > 0) {
-    if (split) knn_buf.ensure(7 * total_q);
+    const float4* q = src;
+    const uint32_t* perm = nullptr;
+    if (split) {
+      knn_buf.ensure(7 * total_q);
+      q = sort_queries(src, offsets.p, n_scans, total_q, max_pts, &perm, s);
+    }
     const size_t search_pb = size_t(kLoamWarps) * 32;
     const dim3 sgrid(unsigned((max_pts + search_pb - 1) / search_pb), unsigned(n_scans));
     for (int it = 0; it < prm.max_iters; it++) {
       if (split) {
-        loam_iter_kernel<1, false, kModeSearch><<<sgrid, kLoamBlock, 0, s>>>(src, offsets.p, view, prm, states.p, partials.p, int(sgrid.x), logs.p, 1, 32,
-                                                                            slack, grid.max_ring, nullptr, nullptr, knn_buf.p, total_q);
-        loam_iter_kernel<1, false, kModeFit><<<gridDim, kLoamBlock, kLoamDynSmem, s>>>(src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 1,
-                                                                                      32, slack, grid.max_ring, nullptr, nullptr, knn_buf.p, total_q);
+        loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, knn_buf.p, total_q);
+        loam_iter_kernel<1, false, kModeFit><<<gridDim, kLoamBlock, kLoamDynSmem, s>>>(q, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 1,
+                                                                                      32, slack, grid.max_ring, nullptr, nullptr, knn_buf.p, total_q, perm);
         launches += 2;
       } else {
         launch_iter<false>(lpq, gridDim, s, src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 1, tile, slack, grid.max_ring, nullptr, nullptr);
@@ -634,12 +889,13 @@ int LoamDriver::linearize(const float4* src, size_t ns, const CellGrid& grid, co
     GridView view = make_view(grid);
     if (split) {
       knn_buf.ensure(7 * ns);
+      const uint32_t* perm = nullptr;
+      const float4* q = sort_queries(src, offsets.p, 1, ns, ns, &perm, s);
       const size_t search_pb = size_t(kLoamWarps) * 32;
       const dim3 sgrid(unsigned((ns + search_pb - 1) / search_pb), 1);
-      loam_iter_kernel<1, false, kModeSearch><<<sgrid, kLoamBlock, 0, s>>>(src, offsets.p, view, prm, states.p, partials.p, int(sgrid.x), logs.p, 0, 32, slack,
-                                                                          grid.max_ring, nullptr, nullptr, knn_buf.p, ns);
-      loam_iter_kernel<1, true, kModeFit><<<dim3(max_blocks, 1), kLoamBlock, kLoamDynSmem, s>>>(src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p,
-                                                                                               0, 32, slack, grid.max_ring, dbg_knn.p, dbg_status.p, knn_buf.p, ns);
+      loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, knn_buf.p, ns);
+      loam_iter_kernel<1, true, kModeFit><<<dim3(max_blocks, 1), kLoamBlock, kLoamDynSmem, s>>>(q, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p,
+                                                                                               0, 32, slack, grid.max_ring, dbg_knn.p, dbg_status.p, knn_buf.p, ns, perm);
       last_split = true;
     } else {
       launch_iter<true>(lpq, dim3(max_blocks, 1), s, src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 0, tile, slack,

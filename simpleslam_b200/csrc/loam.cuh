@@ -33,6 +33,11 @@ struct LoamDriver {
   DevBuf<uint32_t> offsets;
   DevBuf<int32_t> dbg_knn, dbg_status;
   DevBuf<int32_t> knn_buf;  // split mode: 5 winners + 2 counters per query (seven planes)
+  // split mode: queries re-ordered along a Morton curve of their scan-frame position (once per call)
+  DevBuf<unsigned long long> q_keys0, q_keys1;
+  DevBuf<uint32_t> q_vals0, q_vals1;
+  DevBuf<float4> q_sorted;
+  DevBuf<unsigned char> q_tmp;
   PinBuf<LoamState> h_states;
   PinBuf<uint32_t> h_offsets;
   PinBuf<pcr_loam_iter_log> h_logs;
@@ -53,6 +58,9 @@ struct LoamDriver {
   int align(const float4* src, const size_t* offs, size_t n_scans, const CellGrid& grid, const LoamParams& prm, double* T,
             int32_t* converged, int32_t* iters_out, int64_t* n_last_out, bool profile, cudaStream_t s);
   // one linearisation at pose T for a single scan; outputs are host pointers (nullable)
+  // Morton re-ordering of the queries of every scan: returns the sorted copy, *perm = sorted position -> original position
+  const float4* sort_queries(const float4* src, const uint32_t* d_offs, size_t n_scans, size_t total_q, size_t max_pts, const uint32_t** perm,
+                             cudaStream_t s);
   int linearize(const float4* src, size_t ns, const CellGrid& grid, const LoamParams& prm, const double* T, int32_t* knn_idx,
                 int32_t* status, double* JtJ, double* JtE, int64_t* n_acc, cudaStream_t s);
 };
