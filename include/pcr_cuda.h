@@ -156,6 +156,26 @@ int pcr_target_blob_size(pcr_ctx* c, size_t* bytes);
 int pcr_target_export(pcr_ctx* c, void* dev_blob, size_t cap);
 int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes);
 
+/* Device allocations released by contexts are parked in a process-wide, mutex-protected cache (cudaMalloc / cudaFree cost
+ * milliseconds inside host-driven loops). A long-running caller can hand the parked buffers back to the driver at a quiet
+ * moment: *freed_bytes (nullable) = bytes returned. Buffers owned by live contexts are not touched. */
+int pcr_trim_device_cache(size_t* freed_bytes);
+
+/* Several GPUs in ONE process (test/loc.cpp with a static map, SURVEY.md 8e / 8b "pcr_batch_align(ctxs/devices...)"): one context per
+ * entry of devices[] (an ordinal may repeat). pcr_multi_set_target builds the index on devices[0], serialises it
+ * (pcr_target_export) and copies the blob to every other device over NVLink (cudaMemcpyPeerAsync), where it is imported
+ * without a rebuild. pcr_multi_batch_align shards the scans in contiguous blocks (scan i of n -> device i * n_devices / n),
+ * runs the shards concurrently (one host thread per device, no collective while a registration runs) and returns all
+ * poses / flags in the caller's arrays. Same argument meaning as pcr_set_target / pcr_batch_align. */
+typedef struct pcr_multi pcr_multi;
+int pcr_multi_create(const pcr_params* p, const int32_t* devices, size_t n_devices, pcr_multi** out);
+void pcr_multi_destroy(pcr_multi* m);
+const char* pcr_multi_last_error(const pcr_multi* m);
+int pcr_multi_set_target(pcr_multi* m, const void* pts, size_t n, size_t stride);
+int pcr_multi_batch_align(pcr_multi* m, const void* src, const size_t* offsets, size_t n_scans, size_t stride, double* T, int32_t* converged);
+/* bytes of the index blob the last pcr_multi_set_target copied to each peer, and the milliseconds the copies took */
+int pcr_multi_get_broadcast(const pcr_multi* m, size_t* blob_bytes, double* copy_ms);
+
 /* On-disk index cache: the built target index (the same blob pcr_target_export produces) written to /
  * read from a file, so that the localisation mode (test/loc.cpp -> MapManager(pcd_file), frontend/src/MapManager.cpp:52-84)
  * does not re-downsample and re-index its static map at every start. */

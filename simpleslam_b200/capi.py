@@ -25,6 +25,7 @@ SYMBOLS = [
     "pcr_gicp_covariances", "pcr_vgicp_num_voxels", "pcr_vgicp_get_voxels", "pcr_vgicp_evaluate",
     "pcr_submap_build", "pcr_submap_cache_clear", "pcr_target_save", "pcr_target_load", "pcr_read_pcd", "pcr_static_map_load",
     "pcr_scancontext_make", "pcr_scancontext_distance", "pcr_loam_last_shape",
+    "pcr_multi_create", "pcr_multi_destroy", "pcr_multi_last_error", "pcr_multi_set_target", "pcr_multi_batch_align", "pcr_multi_get_broadcast", "pcr_trim_device_cache",
 ]
 
 
@@ -138,6 +139,65 @@ def default_params(method, device=0):
     lib().pcr_default_params(int(method), ctypes.byref(p))
     p.device = device
     return p
+
+
+def trim_device_cache():
+    """hand the process-wide cache of released device buffers back to the driver; returns the bytes freed"""
+    b = ctypes.c_size_t(0)
+    lib().pcr_trim_device_cache(ctypes.byref(b))
+    return b.value
+
+
+class MultiContext:
+    """pcr_multi: one context per device in one process (loc.cpp mode with several GPUs, no Python-side collective)"""
+
+    def __init__(self, method, devices, **overrides):
+        p = default_params(method, devices[0])
+        for k, v in overrides.items():
+            setattr(p, k, v)
+        devs = (ctypes.c_int32 * len(devices))(*devices)
+        self._h = ctypes.c_void_p()
+        L = lib()
+        L.pcr_multi_last_error.restype = ctypes.c_char_p
+        L.pcr_multi_last_error.argtypes = [ctypes.c_void_p]
+        L.pcr_multi_destroy.argtypes = [ctypes.c_void_p]
+        rc = L.pcr_multi_create(ctypes.byref(p), devs, ctypes.c_size_t(len(devices)), ctypes.byref(self._h))
+        if rc != 0:
+            self._h = None
+            raise PcrError(rc, L.pcr_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pcr_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PcrError(rc, lib().pcr_multi_last_error(self._h).decode())
+
+    def set_target(self, dst):
+        a, n, st = _cloud(dst)
+        self._check(lib().pcr_multi_set_target(self._h, _vp(a), ctypes.c_size_t(n), ctypes.c_size_t(st)))
+
+    def batch_align(self, src_concat, offsets, Ts):
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        ns = len(offs) - 1
+        Tb = np.concatenate([_T_in(T) for T in Ts]) if ns else np.zeros(0)
+        conv = np.zeros(max(ns, 1), np.int32)
+        a, n, st = _cloud(src_concat)
+        self._check(lib().pcr_multi_batch_align(self._h, _vp(a), _vp(offs), ctypes.c_size_t(ns), ctypes.c_size_t(st), _vp(Tb), _vp(conv)))
+        return [_T_out(Tb[i * 16:(i + 1) * 16]) for i in range(ns)], conv[:ns].astype(bool)
+
+    def broadcast_info(self):
+        b, ms = ctypes.c_size_t(0), ctypes.c_double(0)
+        self._check(lib().pcr_multi_get_broadcast(self._h, ctypes.byref(b), ctypes.byref(ms)))
+        return dict(blob_bytes=b.value, copy_ms=ms.value)
 
 
 class Context:

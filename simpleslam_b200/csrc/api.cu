@@ -18,6 +18,8 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
+#include <vector>
 
 using namespace pcr;
 
@@ -771,6 +773,141 @@ extern "C" int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes)
   c->has_target = true;
   return PCR_OK;
   PCR_API_END(c)
+}
+
+extern "C" int pcr_trim_device_cache(size_t* freed_bytes) {
+  const size_t before = DevPool::cached_bytes();
+  cudaDeviceSynchronize();
+  DevPool::trim();
+  if (freed_bytes) *freed_bytes = before;
+  return PCR_OK;
+}
+
+// ---- several GPUs in one process (loc.cpp mode) --------------------------------------------------------------------
+struct pcr_multi {
+  std::vector<pcr_ctx*> ctx;
+  std::vector<int> dev;
+  std::string err;
+  size_t blob_bytes = 0;
+  double copy_ms = 0.0;
+};
+
+extern "C" int pcr_multi_create(const pcr_params* p, const int32_t* devices, size_t n_devices, pcr_multi** out) {
+  if (!p || !devices || !out || n_devices == 0) return PCR_ERR_INVALID;
+  *out = nullptr;
+  pcr_multi* m = new pcr_multi();
+  for (size_t k = 0; k < n_devices; k++) {
+    pcr_params q = *p;
+    q.device = devices[k];
+    pcr_ctx* c = nullptr;
+    const int rc = pcr_create(&q, &c);
+    if (rc) {
+      for (pcr_ctx* x : m->ctx) pcr_destroy(x);
+      delete m;
+      return rc;  // pcr_last_error(NULL) has the text
+    }
+    m->ctx.push_back(c);
+    m->dev.push_back(devices[k]);
+  }
+  *out = m;
+  return PCR_OK;
+}
+
+extern "C" void pcr_multi_destroy(pcr_multi* m) {
+  if (!m) return;
+  for (pcr_ctx* c : m->ctx) pcr_destroy(c);
+  delete m;
+}
+
+extern "C" const char* pcr_multi_last_error(const pcr_multi* m) { return m ? m->err.c_str() : ""; }
+
+extern "C" int pcr_multi_get_broadcast(const pcr_multi* m, size_t* blob_bytes, double* copy_ms) {
+  if (!m) return PCR_ERR_INVALID;
+  if (blob_bytes) *blob_bytes = m->blob_bytes;
+  if (copy_ms) *copy_ms = m->copy_ms;
+  return PCR_OK;
+}
+
+extern "C" int pcr_multi_set_target(pcr_multi* m, const void* pts, size_t n, size_t stride) {
+  if (!m) return PCR_ERR_INVALID;
+  pcr_ctx* c0 = m->ctx[0];
+  int rc = pcr_set_target(c0, pts, n, stride);
+  if (rc) { m->err = pcr_last_error(c0); return rc; }
+  m->blob_bytes = 0;
+  m->copy_ms = 0.0;
+  if (m->ctx.size() == 1) return PCR_OK;
+  size_t bytes = 0;
+  rc = pcr_target_blob_size(c0, &bytes);
+  if (rc) { m->err = pcr_last_error(c0); return rc; }
+  void* blob0 = nullptr;
+  std::vector<void*> blobs(m->ctx.size(), nullptr);
+  auto cleanup = [&]() {
+    for (size_t k = 0; k < blobs.size(); k++)
+      if (blobs[k]) { cudaSetDevice(m->dev[k]); cudaFree(blobs[k]); }
+  };
+  try {
+    PCR_CUDA_CHECK(cudaSetDevice(m->dev[0]));
+    PCR_CUDA_CHECK(cudaMalloc(&blob0, bytes));
+    blobs[0] = blob0;
+    rc = pcr_target_export(c0, blob0, bytes);
+    if (rc) { m->err = pcr_last_error(c0); cleanup(); return rc; }
+    // all copies are queued before the first one is waited for: NVSwitch gives every peer the full link rate
+    for (size_t k = 1; k < m->ctx.size(); k++) {
+      PCR_CUDA_CHECK(cudaSetDevice(m->dev[k]));
+      PCR_CUDA_CHECK(cudaMalloc(&blobs[k], bytes));
+      if (m->dev[k] != m->dev[0]) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, m->dev[k], m->dev[0]);
+        if (can) { cudaError_t e = cudaDeviceEnablePeerAccess(m->dev[0], 0); if (e != cudaSuccess) cudaGetLastError(); }  // already enabled is fine
+      }
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (size_t k = 1; k < m->ctx.size(); k++) {
+      PCR_CUDA_CHECK(cudaSetDevice(m->dev[k]));
+      PCR_CUDA_CHECK(cudaMemcpyPeerAsync(blobs[k], m->dev[k], blob0, m->dev[0], bytes, m->ctx[k]->stream));
+    }
+    for (size_t k = 1; k < m->ctx.size(); k++) {
+      PCR_CUDA_CHECK(cudaSetDevice(m->dev[k]));
+      PCR_CUDA_CHECK(cudaStreamSynchronize(m->ctx[k]->stream));
+    }
+    m->copy_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    m->blob_bytes = bytes;
+    for (size_t k = 1; k < m->ctx.size(); k++) {
+      rc = pcr_target_import(m->ctx[k], blobs[k], bytes);
+      if (rc) { m->err = pcr_last_error(m->ctx[k]); cleanup(); return rc; }
+    }
+  } catch (const std::exception& e) {
+    m->err = e.what();
+    cudaGetLastError();
+    cleanup();
+    return PCR_ERR_CUDA;
+  }
+  cleanup();
+  return PCR_OK;
+}
+
+extern "C" int pcr_multi_batch_align(pcr_multi* m, const void* src, const size_t* offsets, size_t n_scans, size_t stride, double* T,
+                                     int32_t* converged) {
+  if (!m || !offsets || !T) return PCR_ERR_INVALID;
+  const size_t nd = m->ctx.size();
+  std::vector<int> rcs(nd, PCR_OK);
+  std::vector<std::thread> th;
+  auto shard = [&](size_t k) {  // contiguous blocks, the first n % nd shards one scan longer (multigpu.shard)
+    const size_t base = n_scans / nd, rem = n_scans % nd;
+    const size_t lo = k * base + std::min(k, rem);
+    return std::make_pair(lo, lo + base + (k < rem ? 1 : 0));
+  };
+  for (size_t k = 0; k < nd; k++) {
+    th.emplace_back([&, k]() {
+      const auto r = shard(k);
+      if (r.second == r.first) return;
+      rcs[k] = pcr_batch_align(m->ctx[k], src, offsets + r.first, r.second - r.first, stride, T + 16 * r.first, converged ? converged + r.first : nullptr);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (size_t k = 0; k < nd; k++)
+    if (rcs[k]) { m->err = pcr_last_error(m->ctx[k]); return rcs[k]; }
+  return PCR_OK;
 }
 
 // ---- on-disk index cache + PCD reader -----------------------------------------------------------

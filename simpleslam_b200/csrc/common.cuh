@@ -38,9 +38,9 @@ class DevPool {
     while (c < bytes) c <<= 1;
     return c;
   }
-  static void* alloc(size_t bytes, size_t& got) {
+  static void* alloc(size_t bytes, size_t& got, int& dev) {
     got = size_class(bytes);
-    int dev = 0;
+    dev = 0;
     PCR_CUDA_CHECK(cudaGetDevice(&dev));
     {
       std::lock_guard<std::mutex> lk(mu());
@@ -57,20 +57,29 @@ class DevPool {
     if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc(") + std::to_string(got) + " bytes) failed: " + cudaGetErrorString(e));
     return p;
   }
-  // the caller guarantees that no work touching p is still in flight
-  static void release(void* p, size_t got) {
+  // the caller guarantees that no work touching p is still in flight; dev = the device the allocation came from
+  static void release(void* p, size_t got, int dev) {
     if (!p) return;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) { cudaFree(p); return; }
     std::lock_guard<std::mutex> lk(mu());
     free_list()[std::make_pair(dev, got)].push_back(p);
   }
+  // bytes parked in the cache (all devices)
+  static size_t cached_bytes() {
+    std::lock_guard<std::mutex> lk(mu());
+    size_t t = 0;
+    for (auto& kv : free_list()) t += kv.first.second * kv.second.size();
+    return t;
+  }
   static void trim() {
     std::lock_guard<std::mutex> lk(mu());
+    int cur = 0;
+    const bool have = cudaGetDevice(&cur) == cudaSuccess;
     for (auto& kv : free_list()) {
+      if (!kv.second.empty()) cudaSetDevice(kv.first.first);
       for (void* p : kv.second) cudaFree(p);
       kv.second.clear();
     }
+    if (have) cudaSetDevice(cur);
   }
 
  private:
@@ -87,6 +96,7 @@ struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;        // elements
   size_t bytes_ = 0;     // size class the allocation was taken from
+  int dev_ = 0;          // device the allocation lives on
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -95,18 +105,18 @@ struct DevBuf {
     if (n > cap) {
       if (p) {
         cudaDeviceSynchronize();  // the old buffer may still be read by queued work (what cudaFree's implicit sync used to cover)
-        DevPool::release(p, bytes_);
+        DevPool::release(p, bytes_, dev_);
         p = nullptr;
         cap = 0;
       }
       const size_t want = n + n / 4 + 64;
-      p = static_cast<T*>(DevPool::alloc(want * sizeof(T), bytes_));
+      p = static_cast<T*>(DevPool::alloc(want * sizeof(T), bytes_, dev_));
       cap = bytes_ / sizeof(T);
     }
     return p;
   }
   void release() {
-    if (p) DevPool::release(p, bytes_);
+    if (p) DevPool::release(p, bytes_, dev_);
     p = nullptr;
     cap = 0;
   }
