@@ -87,29 +87,47 @@ def _big_map(sc, extent, spacing, seed=7, strips=16):
     return np.concatenate(parts)
 
 
-def c4_batched(method, downsample, n_scans, seed_offset=0, tiles=4, spacing=0.24):
+C4_TILES, C4_SPACING = 4, 0.24
+
+
+def c4_map(downsample, tiles=C4_TILES, spacing=C4_SPACING):
+    """the static map of C4: surfaces of tiles x tiles 200 m tiles sampled at `spacing`, voxel-downsampled at 0.2 m (~20M points)"""
+    sc = synth.Scene(seed=SEED, tiles=(tiles, tiles))
+    raw = _big_map(sc, 200.0 * tiles, spacing)
+    dst = downsample(raw, 0.2)
+    return dst, len(raw)
+
+
+def c4_scans(method, downsample, lo, hi, n_total, seed_offset=0, tiles=C4_TILES, workers=8):
+    """scans [lo, hi) of the n_total-scan localisation job (every rank generates only its shard; scan k is the same whatever
+    the sharding): random poses all over the map, LOAM: VLP-16 scans downsampled at 0.5 m, NDT: raw 64-beam scans,
+    guess = truth o small perturbation."""
+    from concurrent.futures import ThreadPoolExecutor
+    sc = synth.Scene(seed=SEED, tiles=(tiles, tiles))
+    extent = 200.0 * tiles
+    rng = np.random.RandomState(41 + seed_offset)
+    truths, guesses = [], []
+    for k in range(n_total):  # the pose stream is drawn for the whole job so that shards agree on it
+        T = sc.free_pose_near(rng.uniform(60.0, extent - 60.0), rng.uniform(60.0, extent - 60.0), 2.0, rng.uniform(-np.pi, np.pi))
+        G = T @ (_perturb(rng, 0.3, 2.0) if method == "loam" else _perturb(rng, 0.5, 3.0))
+        truths.append(T)
+        guesses.append(G)
+    sensor, base = ("vlp16", 11000) if method == "loam" else ("hdl64", 12000)
+
+    def one(k):
+        return np.ascontiguousarray(sc.scan(truths[k], sensor, seed=base + k + 100000 * seed_offset))
+    with ThreadPoolExecutor(max_workers=workers) as ex:  # the raycaster releases the GIL
+        raw = list(ex.map(one, range(lo, hi)))
+    scans = [downsample(r, 0.5) for r in raw] if method == "loam" else raw
+    return scans, truths[lo:hi], guesses[lo:hi]
+
+
+def c4_batched(method, downsample, n_scans, seed_offset=0, tiles=C4_TILES, spacing=C4_SPACING):
     """C4 batched localisation (loc.cpp mode): independent scans at random poses all over a static map of ~20M points
     (4x4 tiles of 200 m, surfaces sampled at 0.24 m then voxel-downsampled at 0.2 m). LOAM: VLP-16 scans downsampled at
     0.5 m; NDT: raw 64-beam scans. Guess = truth o small perturbation."""
-    sc = synth.Scene(seed=SEED, tiles=(tiles, tiles))
-    extent = 200.0 * tiles
-    raw = _big_map(sc, extent, spacing)
-    dst = downsample(raw, 0.2)
-    n_raw = len(raw)
-    del raw
-    rng = np.random.RandomState(41 + seed_offset)
-    scans, truths, guesses = [], [], []
-    for k in range(n_scans):
-        T = sc.free_pose_near(rng.uniform(60.0, extent - 60.0), rng.uniform(60.0, extent - 60.0), 2.0, rng.uniform(-np.pi, np.pi))
-        if method == "loam":
-            s = downsample(sc.scan(T, "vlp16", seed=11000 + k + 100000 * seed_offset), 0.5)
-            G = T @ _perturb(rng, 0.3, 2.0)
-        else:
-            s = sc.scan(T, "hdl64", seed=12000 + k + 100000 * seed_offset)
-            G = T @ _perturb(rng, 0.5, 3.0)
-        scans.append(s)
-        truths.append(T)
-        guesses.append(G)
+    dst, n_raw = c4_map(downsample, tiles, spacing)
+    scans, truths, guesses = c4_scans(method, downsample, 0, n_scans, n_scans, seed_offset, tiles)
     name = "C4 batched localisation (%s): independent %s scans vs a %.1fM-pt static map (%dx%d tiles)" % (
         method.upper(), "VLP-16 (0.5 m downsample)" if method == "loam" else "64-beam", len(dst) / 1e6, tiles, tiles)
     return dict(name=name, method=method, dst=dst, scans=scans, truths=truths, guesses=guesses, raw_map_points=n_raw)
