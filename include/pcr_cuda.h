@@ -143,11 +143,17 @@ int pcr_voxel_downsample_device(pcr_ctx* c, const void* dev_pts, size_t n, size_
  * transformed by poses[i] (cast to float, pcp::transformPointCloud, common/pcp/pcp.hpp:38-62), the clouds are
  * concatenated in the given order and voxel-downsampled at `leaf` (pcp::voxelDownSample). The result becomes the
  * context's current target (index built as by pcr_set_target) and stays on the device; `out` (nullable, HOST) receives
- * up to `cap` 32-byte PointXYZI records, *m their number. Keyframe clouds are immutable in the reference (KeyFrame::pc is
- * a const shared_ptr): their device copies are cached by (host pointer, count) so that a keyframe crosses PCIe once;
- * pcr_submap_cache_clear drops the cache. poses: 16 doubles per cloud, column-major. */
-int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const size_t* counts, size_t n_clouds, size_t stride, const double* poses,
-                     float leaf, void* out, size_t cap, size_t* m);
+ * up to `cap` 32-byte PointXYZI records, *m their number. poses: 16 doubles per cloud, column-major.
+ * Keyframe clouds are immutable in the reference (KeyFrame::pc is a const shared_ptr), so a keyframe should cross PCIe once:
+ * `ids` (nullable) names every cloud with a caller-chosen keyframe id (the keyframe's index in the reference's keyframe
+ * deque); device copies are cached BY ID (never by host address) and re-uploaded when the count under an id changes.
+ * The cache is bounded: entries not part of the submap being built are evicted least-recently-used first once the
+ * cache exceeds its byte budget (pcr_submap_cache_budget, default 1 GiB). ids == NULL: nothing is cached. */
+int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const size_t* counts, const int64_t* ids, size_t n_clouds, size_t stride,
+                     const double* poses, float leaf, void* out, size_t cap, size_t* m);
+int pcr_submap_cache_budget(pcr_ctx* c, size_t bytes);
+/* bytes / entries currently cached (either pointer may be NULL) */
+int pcr_submap_cache_info(const pcr_ctx* c, size_t* bytes, size_t* entries);
 int pcr_submap_cache_clear(pcr_ctx* c);
 
 /* Multi-GPU: serialise the built target index into one contiguous DEVICE blob so that it can be broadcast with NCCL

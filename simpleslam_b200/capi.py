@@ -23,7 +23,7 @@ SYMBOLS = [
     "pcr_target_blob_size", "pcr_target_export", "pcr_target_import", "pcr_debug_voxel", "pcr_loam_linearize",
     "pcr_loam_get_logs", "pcr_ndt_num_leaves", "pcr_ndt_get_leaves", "pcr_ndt_derivatives", "pcr_ndt_hessian",
     "pcr_gicp_covariances", "pcr_vgicp_num_voxels", "pcr_vgicp_get_voxels", "pcr_vgicp_evaluate",
-    "pcr_submap_build", "pcr_submap_cache_clear", "pcr_target_save", "pcr_target_load", "pcr_read_pcd", "pcr_static_map_load",
+    "pcr_submap_build", "pcr_submap_cache_clear", "pcr_submap_cache_budget", "pcr_submap_cache_info", "pcr_target_save", "pcr_target_load", "pcr_read_pcd", "pcr_static_map_load",
     "pcr_scancontext_make", "pcr_scancontext_distance", "pcr_loam_last_shape",
     "pcr_multi_create", "pcr_multi_destroy", "pcr_multi_last_error", "pcr_multi_set_target", "pcr_multi_batch_align", "pcr_multi_get_broadcast", "pcr_trim_device_cache",
 ]
@@ -319,21 +319,31 @@ class Context:
         return dict(keys=keys[:n], out_keys=ok[:m], counts=oc[:m], grid=grid)
 
     # -- submap assembly (MapManager::updateMap / loopFindNearKeyframes): transform + concat + downsample on the device;
-    # the result becomes the current target. clouds: list of (n, 8) float32 arrays that must stay alive (cached by pointer)
-    def submap_build(self, clouds, poses, leaf, want_points=True):
+    # the result becomes the current target. ids (optional): keyframe ids — device copies of the clouds are cached by id
+    # (bounded, LRU), never by host address; without ids every cloud is uploaded again
+    def submap_build(self, clouds, poses, leaf, want_points=True, ids=None):
         k = len(clouds)
         arrs = [_cloud(cl) for cl in clouds]
         ptrs = (ctypes.c_void_p * max(k, 1))(*[a.ctypes.data for a, _, _ in arrs])
         counts = (ctypes.c_size_t * max(k, 1))(*[n for _, n, _ in arrs])
+        idarr = (ctypes.c_int64 * max(k, 1))(*[int(i) for i in ids]) if ids is not None else None
         stride = arrs[0][2] if k else 32
         assert all(st == stride for _, _, st in arrs), "all keyframe clouds must share one record stride"
         P = np.ascontiguousarray(np.concatenate([_T_in(T) for T in poses]) if k else np.zeros(16))
         total = int(sum(n for _, n, _ in arrs))
         out = np.empty((max(total, 1), 8), np.float32) if want_points else None
         m = ctypes.c_size_t(0)
-        self._check(lib().pcr_submap_build(self._h, ptrs, counts, ctypes.c_size_t(k), ctypes.c_size_t(stride), _vp(P), ctypes.c_float(leaf),
+        self._check(lib().pcr_submap_build(self._h, ptrs, counts, idarr, ctypes.c_size_t(k), ctypes.c_size_t(stride), _vp(P), ctypes.c_float(leaf),
                                            _vp(out), ctypes.c_size_t(total), ctypes.byref(m)))
         return (out[:m.value].copy() if want_points else None), m.value
+
+    def submap_cache_budget(self, nbytes):
+        self._check(lib().pcr_submap_cache_budget(self._h, ctypes.c_size_t(int(nbytes))))
+
+    def submap_cache_info(self):
+        b, e = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        self._check(lib().pcr_submap_cache_info(self._h, ctypes.byref(b), ctypes.byref(e)))
+        return dict(bytes=b.value, entries=e.value)
 
     def submap_cache_clear(self):
         self._check(lib().pcr_submap_cache_clear(self._h))

@@ -13,6 +13,7 @@
 #include <pcr_cuda.h>
 
 #include <cstdio>
+#include <limits>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -116,8 +117,13 @@ class VgicpRegister : public CudaRegister {
   explicit VgicpRegister(int cores_ = 4, int device = 0) : CudaRegister(PCR_VGICP, cores_, device) {}
   void initForLC() { pcr_vgicp_init_for_lc(ctx_); }  // PCR/src/VgicpRegister.cpp:21-28
   scalar_t getFitnessScore() override {             // PCR/src/VgicpRegister.cpp:42-45
-    double s = 0;
-    if (pcr_fitness(ctx_, &s) != PCR_OK) std::fprintf(stderr, "[PCR] fitness failed: %s\n", pcr_last_error(ctx_));
+    // fails CLOSED: pcl::Registration::getFitnessScore answers max() when it has nothing to measure, and the loop-closure
+    // gate is `fitness < 0.3` (backend/src/LoopClosureManager.cpp:98) — a failed computation must not pass as a perfect match
+    double s = std::numeric_limits<double>::max();
+    if (pcr_fitness(ctx_, &s) != PCR_OK) {
+      std::fprintf(stderr, "[PCR] fitness failed: %s\n", pcr_last_error(ctx_));
+      return std::numeric_limits<double>::max();
+    }
     return s;
   }
 };

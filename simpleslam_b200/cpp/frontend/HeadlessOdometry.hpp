@@ -125,6 +125,7 @@ class MapManager {
     std::vector<const void*> clouds;
     std::vector<size_t> counts;
     std::vector<double> poses;
+    std::vector<int64_t> ids;  // keyframe index = cache key of the device copy (a keyframe crosses PCIe once)
     submap_idx_.clear();
     for (size_t i = 0; i < keyframes_.size(); i++) {
       const double d = m4::dist(keyframes_[i].pose.matrix().data(), cur_.matrix().data());
@@ -132,12 +133,13 @@ class MapManager {
         submap_idx_.push_back(i);
         clouds.push_back(keyframes_[i].pc->points.data());
         counts.push_back(keyframes_[i].pc->size());
+        ids.push_back(int64_t(i));
         const double* T = keyframes_[i].pose.matrix().data();
         poses.insert(poses.end(), T, T + 16);
       }
     }
     size_t m = 0;
-    if (pcr_submap_build(ctx_, clouds.data(), counts.data(), clouds.size(), sizeof(pt_t), poses.data(), grid_, nullptr, 0, &m) != PCR_OK)
+    if (pcr_submap_build(ctx_, clouds.data(), counts.data(), ids.data(), clouds.size(), sizeof(pt_t), poses.data(), grid_, nullptr, 0, &m) != PCR_OK)
       throw std::runtime_error(std::string("pcr_submap_build: ") + pcr_last_error(ctx_));
     submap_size_ = m;
   }

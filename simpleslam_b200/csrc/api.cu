@@ -34,7 +34,7 @@ struct pcr_ctx {
 
   // staging
   DevBuf<unsigned char> raw_src, raw_dst;
-  DevBuf<float4> src, dst, ds_in;
+  DevBuf<float4> src, dst, ds_in, nf_scratch;
   DevBuf<unsigned char> ds_out;
   PinBuf<unsigned char> pin;
   KeySort ks, ks_ds;
@@ -56,15 +56,18 @@ struct pcr_ctx {
   NdtDriver ndtd;
   VgicpDriver vgd;
 
-  // submap assembly: device copies of immutable keyframe clouds, keyed by (host pointer, count)
-  struct CachedCloud { DevBuf<float4> pts; size_t n = 0; };
-  std::map<std::pair<const void*, size_t>, std::unique_ptr<CachedCloud>> kf_cache;
+  // submap assembly: device copies of immutable keyframe clouds, keyed by the caller's keyframe id, LRU within a byte budget
+  struct CachedCloud { DevBuf<float4> pts; size_t n = 0; uint64_t last_use = 0; };
+  std::map<int64_t, std::unique_ptr<CachedCloud>> kf_cache;
+  size_t kf_budget = size_t(1) << 30;
+  uint64_t kf_clock = 0;
+  DevBuf<float4> sub_uncached;  // clouds of a build without ids
   DevBuf<float4> sub_concat;
   DevBuf<unsigned char> sub_meta;
   PinBuf<unsigned char> sub_meta_h;
 
   // VGICP: last registration (for getFitnessScore)
-  size_t last_ns = 0;
+  size_t last_ns = 0, last_off = 0;
   double last_T[16];
   bool has_last = false;
 };
@@ -213,21 +216,26 @@ static const float4* adopt_points(pcr_ctx* c, const void* dev, size_t n, size_t 
   return out.p;
 }
 
+static int build_target_once(pcr_ctx* c, const float4* pts, size_t n) {
+  switch (c->prm.method) {
+    case PCR_LOAM: return loam_build_target(pts, n, double(c->prm.loam_max_knn_d2), c->loam_grid, c->ks, c->bw, c->stream);
+    case PCR_NDT: return ndt_build_target(pts, n, c->prm, c->ndt, c->ks, c->bw, c->stream);
+    case PCR_VGICP: return vgicp_build_target(pts, n, c->prm, c->vg, c->ks, c->bw, c->stream);
+  }
+  return PCR_ERR_INVALID;
+}
+
+// pts: a context-owned packed copy of the cloud (c->dst). Records with a NaN / Inf coordinate are dropped (order kept) the
+// way the reference never lets them reach a register (LidarDataProxy.cpp:47) and PCL's voxel grids skip them.
 static int build_target(pcr_ctx* c, const float4* pts, size_t n) {
   c->has_target = false;
   c->n_target = n;
   c->has_last = false;
-  int rc = 0;
-  switch (c->prm.method) {
-    case PCR_LOAM:
-      rc = loam_build_target(pts, n, double(c->prm.loam_max_knn_d2), c->loam_grid, c->ks, c->bw, c->stream);
-      break;
-    case PCR_NDT:
-      rc = ndt_build_target(pts, n, c->prm, c->ndt, c->ks, c->bw, c->stream);
-      break;
-    case PCR_VGICP:
-      rc = vgicp_build_target(pts, n, c->prm, c->vg, c->ks, c->bw, c->stream);
-      break;
+  int rc = build_target_once(c, pts, n);
+  if (rc == kRetryNonFinite) {
+    n = drop_nonfinite(const_cast<float4*>(pts), n, c->nf_scratch, c->ks.tmp, c->ks.d_count, c->ks.h_count, c->stream);
+    c->n_target = n;
+    rc = build_target_once(c, pts, n);
   }
   if (rc == PCR_ERR_GRID_TOO_LARGE) return fail(c, rc, "target bounding box needs a cell table larger than the dense-table budget");
   if (rc) return fail(c, rc, "target build failed");
@@ -300,11 +308,18 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       float hot = 0.f;
       int hotl = 0, evals = 0;
       long long corr = 0;
+      size_t last_off = 0, last_cnt = 0;
       for (size_t i = 0; i < n_scans && rc == 0; i++) {  // independent scans, processed one after the other
-        const size_t ns = offs[i + 1] - offs[i];
+        size_t ns = offs[i + 1] - offs[i];
         const float4* sp = src + (offs[i] - offs[0]);
         rc = c->vgd.compute_source_covs(sp, ns, c->prm.vgicp_k, c->ks, c->bw, c->stream);
+        if (rc == kRetryNonFinite) {  // NaN / Inf records of this scan are dropped inside its own segment of the staging copy
+          ns = drop_nonfinite(const_cast<float4*>(sp), ns, c->nf_scratch, c->ks.tmp, c->ks.d_count, c->ks.h_count, c->stream);
+          rc = c->vgd.compute_source_covs(sp, ns, c->prm.vgicp_k, c->ks, c->bw, c->stream);
+        }
         if (rc) break;
+        last_off = offs[i] - offs[0];
+        last_cnt = ns;
         rc = c->vgd.align(sp, ns, c->vg, c->prm, T + i * 16, &conv[i], &iters[i], c->profiling, c->stream);
         hot += c->vgd.hot_ms;
         hotl += c->vgd.hot_launches;
@@ -322,9 +337,13 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       st.ms_hot_kernel = hot;
       st.hot_kernel_launches = hotl;
       // remember the last scan for getFitnessScore (pcl keeps input_ + final_transformation_)
-      c->last_ns = offs[n_scans] - offs[n_scans - 1];
-      memcpy(c->last_T, T + (n_scans - 1) * 16, sizeof(double) * 16);
-      c->has_last = true;
+      c->has_last = false;
+      if (rc == 0) {
+        c->last_ns = last_cnt;
+        c->last_off = last_off;
+        memcpy(c->last_T, T + (n_scans - 1) * 16, sizeof(double) * 16);
+        c->has_last = true;
+      }
       break;
     }
   }
@@ -391,11 +410,14 @@ extern "C" int pcr_batch_align_device(pcr_ctx* c, const void* dev_src, const siz
 extern "C" int pcr_fitness(pcr_ctx* c, double* score) {
   PCR_API_BEGIN(c)
   if (!score) return PCR_ERR_INVALID;
-  *score = 0.0;  // PointCloudRegister::getFitnessScore() base implementation returns 0
+  *score = 0.0;  // PointCloudRegister::getFitnessScore() base implementation returns 0 (LOAM / NDT)
   if (c->prm.method != PCR_VGICP) return PCR_OK;
+  // pcl::Registration::getFitnessScore answers DBL_MAX when it has nothing to measure: a failed call must never look like a
+  // perfect match to the loop-closure gate (`fitness < 0.3`, LoopClosureManager.cpp:98)
+  *score = DBL_MAX;
   if (!c->has_target || !c->has_last) return fail(c, PCR_ERR_NO_TARGET, "getFitnessScore before scan2Map");
-  // the last source scan is still resident at the tail of c->src
-  const float4* sp = c->src.p + (size_t(c->stats.n_source) - c->last_ns);
+  // the last source scan is still resident in the staging copy c->src
+  const float4* sp = c->src.p + c->last_off;
   return c->vgd.fitness(sp, c->last_ns, c->vg, c->last_T, DBL_MAX, score, c->stream);
   PCR_API_END(c)
 }
@@ -408,6 +430,12 @@ static int downsample_packed(pcr_ctx* c, const float4* pts, size_t n, float leaf
   if (n == 0) { *m = 0; return PCR_OK; }
   float mn[3], mx[3];
   bbox_blocking(pts, n, mn, mx, c->bw, c->stream);
+  if (c->bw.n_nonfinite) {  // pcl::VoxelGrid skips non-finite points of a non-dense cloud (voxel_grid.hpp: `if (!isFinite(point)) continue`)
+    n = drop_nonfinite(const_cast<float4*>(pts), n, c->nf_scratch, c->ks_ds.tmp, c->ks_ds.d_count, c->ks_ds.h_count, c->stream);
+    c->ds_n = n;
+    if (n == 0) { *m = 0; return PCR_OK; }
+    bbox_blocking(pts, n, mn, mx, c->bw, c->stream);
+  }
   if (!make_grid_spec(mn, mx, leaf, c->ds_grid)) {
     // PCL: "Leaf size is too small for the input dataset" -> the input is returned unchanged
     c->ds_overflow = true;
@@ -492,7 +520,22 @@ extern "C" int pcr_submap_cache_clear(pcr_ctx* c) {
   return PCR_OK;
 }
 
-extern "C" int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const size_t* counts, size_t n_clouds, size_t stride,
+extern "C" int pcr_submap_cache_budget(pcr_ctx* c, size_t bytes) {
+  if (!c) return PCR_ERR_INVALID;
+  c->kf_budget = bytes;
+  return PCR_OK;
+}
+
+extern "C" int pcr_submap_cache_info(const pcr_ctx* c, size_t* bytes, size_t* entries) {
+  if (!c) return PCR_ERR_INVALID;
+  size_t b = 0;
+  for (const auto& kv : c->kf_cache) b += kv.second->pts.bytes_;
+  if (bytes) *bytes = b;
+  if (entries) *entries = c->kf_cache.size();
+  return PCR_OK;
+}
+
+extern "C" int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const size_t* counts, const int64_t* ids, size_t n_clouds, size_t stride,
                                 const double* poses, float leaf, void* out, size_t cap, size_t* m) {
   PCR_API_BEGIN(c)
   if (!m || !(leaf > 0.f) || stride < 12 || stride % 4 || (n_clouds && (!clouds || !counts || !poses))) return fail(c, PCR_ERR_INVALID, "bad arguments");
@@ -501,21 +544,38 @@ extern "C" int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const siz
   auto now = [&]() { if (trace) cudaStreamSynchronize(c->stream); return std::chrono::steady_clock::now(); };
   auto t_start = now();
   SubmapPart* hp = reinterpret_cast<SubmapPart*>(c->sub_meta_h.ensure((n_clouds + 1) * sizeof(SubmapPart)));
-  size_t total = 0, np = 0;
+  size_t total = 0, np = 0, uncached_total = 0;
+  if (!ids) {
+    for (size_t k = 0; k < n_clouds; k++) uncached_total += counts[k];
+    c->sub_uncached.ensure(uncached_total + 1);
+  }
+  const uint64_t stamp = ++c->kf_clock;
+  size_t unc_off = 0;
   for (size_t k = 0; k < n_clouds; k++) {
     if (counts[k] == 0) continue;
     if (!clouds[k]) return fail(c, PCR_ERR_INVALID, "null keyframe cloud");
-    auto key = std::make_pair(clouds[k], counts[k]);
-    auto it = c->kf_cache.find(key);
-    if (it == c->kf_cache.end()) {
-      std::unique_ptr<pcr_ctx::CachedCloud> cc(new pcr_ctx::CachedCloud());
-      cc->n = counts[k];
-      upload_points(c, clouds[k], counts[k], stride, c->raw_src, cc->pts);
-      // raw_src is reused by the next upload: the pack kernel of this one is already queued on the same stream
-      it = c->kf_cache.emplace(key, std::move(cc)).first;
+    const float4* dev_pts = nullptr;
+    if (ids) {
+      auto it = c->kf_cache.find(ids[k]);
+      if (it == c->kf_cache.end() || it->second->n != counts[k]) {
+        std::unique_ptr<pcr_ctx::CachedCloud> cc(new pcr_ctx::CachedCloud());
+        cc->n = counts[k];
+        upload_points(c, clouds[k], counts[k], stride, c->raw_src, cc->pts);
+        // raw_src is reused by the next upload: the pack kernel of this one is already queued on the same stream
+        if (it != c->kf_cache.end()) { cudaStreamSynchronize(c->stream); c->kf_cache.erase(it); }
+        it = c->kf_cache.emplace(ids[k], std::move(cc)).first;
+      }
+      it->second->last_use = stamp;
+      dev_pts = it->second->pts.p;
+    } else {
+      c->raw_src.ensure(counts[k] * stride);
+      PCR_CUDA_CHECK(cudaMemcpyAsync(c->raw_src.p, clouds[k], counts[k] * stride, cudaMemcpyHostToDevice, c->stream));
+      pack_points(c->raw_src.p, counts[k], stride, c->sub_uncached.p + unc_off, c->stream);
+      dev_pts = c->sub_uncached.p + unc_off;
+      unc_off += counts[k];
     }
     SubmapPart& p = hp[np++];
-    p.src = it->second->pts.p;
+    p.src = dev_pts;
     p.offset = total;
     p.n = counts[k];
     const double* T = poses + k * 16;
@@ -523,6 +583,20 @@ extern "C" int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const siz
       p.T[r * 4 + 0] = float(T[r]); p.T[r * 4 + 1] = float(T[4 + r]); p.T[r * 4 + 2] = float(T[8 + r]); p.T[r * 4 + 3] = float(T[12 + r]);
     }
     total += counts[k];
+  }
+  if (ids) {  // bound the cache: least-recently-used entries that are not part of this submap go first
+    size_t bytes = 0;
+    for (const auto& kv : c->kf_cache) bytes += kv.second->pts.bytes_;
+    bool synced = false;
+    while (bytes > c->kf_budget) {
+      auto victim = c->kf_cache.end();
+      for (auto it = c->kf_cache.begin(); it != c->kf_cache.end(); ++it)
+        if (it->second->last_use != stamp && (victim == c->kf_cache.end() || it->second->last_use < victim->second->last_use)) victim = it;
+      if (victim == c->kf_cache.end()) break;  // everything left belongs to the current submap
+      if (!synced) { PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream)); synced = true; }  // an older build may still read it
+      bytes -= victim->second->pts.bytes_;
+      c->kf_cache.erase(victim);
+    }
   }
   c->has_target = false;
   c->has_last = false;
@@ -535,8 +609,10 @@ extern "C" int pcr_submap_build(pcr_ctx* c, const void* const* clouds, const siz
   c->sub_meta.ensure(np * sizeof(SubmapPart));
   PCR_CUDA_CHECK(cudaMemcpyAsync(c->sub_meta.p, hp, np * sizeof(SubmapPart), cudaMemcpyHostToDevice, c->stream));
   c->sub_concat.ensure(total);
+  if ((np + 1) * sizeof(unsigned long long) > 40 * 1024) return fail(c, PCR_ERR_INVALID, "too many keyframe clouds in one submap (limit 5000)");
   submap_transform_kernel<<<unsigned((total + 255) / 256), 256, (np + 1) * sizeof(unsigned long long), c->stream>>>(
       reinterpret_cast<const SubmapPart*>(c->sub_meta.p), int(np), total, c->sub_concat.p);
+  PCR_CUDA_CHECK(cudaGetLastError());
   auto t_tr = now();
   c->ds_out.ensure(total * 32);
   size_t mm = 0;
@@ -602,8 +678,79 @@ struct BlobHeader {
   int32_t i[16];
   float f[16];
   uint64_t u[4];
+  uint64_t params_hash;  // of the build parameters the index depends on (an index built with other parameters is refused)
+  uint64_t reserved;
 };
-constexpr uint64_t kMagic = 0x32505242323030ull;  // "PCRB200" v2
+constexpr uint64_t kMagic = 0x33505242323030ull;  // "PCRB200" v3
+
+// FNV-1a over the parameters a built index depends on
+uint64_t params_hash(const pcr_params& p) {
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&](const void* v, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(v);
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+  };
+  mix(&p.method, sizeof(p.method));
+  switch (p.method) {
+    case PCR_LOAM: mix(&p.loam_max_knn_d2, sizeof(p.loam_max_knn_d2)); break;
+    case PCR_NDT:
+      mix(&p.ndt_resolution, sizeof(p.ndt_resolution)); mix(&p.ndt_min_points, sizeof(p.ndt_min_points));
+      mix(&p.ndt_eig_mult, sizeof(p.ndt_eig_mult)); mix(&p.ndt_outlier_ratio, sizeof(p.ndt_outlier_ratio));
+      break;
+    case PCR_VGICP: mix(&p.vgicp_resolution, sizeof(p.vgicp_resolution)); mix(&p.vgicp_k, sizeof(p.vgicp_k)); break;
+  }
+  return h;
+}
+
+// a blob is only trusted after every section has been checked against the blob length and against the grid / counts
+// the header itself states (a truncated, corrupt or older-layout file must not drive copies or allocations)
+const char* validate_blob(const BlobHeader& h, size_t bytes) {
+  size_t off = (sizeof(BlobHeader) + 255) & ~size_t(255);
+  for (int k = 0; k < 8; k++) {
+    if (h.sizes[k] > bytes) return "section larger than the blob";
+    const size_t a = (size_t(h.sizes[k]) + 255) & ~size_t(255);
+    if (off + a > bytes || off + a < off) return "sections run past the end of the blob";
+    off += a;
+  }
+  auto grid_ok = [](const GridSpec& g) {
+    if (g.ncell <= 0 || g.ncell > (1ll << 29)) return false;
+    for (int a = 0; a < 3; a++)
+      if (g.div_b[a] <= 0 || g.max_b[a] - g.min_b[a] + 1 != g.div_b[a] || !(g.leaf[a] > 0.f)) return false;
+    if ((long long)g.div_b[0] * g.div_b[1] * g.div_b[2] != g.ncell) return false;
+    return g.mul[0] == 1 && g.mul[1] == g.div_b[0] && (long long)g.mul[2] == (long long)g.div_b[0] * g.div_b[1];
+  };
+  if (h.method == PCR_LOAM) {
+    if (h.i[0] == 0) return (h.sizes[0] || h.sizes[1]) ? "unbuilt LOAM index with sections" : nullptr;
+    if (!grid_ok(h.g)) return "LOAM grid inconsistent";
+    if (h.sizes[0] != h.n_target * sizeof(float4) || h.sizes[0] > (size_t(1) << 36)) return "LOAM point section does not match n_target";
+    if (h.sizes[1] != (size_t(h.g.ncell) + 1) * sizeof(int32_t)) return "LOAM start table does not match the grid";
+    if (h.i[1] != 1 && h.i[1] != 2) return "LOAM ring count out of range";
+  } else if (h.method == PCR_NDT) {
+    if (h.i[0] != 0 || h.i[1] == 0) return nullptr;  // overflow / no leaves: nothing follows
+    if (h.i[1] < 0 || !grid_ok(h.g)) return "NDT grid inconsistent";
+    const size_t L = size_t(h.i[1]);
+    const size_t want[8] = {L * sizeof(NdtLeafRec), size_t(h.g.ncell) * sizeof(int32_t), L * 24, L * 72, L * 72, L * 4, L * 4, L * sizeof(float4)};
+    for (int k = 0; k < 8; k++)
+      if (h.sizes[k] != want[k]) return "NDT section size does not match the leaf count / grid";
+  } else if (h.method == PCR_VGICP) {
+    if (h.sizes[0] == 0) return nullptr;
+    const size_t n = size_t(h.n_target), cap = size_t(h.u[0]), nvox = size_t(h.u[3]);
+    if (h.u[1] != h.n_target || cap < 1024 || (cap & (cap - 1)) || cap > (size_t(1) << 33)) return "VGICP hash capacity inconsistent";
+    if (h.sizes[0] != n * sizeof(float4) || h.sizes[1] != size_t(kKnnLevels) * cap * sizeof(uint4) || h.sizes[2] != n * 6 * sizeof(double))
+      return "VGICP kNN sections do not match n_target";
+    if (nvox) {
+      if (h.u[2] == 0 || h.u[2] > (1ull << 29)) return "VGICP voxel grid too large";
+      long long nc = 1;
+      for (int a = 0; a < 3; a++) { if (h.i[4 + a] <= 0) return "VGICP voxel grid inconsistent"; nc *= h.i[4 + a]; }
+      if ((unsigned long long)nc != h.u[2]) return "VGICP voxel grid inconsistent";
+      if (h.sizes[3] != nvox * sizeof(VoxelRec) || h.sizes[4] != nvox * sizeof(int32_t) || h.sizes[5] != size_t(h.u[2]) * sizeof(int32_t))
+        return "VGICP voxel sections do not match the voxel count / grid";
+    }
+  } else {
+    return "unknown method";
+  }
+  return nullptr;
+}
 size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct Section { const void* src; void* dst_holder; size_t bytes; };
@@ -614,6 +761,7 @@ int collect_sections(pcr_ctx* c, BlobHeader& h, const void* ptrs[8]) {
   h.magic = kMagic;
   h.method = c->prm.method;
   h.n_target = c->n_target;
+  h.params_hash = params_hash(c->prm);
   for (int k = 0; k < 8; k++) ptrs[k] = nullptr;
   switch (c->prm.method) {
     case PCR_LOAM:
@@ -710,7 +858,10 @@ extern "C" int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes)
   if (!dev_blob || bytes < sizeof(BlobHeader)) return fail(c, PCR_ERR_INVALID, "bad blob");
   BlobHeader h;
   PCR_CUDA_CHECK(cudaMemcpy(&h, dev_blob, sizeof(h), cudaMemcpyDeviceToHost));
-  if (h.magic != kMagic || h.method != c->prm.method) return fail(c, PCR_ERR_INVALID, "blob does not match this context's method");
+  if (h.magic != kMagic) return fail(c, PCR_ERR_INVALID, "not a target index blob of this library version");
+  if (h.method != c->prm.method) return fail(c, PCR_ERR_INVALID, "blob does not match this context's method");
+  if (h.params_hash != params_hash(c->prm)) return fail(c, PCR_ERR_INVALID, "index was built with other parameters than this context's");
+  if (const char* why = validate_blob(h, bytes)) return fail(c, PCR_ERR_INVALID, why);
   const unsigned char* base = static_cast<const unsigned char*>(dev_blob);
   size_t off = align256(sizeof(BlobHeader));
   auto take = [&](void* dst, int k) {
@@ -913,7 +1064,7 @@ extern "C" int pcr_multi_batch_align(pcr_multi* m, const void* src, const size_t
 // ---- on-disk index cache + PCD reader -----------------------------------------------------------
 namespace {
 struct FileHeader {
-  char magic[8];       // "PCRIDX01"
+  char magic[8];       // "PCRIDX02"
   uint64_t blob_bytes;
 };
 }  // namespace
@@ -933,7 +1084,7 @@ extern "C" int pcr_target_save(pcr_ctx* c, const char* path) {
   FILE* f = std::fopen(path, "wb");
   if (!f) return fail(c, PCR_ERR_INVALID, "cannot open index file for writing");
   FileHeader h;
-  std::memcpy(h.magic, "PCRIDX01", 8);
+  std::memcpy(h.magic, "PCRIDX02", 8);
   h.blob_bytes = bytes;
   const bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(host.data(), 1, bytes, f) == bytes;
   std::fclose(f);
@@ -948,7 +1099,14 @@ extern "C" int pcr_target_load(pcr_ctx* c, const char* path) {
   FILE* f = std::fopen(path, "rb");
   if (!f) return fail(c, PCR_ERR_INVALID, "cannot open index file");
   FileHeader h;
-  if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "PCRIDX01", 8) != 0) { std::fclose(f); return fail(c, PCR_ERR_INVALID, "not an index file"); }
+  if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, "PCRIDX02", 8) != 0) { std::fclose(f); return fail(c, PCR_ERR_INVALID, "not an index file"); }
+  std::fseek(f, 0, SEEK_END);
+  const long fsize = std::ftell(f);
+  std::fseek(f, long(sizeof(h)), SEEK_SET);
+  if (fsize < 0 || h.blob_bytes < sizeof(BlobHeader) || h.blob_bytes > size_t(fsize) - sizeof(h)) {
+    std::fclose(f);
+    return fail(c, PCR_ERR_INVALID, "truncated index file");
+  }
   unsigned char* host = c->pin.ensure(h.blob_bytes);
   const bool ok = std::fread(host, 1, h.blob_bytes, f) == h.blob_bytes;
   std::fclose(f);
@@ -1209,6 +1367,7 @@ extern "C" int pcr_gicp_covariances(pcr_ctx* c, const void* pts, size_t n, size_
   c->has_last = false;
   MortonGrid& grid = c->vgd.src_grid;
   int rc = build_morton_grid(d, n, grid, c->bw, c->stream);
+  if (rc == kRetryNonFinite) return fail(c, PCR_ERR_INVALID, "cloud holds NaN / Inf records (per-point outputs would not line up): strip them first");
   if (rc) return fail(c, rc, "grid too large");
   c->vgd.src_covs.ensure(n * 6);
   int32_t* dk = c->vgd.knn_dbg.ensure(n * size_t(k));
@@ -1271,6 +1430,7 @@ extern "C" int pcr_vgicp_evaluate(pcr_ctx* c, const void* src, size_t ns, size_t
   const float4* d = upload_points(c, src, ns, stride, c->raw_src, c->src);
   c->has_last = false;  // c->src no longer holds the last aligned scan (getFitnessScore needs a new scan2Map)
   int rc = c->vgd.compute_source_covs(d, ns, c->prm.vgicp_k, c->ks, c->bw, c->stream);
+  if (rc == kRetryNonFinite) return fail(c, PCR_ERR_INVALID, "source cloud holds NaN / Inf records: strip them first");
   if (rc) return fail(c, rc, "source covariance build failed");
   uint32_t* ho = c->vgd.h_offsets.ensure(2);
   ho[0] = 0; ho[1] = uint32_t(ns);

@@ -65,6 +65,7 @@ int build_morton_grid(const float4* pts, size_t n, MortonGrid& grid, BBoxWork& b
   if (n == 0) return 0;
   float mn[3], mx[3];
   bbox_blocking(pts, n, mn, mx, bw, s);
+  if (bw.n_nonfinite) return kRetryNonFinite;
   double m = 1.0;
   for (int a = 0; a < 3; a++) {
     grid.mn[a] = mn[a];

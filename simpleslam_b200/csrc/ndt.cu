@@ -122,6 +122,7 @@ int ndt_build_target(const float4* pts, size_t n, const pcr_params& prm, NdtTarg
   if (n == 0) { tgt.overflow = true; tgt.built = true; return 0; }
   float mn[3], mx[3];
   bbox_blocking(pts, n, mn, mx, bw, s);
+  if (bw.n_nonfinite) return kRetryNonFinite;
   if (!make_grid_spec(mn, mx, prm.ndt_resolution, tgt.g)) {  // :79-84 leaf size too small -> no leaves
     tgt.overflow = true;
     tgt.built = true;
@@ -323,8 +324,13 @@ __global__ void __launch_bounds__(kNdtBlock, DOUBLE_PATH ? 2 : 5)
 ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, NdtTargetView tgt, NdtScanState* __restrict__ states,
                  NdtScanOut* __restrict__ outs, int32_t* __restrict__ float_round, int32_t* __restrict__ hess_round, int n_scans, int round,
                  int step, NdtCfg cfg, double* __restrict__ partials, unsigned* __restrict__ tickets, NdtProgress* progress,
-                 NdtCounters* __restrict__ counters) {
+                 NdtCounters* __restrict__ counters, int* __restrict__ round_flags) {
   constexpr int NNB = NbTraits<SEARCH>::N;
+  // round_flags[r]: bit 0 = some scan wants a float evaluation in round r, bit 1 = a double-path Hessian. Written only by
+  // tails of EARLIER kernels (or, for bit 1 of this round, by the float kernel that has completed): a launch without
+  // work returns at once (most double-path launches, and the rounds queued past the end of the registration)
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !DOUBLE_PATH && progress) progress->round = round;
+  if (step && !(round_flags[round] & (DOUBLE_PATH ? 2 : 1))) return;
   __shared__ __align__(16) NdtScanState s_state;
   __shared__ double sacc[kNdtNV * kNdtBlock];
   __shared__ double s_tot[kNdtNV + 1];
@@ -356,10 +362,7 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
   int pos = base + incl - cnt;
   for (int k = lo; k < hi; k++)
     if (stamps[k] == round) s_list[pos++] = (unsigned short)k;
-  if (blockIdx.x == 0 && tid == 0) {
-    if (!DOUBLE_PATH && progress) progress->round = round;
-    if (n_active > 0) atomicAdd(&counters->work_launches, 1);
-  }
+  if (blockIdx.x == 0 && tid == 0 && n_active > 0) atomicAdd(&counters->work_launches, 1);
   if (n_active == 0) return;
   __syncthreads();
 
@@ -517,8 +520,8 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
       const uint4* sp4 = reinterpret_cast<const uint4*>(&s_state);
       for (int k = tid; k < nwords; k += kNdtBlock) gp[k] = sp4[k];
       if (tid == 0) {
-        if (s_state.pend == NDT_PEND_FLOAT) float_round[scan] = round + 1;
-        else if (s_state.pend == NDT_PEND_DOUBLE) hess_round[scan] = round;  // served by the double-path kernel of this round
+        if (s_state.pend == NDT_PEND_FLOAT) { float_round[scan] = round + 1; atomicOr(round_flags + round + 1, 1); }
+        else if (s_state.pend == NDT_PEND_DOUBLE) { hess_round[scan] = round; atomicOr(round_flags + round, 2); }  // served by the double-path kernel of this round
       }
       if (s_state.pend == NDT_PEND_NONE) {
         NdtScanOut* o = outs + scan;
@@ -539,7 +542,7 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
 // empty target evaluate to all-zero sums (no block would contribute), which the state machine digests right here.
 __global__ void ndt_init_kernel(const double* __restrict__ guesses, const uint32_t* __restrict__ offs, NdtScanState* __restrict__ states,
                                 NdtScanOut* __restrict__ outs, int32_t* __restrict__ float_round, int32_t* __restrict__ hess_round, int n_scans,
-                                int no_target, NdtCfg cfg, NdtProgress* progress, NdtCounters* __restrict__ counters) {
+                                int no_target, NdtCfg cfg, NdtProgress* progress, NdtCounters* __restrict__ counters, int* __restrict__ round_flags) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_scans) return;
   NdtScanState st;
@@ -561,6 +564,7 @@ __global__ void ndt_init_kernel(const double* __restrict__ guesses, const uint32
     if (f == n_scans && progress) { __threadfence_system(); progress->all_done = 1; }
   } else {
     float_round[s] = 0;
+    atomicOr(round_flags, 1);
   }
 }
 
@@ -584,6 +588,8 @@ void NdtDriver::prepare(size_t n_scans, int grid_blocks, cudaStream_t s) {
     PCR_CUDA_CHECK(cudaMemsetAsync(tickets.p, 0, tickets.cap * sizeof(unsigned), s));
   }
   PCR_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, sizeof(NdtCounters), s));
+  round_flags.ensure(size_t(max_rounds_cap) + 2);
+  PCR_CUDA_CHECK(cudaMemsetAsync(round_flags.p, 0, (size_t(max_rounds_cap) + 2) * sizeof(int), s));
   progress->round = -1;
   progress->all_done = 0;
 }
@@ -600,11 +606,11 @@ static NdtTargetView make_view(const NdtTarget& tgt) {
 template <int SEARCH>
 static void launch_round_t(bool dbl, int grid, cudaStream_t s, const float4* src, const uint32_t* offs, const NdtTargetView& v, NdtScanState* states,
                            NdtScanOut* outs, int32_t* fr, int32_t* hr, int n, int round, int step, const NdtCfg& cfg, double* partials,
-                           unsigned* tickets, NdtProgress* prog, NdtCounters* cnt) {
-  if (dbl)
-    ndt_round_kernel<SEARCH, true><<<grid, kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt);
+                           unsigned* tickets, NdtProgress* prog, NdtCounters* cnt, int* flags) {
+  if (dbl)  // 218 registers: two blocks per SM, one resident wave
+    ndt_round_kernel<SEARCH, true><<<std::min(grid, kNumSMs * 2), kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt, flags);
   else
-    ndt_round_kernel<SEARCH, false><<<grid, kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt);
+    ndt_round_kernel<SEARCH, false><<<grid, kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt, flags);
 }
 
 void NdtDriver::launch_round(const float4* src, const NdtTarget& tgt, int search, int n, int round, int step, const NdtCfg& cfg, int grid_blocks,
@@ -618,10 +624,10 @@ void NdtDriver::launch_round(const float4* src, const NdtTarget& tgt, int search
     if (part == 0 ? !float_kernel : !double_kernel) continue;
     const bool dbl = part == 1;
     switch (search) {
-      case PCR_NDT_DIRECT1: launch_round_t<PCR_NDT_DIRECT1>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p); break;
-      case PCR_NDT_DIRECT26: launch_round_t<PCR_NDT_DIRECT26>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p); break;
-      case PCR_NDT_KDTREE: launch_round_t<PCR_NDT_KDTREE>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p); break;
-      default: launch_round_t<PCR_NDT_DIRECT7>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p); break;
+      case PCR_NDT_DIRECT1: launch_round_t<PCR_NDT_DIRECT1>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p); break;
+      case PCR_NDT_DIRECT26: launch_round_t<PCR_NDT_DIRECT26>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p); break;
+      case PCR_NDT_KDTREE: launch_round_t<PCR_NDT_KDTREE>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p); break;
+      default: launch_round_t<PCR_NDT_DIRECT7>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p); break;
     }
     launches++;
   }
@@ -680,7 +686,7 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
   const int no_target = (tgt.overflow || tgt.nleaves == 0) ? 1 : 0;
   static const int lookahead = [] { const char* v = std::getenv("PCR_NDT_LOOKAHEAD"); return v ? std::max(1, std::atoi(v)) : 3; }();
   // every outer iteration costs at most 1 + kMaxStepIterations float evaluations (+ 1 double-path Hessian in the same round)
-  const int max_rounds = (prm.ndt_max_iters + 3) * (ndt_logic::kMaxStepIterations + 2) + 2;
+  const int max_rounds = std::min((prm.ndt_max_iters + 3) * (ndt_logic::kMaxStepIterations + 2) + 2, max_rounds_cap);
   if (profile && !ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
 
   for (size_t c0 = 0; c0 < n_scans; c0 += kNdtMaxBatch) {  // chunks of scans (request list size); normally a single chunk
@@ -700,7 +706,7 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
     NdtProgress* dprog = nullptr;
     PCR_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dprog), progress, 0));
     ndt_init_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(guesses.p, offsets.p, states.p, outs.p, stamps.p, stamps.p + n, int(n), no_target, cfg,
-                                                              dprog, counters.p);
+                                                              dprog, counters.p, round_flags.p);
     launches++;
     if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
     int r = 0;

@@ -62,6 +62,8 @@ struct NdtDriver {
   DevBuf<uint32_t> offsets;
   DevBuf<double> guesses;
   DevBuf<NdtCounters> counters;
+  DevBuf<int> round_flags;  // per round: which kinds of evaluation are wanted (lets idle launches return at once)
+  static constexpr int max_rounds_cap = 4096;
   PinBuf<NdtScanOut> h_outs;
   PinBuf<NdtScanState> h_state;
   PinBuf<uint32_t> h_offsets;

@@ -7,6 +7,7 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <cub/device/device_scan.cuh>
 #include <thrust/iterator/reverse_iterator.h>
+#include <cfloat>
 #include <cmath>
 #include <limits>
 
@@ -62,8 +63,10 @@ void write_xyzi32(const float4* pts, size_t n, void* dev_out32, cudaStream_t s) 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ pts, size_t n, unsigned* __restrict__ out) {
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  unsigned bad = 0;
   for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
     float4 p = __ldg(pts + i);
+    if (!(fabsf(p.x) <= FLT_MAX && fabsf(p.y) <= FLT_MAX && fabsf(p.z) <= FLT_MAX)) { bad++; continue; }  // NaN / Inf: not part of the box
     mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
     mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
     mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
@@ -76,8 +79,10 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ pt
       mx[a] = fmaxf(mx[a], __shfl_down_sync(0xffffffffu, mx[a], o));
     }
   }
+  bad = __reduce_add_sync(0xffffffffu, bad);
   __shared__ float smn[8][3], smx[8][3];
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0 && bad) atomicAdd(out + 6, bad);
   if (lane == 0)
     for (int a = 0; a < 3; a++) { smn[warp][a] = mn[a]; smx[warp][a] = mx[a]; }
   __syncthreads();
@@ -91,16 +96,57 @@ __global__ void __launch_bounds__(256) bbox_kernel(const float4* __restrict__ pt
 }
 
 void bbox_blocking(const float4* pts, size_t n, float mn[3], float mx[3], BBoxWork& w, cudaStream_t s) {
-  unsigned* d = w.d.ensure(6);
-  unsigned* h = w.h.ensure(6);
+  unsigned* d = w.d.ensure(8);
+  unsigned* h = w.h.ensure(8);
   h[0] = h[1] = h[2] = 0xffffffffu;
   h[3] = h[4] = h[5] = 0u;
-  PCR_CUDA_CHECK(cudaMemcpyAsync(d, h, 6 * sizeof(unsigned), cudaMemcpyHostToDevice, s));
+  h[6] = h[7] = 0u;
+  PCR_CUDA_CHECK(cudaMemcpyAsync(d, h, 8 * sizeof(unsigned), cudaMemcpyHostToDevice, s));
   unsigned blocks = unsigned(std::min<size_t>((n + 255) / 256, size_t(kNumSMs) * 8));
   bbox_kernel<<<blocks, 256, 0, s>>>(pts, n, d);
-  PCR_CUDA_CHECK(cudaMemcpyAsync(h, d, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  PCR_CUDA_CHECK(cudaMemcpyAsync(h, d, 8 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
   PCR_CUDA_CHECK(cudaStreamSynchronize(s));
+  w.n_nonfinite = h[6];
   for (int a = 0; a < 3; a++) { mn[a] = dec_f32(h[a]); mx[a] = dec_f32(h[3 + a]); }
+  if (w.n_nonfinite == n)  // nothing finite: an empty box at the origin
+    for (int a = 0; a < 3; a++) mn[a] = mx[a] = 0.f;
+}
+
+struct FinitePred {
+  const float4* pts;
+  __device__ __forceinline__ bool operator()(const uint32_t& i) const {
+    const float4 p = pts[i];
+    return fabsf(p.x) <= FLT_MAX && fabsf(p.y) <= FLT_MAX && fabsf(p.z) <= FLT_MAX;
+  }
+};
+__global__ void __launch_bounds__(256) gather_idx_kernel(const float4* __restrict__ pts, const uint32_t* __restrict__ idx, size_t m, float4* __restrict__ out) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < m) out[i] = pts[idx[i]];
+}
+
+size_t drop_nonfinite(float4* pts, size_t n, DevBuf<float4>& scratch, DevBuf<unsigned char>& tmp, DevBuf<unsigned>& d_count, PinBuf<unsigned>& h_count,
+                      cudaStream_t s) {
+  if (n == 0) return 0;
+  // scratch: [n indices of the finite records | their records]
+  scratch.ensure(n + (n + 3) / 4 + 1);
+  uint32_t* idx = reinterpret_cast<uint32_t*>(scratch.p);
+  float4* kept = scratch.p + (n + 3) / 4;
+  unsigned* dc = d_count.ensure(1);
+  unsigned* hc = h_count.ensure(1);
+  cub::CountingInputIterator<uint32_t> it(0);
+  FinitePred pred{pts};
+  size_t bytes = 0;
+  cub::DeviceSelect::If(nullptr, bytes, it, idx, dc, int(n), pred, s);
+  tmp.ensure(bytes);
+  PCR_CUDA_CHECK(cub::DeviceSelect::If(tmp.p, bytes, it, idx, dc, int(n), pred, s));
+  PCR_CUDA_CHECK(cudaMemcpyAsync(hc, dc, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(s));
+  const size_t m = *hc;
+  if (m) {
+    gather_idx_kernel<<<unsigned((m + 255) / 256), 256, 0, s>>>(pts, idx, m, kept);
+    PCR_CUDA_CHECK(cudaMemcpyAsync(pts, kept, m * sizeof(float4), cudaMemcpyDeviceToDevice, s));
+  }
+  return m;
 }
 
 bool make_grid_spec(const float mn[3], const float mx[3], float leaf, GridSpec& g) {
@@ -305,6 +351,7 @@ int build_cell_grid(const float4* pts, size_t n, float cell, CellGrid& grid, Key
   if (n == 0) return 0;
   float mn[3], mx[3];
   bbox_blocking(pts, n, mn, mx, bw, s);
+  if (bw.n_nonfinite) return kRetryNonFinite;
   bool ok = make_grid_spec(mn, mx, cell, grid.g);
   if (!ok || grid.g.ncell > (1ll << 29)) return -5;
   ks.sort(pts, n, grid.g, s);

@@ -8,9 +8,16 @@ namespace pcr {
 void pack_points(const void* dev_raw, size_t n, size_t stride, float4* out, cudaStream_t s);
 void write_xyzi32(const float4* pts, size_t n, void* dev_out32, cudaStream_t s);
 
-// Bounding box (blocking: returns host values). n must be > 0.
-struct BBoxWork { DevBuf<unsigned> d; PinBuf<unsigned> h; };
+// Bounding box over the FINITE points (blocking: returns host values). n must be > 0. w.n_nonfinite = records with a NaN / Inf
+// coordinate (the reference strips them before a register sees a cloud, dataproxy/src/LidarDataProxy.cpp:47, and
+// pcl::VoxelGrid / VoxelGridCovariance skip them): index builds answer kRetryNonFinite so that the API layer compacts
+// the context-owned copy of the cloud (drop_nonfinite) and builds again.
+struct BBoxWork { DevBuf<unsigned> d; PinBuf<unsigned> h; size_t n_nonfinite = 0; };
 void bbox_blocking(const float4* pts, size_t n, float mn[3], float mx[3], BBoxWork& w, cudaStream_t s);
+constexpr int kRetryNonFinite = -100;  // internal: never crosses the C ABI
+// order-preserving removal of records with a non-finite coordinate, in place (blocking). Returns the new count.
+size_t drop_nonfinite(float4* pts, size_t n, DevBuf<float4>& scratch, DevBuf<unsigned char>& tmp, DevBuf<unsigned>& d_count, PinBuf<unsigned>& h_count,
+                      cudaStream_t s);
 
 // PCL VoxelGrid grid parameters from a bounding box (pcp.hpp:191-200; voxel_grid_covariance_omp_impl.hpp:75-103).
 // Returns false when dx*dy*dz overflows int32 (PCL's "leaf size too small").

@@ -123,7 +123,7 @@ class MapManager:
         idx = [int(i) for i in np.nonzero(d2 < SUBMAP_RADIUS * SUBMAP_RADIUS)[0]]  # nanoflann radius search: d2 < r^2
         self.submap_idx = idx
         _, self.submap_size = self.ctx.submap_build([self.keyframes[i][0] for i in idx], [self.keyframes[i][1] for i in idx], self.grid_size,
-                                                    want_points=False)
+                                                    want_points=False, ids=idx)  # device copies cached by keyframe index (LRU-bounded)
         self.n_updates += 1
 
 
@@ -211,7 +211,7 @@ class LoopClosureVerifier:
     def verify(self, old_key, cur_key):
         n = len(self.keyframes)
         near = [k for k in range(old_key - self.range, old_key + self.range + 1) if 0 <= k < n]
-        _, m = self.ctx.submap_build([self.keyframes[k][0] for k in near], [self.keyframes[k][1] for k in near], self.ds, want_points=False)
+        _, m = self.ctx.submap_build([self.keyframes[k][0] for k in near], [self.keyframes[k][1] for k in near], self.ds, want_points=False, ids=near)
         cloud, pose = self.keyframes[cur_key]
         T, conv = self.ctx.align(cloud, pose)
         fs = self.ctx.fitness()
