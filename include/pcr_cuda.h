@@ -93,6 +93,11 @@ typedef struct pcr_stats {
   float ms_hot_kernel;       /* summed device time of the dominant correspondence/accumulation kernel */
   int32_t hot_kernel_launches;
   int32_t pad;
+  /* second kernel worth a line of its own — VGICP: gicp_knn_kernel (exact k-NN behind the source / target covariances, the
+   * largest share of a scan-to-scan registration); 0 for LOAM / NDT */
+  float ms_aux_kernel;
+  int32_t aux_kernel_launches;
+  int64_t n_aux_items;        /* VGICP: k-NN queries answered */
 } pcr_stats;
 
 void pcr_default_params(int32_t method, pcr_params* p);

@@ -50,6 +50,7 @@ class Stats(ctypes.Structure):
         ("n_index_reads", ctypes.c_int64),
         ("score", ctypes.c_double), ("ms_total", ctypes.c_float), ("ms_hot_kernel", ctypes.c_float),
         ("hot_kernel_launches", ctypes.c_int32), ("pad", ctypes.c_int32),
+        ("ms_aux_kernel", ctypes.c_float), ("aux_kernel_launches", ctypes.c_int32), ("n_aux_items", ctypes.c_int64),
     ]
 
     def as_dict(self):

@@ -66,6 +66,8 @@ struct pcr_ctx {
   DevBuf<unsigned char> sub_meta;
   PinBuf<unsigned char> sub_meta_h;
 
+  KnnProfile knn_prof;  // VGICP k-NN kernel timing while profiling is on (target build + source covariances)
+
   // VGICP: last registration (for getFitnessScore)
   size_t last_ns = 0, last_off = 0;
   double last_T[16];
@@ -192,6 +194,9 @@ extern "C" int pcr_vgicp_init_for_lc(pcr_ctx* c) {
 extern "C" int pcr_set_profiling(pcr_ctx* c, int enable) {
   if (!c) return PCR_ERR_INVALID;
   c->profiling = enable != 0;
+  c->vg.prof = c->profiling ? &c->knn_prof : nullptr;
+  c->vgd.prof = c->vg.prof;
+  c->knn_prof.reset();
   return PCR_OK;
 }
 
@@ -336,6 +341,14 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
       st.n_index_reads = st.n_point_evals;
       st.ms_hot_kernel = hot;
       st.hot_kernel_launches = hotl;
+      if (c->profiling) {  // k-NN kernel time since the last align: the target build of this registration + the source scans
+        PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->knn_prof.collect();
+        st.ms_aux_kernel = c->knn_prof.ms;
+        st.aux_kernel_launches = c->knn_prof.launches;
+        st.n_aux_items = c->knn_prof.queries;
+        c->knn_prof.reset();
+      }
       // remember the last scan for getFitnessScore (pcl keeps input_ + final_transformation_)
       c->has_last = false;
       if (rc == 0) {

@@ -97,17 +97,48 @@ __device__ __forceinline__ float dist2_f32(float qx, float qy, float qz, const f
 }
 
 struct WarpKnn {
-  float bd;   // this lane's entry of the sorted result (lane < k), +inf when empty
+  float bd;   // this lane's entry of the result (lane < k), +inf when empty. UNSORTED while a search runs: knn_sort_result
   int bi;
-  float td;   // current k-th best (threshold), warp-uniform
+  float td;   // current k-th best = the largest kept entry (threshold), +inf while fewer than k are kept; warp-uniform
   int ti;
+  int tl;     // lane that holds the threshold entry
   int cnt;    // entries found so far (<= k), warp-uniform
 };
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// scan the contiguous run [lo, hi) of the sorted array: lane l holds the l-th best so far; candidates are read coalesced
-// (one float4 per lane) and those beating the current k-th are inserted with ballot / shuffle-up
+// largest kept entry by (d2, index): two hardware redux.sync max + one ballot (d2 >= 0: float bits order like unsigned)
+__device__ __forceinline__ void knn_refresh_threshold(WarpKnn& st, int k, int lane) {
+  const unsigned kh = lane < k ? __float_as_uint(st.bd) : 0u;
+  const unsigned mh = __reduce_max_sync(kFull, kh);
+  const bool e1 = lane < k && kh == mh;
+  const unsigned ml = __reduce_max_sync(kFull, e1 ? unsigned(st.bi) : 0u);
+  st.tl = __ffs(__ballot_sync(kFull, e1 && unsigned(st.bi) == ml)) - 1;
+  st.td = __uint_as_float(mh);
+  st.ti = int(ml);
+}
+
+// ascending (d2, index) order over the lanes (empty lanes = +inf sort to the end): warp bitonic network, 15 shuffle steps
+__device__ __forceinline__ void knn_bitonic_sort(float& d, int& id, int lane) {
+#pragma unroll
+  for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+      const float od = __shfl_xor_sync(kFull, d, jj);
+      const int oi = __shfl_xor_sync(kFull, id, jj);
+      const bool keep_min = ((lane & jj) == 0) == ((lane & kk) == 0);
+      const bool other_less = od < d || (od == d && oi < id);
+      const bool other_more = od > d || (od == d && oi > id);
+      if (keep_min ? other_less : other_more) { d = od; id = oi; }
+    }
+  }
+}
+__device__ __forceinline__ void knn_sort_result(WarpKnn& st, int lane) { knn_bitonic_sort(st.bd, st.bi, lane); }
+
+// scan the contiguous run [lo, hi) of the sorted array: candidates are read coalesced (one float4 per lane). The kept set
+// lives UNSORTED in the lanes (lane < k): a candidate that beats the threshold replaces the largest kept entry and the new
+// largest is found with redux.sync — ~15 warp instructions per accepted candidate instead of a ballot / shuffle-up sorted
+// insertion (~28). The (d2, index) order is total, so the kept SET is the same whatever the arrival order.
 __device__ __forceinline__ void knn_scan_run(WarpKnn& st, const float4* __restrict__ pts, int lo, int hi, float qx, float qy, float qz,
                                              int k, int lane) {
   for (int base = lo; base < hi; base += 32) {
@@ -123,51 +154,49 @@ __device__ __forceinline__ void knn_scan_run(WarpKnn& st, const float4* __restri
     }
     if (st.cnt == 0) {
       // first chunk of a search: the list is empty, so instead of up to 32 serial insertions sort the chunk with a warp
-      // bitonic network on (d2, index) and adopt its k smallest (15 shuffle steps)
+      // bitonic network on (d2, index) and adopt its k smallest
       float d = j < hi ? d2 : INFINITY;
       int id = j < hi ? idx : 0x7fffffff;
-#pragma unroll
-      for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-          const float od = __shfl_xor_sync(kFull, d, jj);
-          const int oi = __shfl_xor_sync(kFull, id, jj);
-          const bool keep_min = ((lane & jj) == 0) == ((lane & kk) == 0);
-          const bool other_less = od < d || (od == d && oi < id);
-          const bool other_more = od > d || (od == d && oi > id);
-          if (keep_min ? other_less : other_more) { d = od; id = oi; }
-        }
-      }
+      knn_bitonic_sort(d, id, lane);
       const int valid = min(hi - base, 32);
       st.cnt = min(k, valid);
       st.bd = lane < st.cnt ? d : INFINITY;
       st.bi = lane < st.cnt ? id : 0x7fffffff;
-      st.td = __shfl_sync(kFull, st.bd, k - 1);
+      st.td = __shfl_sync(kFull, st.bd, k - 1);   // +inf while fewer than k are kept
       st.ti = __shfl_sync(kFull, st.bi, k - 1);
+      st.tl = k - 1;
       continue;
     }
     unsigned mask = __ballot_sync(kFull, pass);
+    if (mask == 0u) continue;
+    if (st.cnt < k) {
+      // empty slots left: lane cnt + r adopts the r-th passing candidate directly
+      const int m = min(k - st.cnt, __popc(mask));
+      const int want = lane - st.cnt;
+      const bool take = want >= 0 && want < m;
+      const int srcl = take ? int(__fns(mask, 0, want + 1)) : 0;
+      const float sd = __shfl_sync(kFull, d2, srcl);
+      const int si = __shfl_sync(kFull, idx, srcl);
+      if (take) { st.bd = sd; st.bi = si; }
+      st.cnt += m;
+      const int rank = __popc(mask & ((1u << lane) - 1u));
+      mask = __ballot_sync(kFull, pass && rank >= m);  // the candidates that did not find an empty slot
+      if (st.cnt == k) knn_refresh_threshold(st, k, lane);
+    }
     while (mask) {
       const int s = __ffs(mask) - 1;
       mask &= mask - 1;
       const float cd = __shfl_sync(kFull, d2, s);
       const int ci = __shfl_sync(kFull, idx, s);
       if (!(cd < st.td || (cd == st.td && ci < st.ti))) continue;  // the threshold moved since the ballot
-      const bool less = st.bd < cd || (st.bd == cd && st.bi < ci);
-      const int pos = __popc(__ballot_sync(kFull, less && lane < k));
-      const float ud = __shfl_up_sync(kFull, st.bd, 1);
-      const int ui = __shfl_up_sync(kFull, st.bi, 1);
-      if (lane == pos) { st.bd = cd; st.bi = ci; }
-      else if (lane > pos && lane < k) { st.bd = ud; st.bi = ui; }
-      if (st.cnt < k) st.cnt++;
-      st.td = __shfl_sync(kFull, st.bd, k - 1);
-      st.ti = __shfl_sync(kFull, st.bi, k - 1);
+      if (lane == st.tl) { st.bd = cd; st.bi = ci; }
+      knn_refresh_threshold(st, k, lane);
     }
   }
 }
 
 __device__ __forceinline__ void knn_reset(WarpKnn& st) {
-  st.bd = INFINITY; st.bi = 0x7fffffff; st.td = INFINITY; st.ti = 0x7fffffff; st.cnt = 0;
+  st.bd = INFINITY; st.bi = 0x7fffffff; st.td = INFINITY; st.ti = 0x7fffffff; st.tl = 0; st.cnt = 0;
 }
 
 // the 27 cells of a level, nearest first: centre, 6 faces, 12 edges, 8 corners; packed (dx+1) | (dy+1)<<2 | (dz+1)<<4
@@ -177,7 +206,7 @@ static __constant__ unsigned char c_knn_nb[27] = {
     42, 40, 34, 32, 10, 8, 2, 0};                           // corners
 
 // Warp-cooperative exact k-NN. `min_pop`: own-cell population that selects the starting level.
-// On return lanes [0, cnt) hold the neighbours in ascending (d2, idx) order.
+// On return lanes [0, k) hold the cnt neighbours UNSORTED (empty lanes +inf); knn_sort_result orders them by (d2, idx).
 __device__ __forceinline__ WarpKnn knn_warp_morton(const MortonView& g, float qx, float qy, float qz, int k, int min_pop, int lane) {
   WarpKnn st;
   knn_reset(st);

@@ -51,7 +51,7 @@ __constant__ signed char c_row_dz[25] = {0, 0, 0, 1, -1, 1, -1, 1, -1, 0, 0, 2, 
 constexpr int kModeFused = 0, kModeSearch = 1, kModeFit = 2;
 
 template <int LPQ, bool DEBUG, int MODE>
-__global__ void __launch_bounds__(kLoamBlock, MODE == kModeSearch ? 4 : 2)
+__global__ void __launch_bounds__(kLoamBlock, MODE == kModeSearch ? 4 : (MODE == kModeFit ? 3 : 2))
 loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, GridView grid, LoamParams prm,
                  LoamState* __restrict__ states, double* __restrict__ partials, int max_blocks,
                  pcr_loam_iter_log* __restrict__ logs, int apply_update, int tile, double slack, int max_ring,
@@ -557,7 +557,7 @@ __device__ __noinline__ void exact_search_one(const GridView& grid, float qf0, f
 
 __global__ void __launch_bounds__(kLoamBlock, 4)
 loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, GridView grid, LoamParams prm,
-                   const LoamState* __restrict__ states, double slack, int max_ring, int32_t* __restrict__ knn_buf, size_t knn_stride) {
+                   const LoamState* __restrict__ states, double slack, int max_ring, int32_t* __restrict__ knn_buf, size_t knn_stride, int warm) {
   const int scan = blockIdx.y;
   const uint32_t begin = offs[scan], end = offs[scan + 1];
   const LoamState* st = states + scan;
@@ -598,6 +598,7 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
         const float ax = qf0 - m.x, ay = qf1 - m.y, az = qf2 - m.z;
         const float f = fmaf(az, az, fmaf(ay, ay, ax * ax));
         if (f <= thr) {
+          if (j == bj[0] || j == bj[1] || j == bj[2] || j == bj[3] || j == bj[4]) return;  // already kept (warm start)
           if (f < bf[4]) {  // branch-free sorted insertion; the old 5th drops out
             f_out = fminf(f_out, bf[4]);
             const bool p3 = f < bf[3], p2 = f < bf[2], p1 = f < bf[1], p0 = f < bf[0];
@@ -612,6 +613,17 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
           }
         }
       };
+      if (warm) {
+        // the five winners of the previous Gauss-Newton iteration (the pose moved a little): with them the bound starts at
+        // about the true 5th distance, so most rows are pruned before their table entries are even read. They are ordinary
+        // candidates — the kept set, its exactness test and the fallback are unaffected by where candidates come from.
+        int pj[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) pj[k] = knn_buf[size_t(k) * knn_stride + i];
+#pragma unroll
+        for (int k = 0; k < 5; k++)
+          if (pj[k] >= 0) { consider(__ldg(grid.pts + pj[k]), pj[k]); ncand++; }
+      }
 #pragma unroll 1
       for (int k = 0; k < NR; k++) {
         if (k >= 9 && thr < q.ring2_min2) break;
@@ -800,6 +812,11 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
   const size_t per_block = size_t(kLoamWarps) * tile;
   int max_blocks = int((max_pts + per_block - 1) / per_block);
   max_blocks = std::max(1, std::min(max_blocks, int(size_t(kNumSMs) * 2 / n_scans)));  // all scans' blocks resident in one wave
+  // large batches (one lane per query, full tiles): search and fit as two kernels per iteration, see kModeSearch
+  const bool split = lpq == 1 && tile == 32 && env_int("PCR_LOAM_SPLIT", 1) != 0;
+  // the fit kernel is a long dependent FP64 chain per query (pivoted QR: ~9 us): one query per thread over as many blocks
+  // as it takes, instead of a single resident wave in which every thread walks through a dozen queries one after the other
+  if (split) max_blocks = std::max(1, int((max_pts + per_block - 1) / per_block));
   states.ensure(n_scans);
   offsets.ensure(n_scans + 1);
   partials.ensure(n_scans * size_t(max_blocks) * kNV);
@@ -812,8 +829,6 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     if (!ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
     PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
   }
-  // large batches (one lane per query, full tiles): search and fit as two kernels per iteration, see kModeSearch
-  const bool split = lpq == 1 && tile == 32 && env_int("PCR_LOAM_SPLIT", 1) != 0;
   last_lpq = lpq; last_tile = tile; last_split = split;
   if (grid.built && grid.has_start && max_pts > 0) {
     const float4* q = src;
@@ -826,7 +841,8 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     const dim3 sgrid(unsigned((max_pts + search_pb - 1) / search_pb), unsigned(n_scans));
     for (int it = 0; it < prm.max_iters; it++) {
       if (split) {
-        loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, knn_buf.p, total_q);
+        loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, knn_buf.p, total_q,
+                                                        (it > 0 && env_int("PCR_LOAM_WARM", 1) != 0) ? 1 : 0);
         loam_iter_kernel<1, false, kModeFit><<<gridDim, kLoamBlock, kLoamDynSmem, s>>>(q, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 1,
                                                                                       32, slack, grid.max_ring, nullptr, nullptr, knn_buf.p, total_q, perm);
         launches += 2;
@@ -893,7 +909,7 @@ int LoamDriver::linearize(const float4* src, size_t ns, const CellGrid& grid, co
       const float4* q = sort_queries(src, offsets.p, 1, ns, ns, &perm, s);
       const size_t search_pb = size_t(kLoamWarps) * 32;
       const dim3 sgrid(unsigned((ns + search_pb - 1) / search_pb), 1);
-      loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, knn_buf.p, ns);
+      loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, knn_buf.p, ns, 0);
       loam_iter_kernel<1, true, kModeFit><<<dim3(max_blocks, 1), kLoamBlock, kLoamDynSmem, s>>>(q, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p,
                                                                                                0, 32, slack, grid.max_ring, dbg_knn.p, dbg_status.p, knn_buf.p, ns, perm);
       last_split = true;

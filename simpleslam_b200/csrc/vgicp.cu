@@ -24,7 +24,8 @@ gicp_knn_kernel(size_t n, MortonView grid, int k, int min_pop, int32_t* __restri
   const size_t warps = size_t(gridDim.x) * (blockDim.x >> 5);
   for (size_t i = size_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
     const float4 q = __ldg(grid.pts + i);
-    const WarpKnn st = knn_warp_morton(grid, q.x, q.y, q.z, k, min_pop, lane);
+    WarpKnn st = knn_warp_morton(grid, q.x, q.y, q.z, k, min_pop, lane);
+    knn_sort_result(st, lane);  // ascending (d2, index): the order pcl::search::KdTree::nearestKSearch returns
     const size_t orig = size_t(__float_as_int(q.w));
     if (lane < k) knn_idx[orig * k + lane] = lane < st.cnt ? st.bi : -1;
   }
@@ -75,13 +76,39 @@ gicp_cov_kernel(const float4* __restrict__ pts, size_t n, int k, const int32_t* 
     }
 }
 
+KnnProfile::~KnnProfile() {
+  for (auto& p : pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+}
+void KnnProfile::begin(cudaStream_t s) {
+  cudaEvent_t a = nullptr, b = nullptr;
+  PCR_CUDA_CHECK(cudaEventCreate(&a));
+  PCR_CUDA_CHECK(cudaEventCreate(&b));
+  pending.emplace_back(a, b);
+  PCR_CUDA_CHECK(cudaEventRecord(a, s));
+}
+void KnnProfile::end(cudaStream_t s, size_t n) {
+  PCR_CUDA_CHECK(cudaEventRecord(pending.back().second, s));
+  launches++;
+  queries += (long long)n;
+}
+void KnnProfile::collect() {
+  for (auto& p : pending) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p.first, p.second) == cudaSuccess) ms += t;
+    cudaEventDestroy(p.first); cudaEventDestroy(p.second);
+  }
+  pending.clear();
+}
+
 // knn_idx: device scratch of n*k ints (always needed)
-void gicp_covariances(const float4* pts, size_t n, const MortonGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s) {
+void gicp_covariances(const float4* pts, size_t n, const MortonGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s, KnnProfile* prof) {
   if (n == 0) return;
   const unsigned blocks = unsigned(std::min<size_t>((n + 7) / 8, size_t(kNumSMs) * 64));
   static const int min_pop_env = std::getenv("PCR_KNN_MINPOP") ? std::atoi(std::getenv("PCR_KNN_MINPOP")) : 0;  // tuning knob
   const int min_pop = min_pop_env > 0 ? min_pop_env : std::max(1, (k * 3) / 4);
+  if (prof) prof->begin(s);
   gicp_knn_kernel<<<blocks, 256, 0, s>>>(n, view_of(grid), k, min_pop, knn_idx);
+  if (prof) prof->end(s, n);
   gicp_cov_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(pts, n, k, knn_idx, covs);
 }
 
@@ -160,7 +187,7 @@ int vgicp_build_target(const float4* pts, size_t n, const pcr_params& prm, Vgicp
   if (rc) return rc;
   tgt.covs.ensure(n * 6);
   tgt.knn.ensure(n * size_t(prm.vgicp_k));
-  gicp_covariances(pts, n, tgt.grid, prm.vgicp_k, tgt.covs.p, tgt.knn.p, s);
+  gicp_covariances(pts, n, tgt.grid, prm.vgicp_k, tgt.covs.p, tgt.knn.p, s, tgt.prof);
   // voxel map
   float mn[3], mx[3];
   bbox_blocking(pts, n, mn, mx, bw, s);
@@ -366,7 +393,7 @@ int VgicpDriver::compute_source_covs(const float4* src, size_t ns, int k, KeySor
   if (rc) return rc;
   src_covs.ensure(ns * 6);
   knn_dbg.ensure(ns * size_t(k));
-  gicp_covariances(src, ns, src_grid, k, src_covs.p, knn_dbg.p, s);
+  gicp_covariances(src, ns, src_grid, k, src_covs.p, knn_dbg.p, s, prof);
   launches += 4;
   return 0;
 }

@@ -5,8 +5,24 @@
 #include "voxel.cuh"
 #include "knn.cuh"
 #include "../../include/pcr_cuda.h"
+#include <utility>
+#include <vector>
 
 namespace pcr {
+
+// `prof` (nullable): CUDA-event time of the k-NN kernel is added to it.
+struct KnnProfile {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  float ms = 0.f;
+  int launches = 0;
+  long long queries = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;  // recorded, not yet read back
+  ~KnnProfile();
+  void begin(cudaStream_t s);
+  void end(cudaStream_t s, size_t n);
+  void collect();  // after a stream synchronise
+  void reset() { ms = 0.f; launches = 0; queries = 0; }
+};
 
 struct __align__(16) VoxelRec {  // 80 B
   double mean[3];
@@ -20,6 +36,7 @@ struct VgicpTarget {
   MortonGrid grid;            // over the raw target (kNN for covariances and fitness)
   DevBuf<double> covs;        // per target point, 6 doubles
   DevBuf<int32_t> knn;        // k neighbour indices per target point (scratch of the covariance build)
+  KnnProfile* prof = nullptr; // set by the API layer while profiling is on
   // voxel map
   double resolution = 1.0;
   int cmin[3] = {0, 0, 0}, cdim[3] = {0, 0, 0};
@@ -61,6 +78,7 @@ struct VgicpDriver {
   long long total_corr = 0;
   double last_cost = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  KnnProfile* prof = nullptr;  // k-NN kernel timing (owned by the context)
   ~VgicpDriver();
 
   void evaluate(const float4* src, const double* covs, const uint32_t* d_offs, size_t max_pts, const VgicpTarget& tgt, int count,
@@ -75,7 +93,8 @@ struct VgicpDriver {
 
 // exact k-NN (float metric, (d2, idx) order) + PLANE-regularised covariance for every point of `pts` using `grid` built over it.
 // covs: 6 doubles per point. knn_idx: device scratch/output, k ints per point.
-void gicp_covariances(const float4* pts, size_t n, const MortonGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s);
+void gicp_covariances(const float4* pts, size_t n, const MortonGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s,
+                      KnnProfile* prof = nullptr);
 
 int vgicp_build_target(const float4* pts, size_t n, const pcr_params& prm, VgicpTarget& tgt, KeySort& ks, BBoxWork& bw, cudaStream_t s);
 

@@ -200,25 +200,58 @@ class LoopClosureVerifier:
     (oldKey, curKey) build the history submap of oldKey (+-range keyframes, transformed, 0.5 m downsample), register the
     current keyframe's cloud with VGICP in loop-closure mode from its own pose, accept iff converged and fitness < thresh."""
 
-    def __init__(self, keyframes, context_pc_ds=0.5, history_submap_range=1, fitness_score=0.3, device=0):
+    def __init__(self, keyframes, context_pc_ds=0.5, history_submap_range=1, fitness_score=0.3, device=0, workers=1, devices=None):
+        """workers / devices: verify_batch spreads independent candidates over `workers` VGICP contexts (one CUDA stream
+        each) placed round-robin on `devices` (default: [device]) — SURVEY §8f-2 'batch across candidates / GPUs'."""
         self.keyframes = keyframes
         self.ds = float(context_pc_ds)
         self.range = int(history_submap_range)
         self.thresh = float(fitness_score)
-        self.ctx = capi.Context(capi.PCR_VGICP, device=device)
-        self.ctx.init_for_lc()
+        devs = list(devices) if devices else [device]
+        self.ctxs = []
+        for w in range(max(1, int(workers))):
+            c = capi.Context(capi.PCR_VGICP, device=devs[w % len(devs)])
+            c.init_for_lc()
+            self.ctxs.append(c)
+        self.ctx = self.ctxs[0]
 
-    def verify(self, old_key, cur_key):
+    def _verify_on(self, ctx, old_key, cur_key):
         n = len(self.keyframes)
         near = [k for k in range(old_key - self.range, old_key + self.range + 1) if 0 <= k < n]
-        _, m = self.ctx.submap_build([self.keyframes[k][0] for k in near], [self.keyframes[k][1] for k in near], self.ds, want_points=False, ids=near)
+        _, m = ctx.submap_build([self.keyframes[k][0] for k in near], [self.keyframes[k][1] for k in near], self.ds, want_points=False, ids=near)
         cloud, pose = self.keyframes[cur_key]
-        T, conv = self.ctx.align(cloud, pose)
-        fs = self.ctx.fitness()
+        T, conv = ctx.align(cloud, pose)
+        fs = ctx.fitness()
         return dict(old=old_key, cur=cur_key, converged=bool(conv), fitness=fs, accepted=bool(conv and fs < self.thresh), T=T, map_points=m)
 
+    def verify(self, old_key, cur_key):
+        return self._verify_on(self.ctx, old_key, cur_key)
+
+    def verify_batch(self, pairs):
+        """independent candidates (old_key, cur_key) verified concurrently, one context per in-flight candidate; results in
+        the order of `pairs`, identical to verifying them one after the other (no state is shared between candidates)"""
+        pairs = list(pairs)
+        if len(self.ctxs) == 1 or len(pairs) <= 1:
+            return [self.verify(o, c) for o, c in pairs]
+        import queue
+        from concurrent.futures import ThreadPoolExecutor
+        free = queue.Queue()
+        for c in self.ctxs:
+            free.put(c)
+
+        def one(p):
+            ctx = free.get()
+            try:
+                return self._verify_on(ctx, p[0], p[1])   # ctypes releases the GIL: the contexts' streams run concurrently
+            finally:
+                free.put(ctx)
+        with ThreadPoolExecutor(max_workers=len(self.ctxs)) as ex:
+            return list(ex.map(one, pairs))
+
     def close(self):
-        self.ctx.close()
+        for c in self.ctxs:
+            c.close()
+        self.ctxs = []
 
 
 class ScanContext:
@@ -273,10 +306,11 @@ class LoopClosureManager:
     old_pose^-1 * cur_pose) — the reference stores the relative pose of the CURRENT keyframe poses, not the refined one
     (:106-108)."""
 
-    def __init__(self, keyframes, context_pc_ds=0.5, history_submap_range=1, fitness_score=0.3, lidar_height=2.0, device=0, **sc_params):
+    def __init__(self, keyframes, context_pc_ds=0.5, history_submap_range=1, fitness_score=0.3, lidar_height=2.0, device=0, workers=1, devices=None,
+                 **sc_params):
         self.keyframes = keyframes   # the MapManager's list of (cloud, pose): shared, grows as mapping proceeds
         self.ds = float(context_pc_ds)
-        self.verifier = LoopClosureVerifier(keyframes, context_pc_ds, history_submap_range, fitness_score, device=device)
+        self.verifier = LoopClosureVerifier(keyframes, context_pc_ds, history_submap_range, fitness_score, device=device, workers=workers, devices=devices)
         self.ctb = ScanContext(self.verifier.ctx, lidar_height=lidar_height, **sc_params)
         self.n_contexts = 0
         self.lc_size = 0
@@ -290,13 +324,17 @@ class LoopClosureManager:
             self.n_contexts = len(self.keyframes)
 
     def lcHandler(self):
+        # the reference verifies candidate after candidate (LoopClosureManager.cpp:73-110); the candidates of the new contexts
+        # are independent of each other, so they are collected first and verified as one batch (verify_batch)
+        cands = []
         for i in range(self.lc_size, self.ctb.size()):
             old, _yaw = self.ctb.query(i)
             if old >= 0:
-                r = self.verifier.verify(old, i)
-                self.checked.append(r)
-                if r["accepted"]:
-                    self.loops.append((old, i, np.linalg.inv(self.keyframes[old][1]) @ self.keyframes[i][1]))
+                cands.append((old, i))
+        for r in self.verifier.verify_batch(cands):
+            self.checked.append(r)
+            if r["accepted"]:
+                self.loops.append((r["old"], r["cur"], np.linalg.inv(self.keyframes[r["old"]][1]) @ self.keyframes[r["cur"]][1]))
         self.lc_size = self.ctb.size()
         return self.loops
 

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported():
 def test_struct_layouts_match_header_sizes():
     # field-by-field mirrors of pcr_params / pcr_stats / pcr_loam_iter_log (natural alignment, same order as the header)
     assert ctypes.sizeof(capi.LoamIterLog) == 16 * 8 + 36 * 8 + 6 * 8 + 6 * 8 + 8 + 4 + 4
-    assert ctypes.sizeof(capi.Stats) == 4 * 4 + 7 * 8 + 8 + 4 + 4 + 4 + 4
+    assert ctypes.sizeof(capi.Stats) == 4 * 4 + 7 * 8 + 8 + 4 + 4 + 4 + 4 + 4 + 4 + 8
     p = capi.default_params(capi.PCR_NDT)
     assert p.method == capi.PCR_NDT and p.cores == 4
     assert p.loam_max_iters == 8 and abs(p.loam_plane_thresh - 0.2) < 1e-7

@@ -139,3 +139,26 @@ def test_loop_closure_manager_pipeline():
 def synth_exp(x):
     from simpleslam_b200 import synth
     return synth.se3_exp(x)
+
+
+def test_loop_closure_batch_equals_serial(seq):
+    """independent candidates verified concurrently on a pool of VGICP contexts (one stream each; spread over
+    the GPUs when there are several) give exactly what one context gives candidate after candidate"""
+    import torch
+    from simpleslam_b200 import synth
+    fr = seq["frames"]
+    kfs = [(np.ascontiguousarray(fr[i]["scan"]), fr[i]["truth"] @ synth.se3_exp([0.05 * (i % 3), -0.04, 0.0, 0, 0, np.deg2rad(0.3 * (i % 4))]))
+           for i in range(0, 44, 4)]
+    pairs = [(k - 1, k) for k in range(2, len(kfs))] + [(0, len(kfs) - 1), (3, 5)]
+    serial = frontend.LoopClosureVerifier(kfs)
+    ref = [serial.verify(o, c) for o, c in pairs]
+    serial.close()
+    devs = list(range(min(torch.cuda.device_count(), 4)))
+    pool = frontend.LoopClosureVerifier(kfs, workers=4, devices=devs)
+    got = pool.verify_batch(pairs)
+    pool.close()
+    assert [(g["old"], g["cur"]) for g in got] == pairs
+    for g, r in zip(got, ref):
+        assert g["converged"] == r["converged"] and g["accepted"] == r["accepted"] and g["map_points"] == r["map_points"]
+        assert np.array_equal(g["T"], r["T"]) and g["fitness"] == r["fitness"]
+    assert any(g["accepted"] for g in got) and not all(g["accepted"] for g in got)

@@ -82,7 +82,7 @@ def test_submap_cache_is_keyed_by_id_and_bounded():
     pts, _ = c.submap_build([cl.copy() for cl in clouds[:4]], poses[:4], 0.5, ids=ids[:4])
     assert np.array_equal(pts.view(np.uint32), ref(range(4)).view(np.uint32))
     L = min(len(clouds[0]), len(clouds[4]))
-    buf = np.ascontiguousarray(clouds[0][:L])
+    buf = np.array(clouds[0][:L], copy=True)
     c.submap_build([buf], [poses[0]], 0.5, ids=[100])
     buf[...] = clouds[4][:L]                      # same host address, same count, other content, NEW id
     pts_b, _ = c.submap_build([buf], [poses[4]], 0.5, ids=[101])
