@@ -256,6 +256,49 @@ def make_roofline(method, prof, c_bar, traffic_key):
                     "latency / issue bound, not HBM bound (DESIGN.md §4, profiles/)"}
 
 
+def measure_index_build(ctx, dev, dst_host, raw_host=None, leaf=0.2, method="loam"):
+    """the map-side kernels (the rows where an HBM fraction is meaningful): voxel downsample of the raw map
+    (104 N + 16 M bytes) and the index build over the downsampled map (104 Nm bytes, + 104 B per NDT leaf), device-resident
+    input, warm allocations, best of 3 host-blocking calls."""
+    import torch
+    peak, peak_src = load_peak()
+    out = {"peak": peak, "unit": "GB/s", "peak_source": peak_src}
+    d = torch.from_numpy(np.ascontiguousarray(dst_host)).to(dev)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        ctx.set_target_device(d.data_ptr(), d.shape[0], 32)
+        ts.append(time.perf_counter() - t0)
+    t = min(ts[1:])
+    nbytes = 104.0 * d.shape[0]
+    if method == "ndt":
+        try:
+            nbytes += 104.0 * len(ctx.ndt_leaves()["keys"])
+        except Exception:
+            pass
+    out["index_build"] = {"points": int(d.shape[0]), "ms": 1e3 * t, "algorithmic_bytes": nbytes, "achieved": nbytes / t / 1e9, "frac": nbytes / t / 1e9 / peak,
+                          "what": "pcr_set_target_device: pack + bounding box + keys + radix sort + cell-sorted copy + dense table%s" % (" + leaf statistics" if method == "ndt" else "")}
+    if raw_host is not None:
+        r = torch.from_numpy(np.ascontiguousarray(raw_host)).to(dev)
+        o = torch.empty((r.shape[0], 8), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        ts, m = [], 0
+        for _ in range(4):
+            t0 = time.perf_counter()
+            m = ctx.voxel_downsample_device(r.data_ptr(), r.shape[0], 32, leaf, o.data_ptr(), r.shape[0])
+            ts.append(time.perf_counter() - t0)
+        t = min(ts[1:])
+        nb = 104.0 * r.shape[0] + 16.0 * m
+        out["voxel_downsample"] = {"points_in": int(r.shape[0]), "points_out": int(m), "leaf": leaf, "ms": 1e3 * t, "algorithmic_bytes": nb,
+                                   "achieved": nb / t / 1e9, "frac": nb / t / 1e9 / peak,
+                                   "what": "pcr_voxel_downsample_device: pack + bounding box + PCL keys + radix sort + gather + per-voxel float centroids"}
+        del r, o
+    del d
+    torch.cuda.empty_cache()
+    return out
+
+
 def add_prof(prof, st, ms_total=None):
     prof["hot_ms"] += st["ms_hot_kernel"]
     prof["hot_launches"] += st["hot_kernel_launches"]
@@ -655,6 +698,7 @@ def measure_replicas(args, name, rank, world, local_rank, dist, dev, cpu=True):
         s0, d0, _, _ = step_inputs(wl, 0)
         errs = np.array(errs)
         roof = make_roofline(method, prof, c_bar, name)
+        idx_roof = measure_index_build(ctx, dev, wl["dst"], None, 0.2, method) if (method != "vgicp" and world == 1) else None
         if method == "vgicp" and prof.get("ms_aux_kernel"):
             # the k-NN behind the covariances dominates a VGICP registration: its own line (16 B per query + 16 B per candidate examined)
             peak, _ = load_peak()
@@ -679,7 +723,7 @@ def measure_replicas(args, name, rank, world, local_rank, dist, dev, cpu=True):
                     "pageable_value": (world / float(np.mean(e2e_pageable_t))) if e2e_pageable_t else None,
                     "static_map_ms_per_step": (1e3 * float(np.mean(e2e_cached_t))) if e2e_cached_t else None},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpub, "parity": par,
-            "setup": dict(setup, data_generation_s=t_gen), "wall_s_timed_region": wall_total,
+            "setup": dict(setup, data_generation_s=t_gen), "wall_s_timed_region": wall_total, "map_kernels": idx_roof,
             "pose_error_vs_truth": {"median_m": float(np.median(errs[:, 0])), "median_rad": float(np.median(errs[:, 1]))},
         }
     ctx.close()
@@ -702,9 +746,9 @@ def measure_c4_job(args, method, rank, world, local_rank, dist, dev, cpu=True):
     setup = {}
     # ---- the static map: rank 0 builds the index, NCCL broadcast, the others import (outside the timed region, reported)
     t0 = time.perf_counter()
-    dst, n_map = None, 0
+    dst, raw_map, n_map = None, None, 0
     if rank == 0:
-        dst, n_raw = workloads.c4_map(ds)
+        dst, raw_map = workloads.c4_map(ds, keep_raw=True)
         n_map = len(dst)
     setup["map_generation_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
@@ -832,6 +876,7 @@ def measure_c4_job(args, method, rank, world, local_rank, dist, dev, cpu=True):
                 qs = [scans[u][:, :3].astype(np.float64) @ guesses[u][:3, :3].T + guesses[u][:3, 3] for u in range(min(4, n_local))]
                 c_bar = float(orc.neighbourhood27(dst, np.concatenate(qs), 1.0, threads=cores))
         roof = make_roofline(method, prof, c_bar, "c4_" + method)
+        idx_roof = measure_index_build(ctx, dev, dst, raw_map, 0.2, method) if world == 1 else None
         out = {
             "metric": "scan registrations/sec (%s)" % method.upper(), "value": value, "unit": "registrations/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "p50_align_ms": float(np.median(lat)) if lat else None,
@@ -849,7 +894,7 @@ def measure_c4_job(args, method, rank, world, local_rank, dist, dev, cpu=True):
                     "what": "pcr_batch_align of every rank's shard from PINNED host memory (scan upload + align + pose read-back) + the gather, per step",
                     "pageable_ms_per_step": 1e3 * t_pg / 2, "pageable_value": 2 * n_job / t_pg},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpub, "parity": par,
-            "setup": setup, "wall_s_timed_region": wall,
+            "setup": setup, "wall_s_timed_region": wall, "map_kernels": idx_roof,
             "job": {"converged": int(np.sum(allc)), "of": int(n_job)},
             "pose_error_vs_truth": {"median_m": float(np.median([pose_err(T, Tt)[0] for T, Tt in zip(myT, truths)])) if n_local else None},
         }

@@ -752,16 +752,34 @@ int loam_build_target(const float4* pts, size_t n, double max_knn_d2, CellGrid& 
   // gate radius r = sqrt(max_knn_d2) (LoamRegister.cpp:59 compares the SQUARED 5th distance with 1.0). With cells of
   // r / (R - 4 * slack) the R-ring cube around a query's cell contains every map point closer than r even after the float
   // rounding of the cell assignment (slack <= 2e-3 cells below ~2 km, grid_slack_cells()).
-  const float r = std::sqrt(float(max_knn_d2));
-  int rc = build_cell_grid(pts, n, r / (1.0f - 0.008f), grid, ks, bw, s, true);
+  // Which of the two cell sizes is used is decided BEFORE the index is built, from the number of gate-sized cells the map
+  // occupies (bitmap + popcount, no sort): dense maps (more than PCR_LOAM_FINE_ABOVE points per occupied gate-sized cell)
+  // get half-gate cells — most 5-NN balls then fit inside the 27 cells around the query, 8x fewer candidates — and the index
+  // is built ONCE. If the half-gate table would not fit the dense-table budget the gate-sized grid is used instead.
+  grid.built = false;
+  grid.has_start = false;
+  grid.n = n;
   grid.max_ring = 1;
-  if (rc || n == 0) return rc;
+  grid.occupied = 0;
+  if (n == 0) return 0;
+  const float r = std::sqrt(float(max_knn_d2));
+  float bb[6];
+  bbox_blocking(pts, n, bb, bb + 3, bw, s);
+  if (bw.n_nonfinite) return kRetryNonFinite;
+  const float coarse = r / (1.0f - 0.008f), fine = r / (2.0f - 0.008f);
+  GridSpec gc;
+  if (!make_grid_spec(bb, bb + 3, coarse, gc) || gc.ncell > (1ll << 29)) return -5;
+  grid.occupied = count_occupied_cells(pts, n, gc, ks.tmp, ks.d_count, ks.h_count, s);
   const double per_cell = double(n) / double(std::max<size_t>(grid.occupied, 1));
-  if (per_cell > double(env_int("PCR_LOAM_FINE_ABOVE", 6))) {  // dense map: most 5-NN balls fit inside the 27 half-width cells, 8x fewer candidates per query
-    CellGrid& fine = grid;
-    rc = build_cell_grid(pts, n, r / (2.0f - 0.008f), fine, ks, bw, s, true);
-    grid.max_ring = 2;
+  if (per_cell > double(env_int("PCR_LOAM_FINE_ABOVE", 6))) {
+    GridSpec gf;
+    if (make_grid_spec(bb, bb + 3, fine, gf) && gf.ncell <= (1ll << 29)) {
+      const int rc = build_cell_grid(pts, n, fine, grid, ks, bw, s, true, bb);
+      if (rc == 0) { grid.max_ring = 2; return 0; }
+    }
   }
+  const int rc = build_cell_grid(pts, n, coarse, grid, ks, bw, s, true, bb);
+  grid.max_ring = 1;
   return rc;
 }
 

@@ -334,6 +334,40 @@ __global__ void __launch_bounds__(256) grid_scatter_start_kernel(const float4* _
   if ((threadIdx.x & 31) == 0 && heads) atomicAdd(occupied, unsigned(__popc(heads)));
 }
 
+__global__ void __launch_bounds__(256) occupancy_bitmap_kernel(const float4* __restrict__ pts, size_t n, GridSpec g, unsigned* __restrict__ bits) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(pts + i);
+  const long long key = (long long)voxel_axis(p.x, g.inv_leaf[0], g.min_b[0]) * g.mul[0] + (long long)voxel_axis(p.y, g.inv_leaf[1], g.min_b[1]) * g.mul[1] +
+                        (long long)voxel_axis(p.z, g.inv_leaf[2], g.min_b[2]) * g.mul[2];
+  const unsigned bit = 1u << (key & 31);
+  unsigned* w = bits + (key >> 5);
+  if (!(__ldg(w) & bit)) atomicOr(w, bit);  // most points find their cell's bit already set
+}
+__global__ void __launch_bounds__(256) popcount_kernel(const unsigned* __restrict__ bits, size_t nwords, unsigned* __restrict__ out) {
+  unsigned c = 0;
+  for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < nwords; i += size_t(gridDim.x) * blockDim.x) c += __popc(bits[i]);
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+size_t count_occupied_cells(const float4* pts, size_t n, const GridSpec& g, DevBuf<unsigned char>& tmp, DevBuf<unsigned>& d_count,
+                            PinBuf<unsigned>& h_count, cudaStream_t s) {
+  if (n == 0) return 0;
+  const size_t nwords = size_t((g.ncell + 31) / 32);
+  tmp.ensure(nwords * 4);
+  unsigned* bits = reinterpret_cast<unsigned*>(tmp.p);
+  unsigned* dc = d_count.ensure(1);
+  unsigned* hc = h_count.ensure(1);
+  PCR_CUDA_CHECK(cudaMemsetAsync(bits, 0, nwords * 4, s));
+  PCR_CUDA_CHECK(cudaMemsetAsync(dc, 0, sizeof(unsigned), s));
+  occupancy_bitmap_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(pts, n, g, bits);
+  popcount_kernel<<<unsigned(std::min<size_t>((nwords + 255) / 256, size_t(kNumSMs) * 8)), 256, 0, s>>>(bits, nwords, dc);
+  PCR_CUDA_CHECK(cudaMemcpyAsync(hc, dc, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  PCR_CUDA_CHECK(cudaStreamSynchronize(s));
+  return *hc;
+}
+
 struct MinOp {
   __device__ __forceinline__ int32_t operator()(const int32_t& a, const int32_t& b) const { return a < b ? a : b; }
 };
@@ -344,14 +378,19 @@ double grid_slack_cells(const GridSpec& g) {
   return std::max(1e-3, m * 4.8e-7);
 }
 
-int build_cell_grid(const float4* pts, size_t n, float cell, CellGrid& grid, KeySort& ks, BBoxWork& bw, cudaStream_t s, bool start_table) {
+int build_cell_grid(const float4* pts, size_t n, float cell, CellGrid& grid, KeySort& ks, BBoxWork& bw, cudaStream_t s, bool start_table,
+                    const float* bbox) {
   grid.built = false;
   grid.has_start = false;
   grid.n = n;
   if (n == 0) return 0;
   float mn[3], mx[3];
-  bbox_blocking(pts, n, mn, mx, bw, s);
-  if (bw.n_nonfinite) return kRetryNonFinite;
+  if (bbox) {
+    for (int a = 0; a < 3; a++) { mn[a] = bbox[a]; mx[a] = bbox[3 + a]; }
+  } else {
+    bbox_blocking(pts, n, mn, mx, bw, s);
+    if (bw.n_nonfinite) return kRetryNonFinite;
+  }
   bool ok = make_grid_spec(mn, mx, cell, grid.g);
   if (!ok || grid.g.ncell > (1ll << 29)) return -5;
   ks.sort(pts, n, grid.g, s);
@@ -363,18 +402,14 @@ int build_cell_grid(const float4* pts, size_t n, float cell, CellGrid& grid, Key
     grid.start.ensure(ncell + 1);
     PCR_CUDA_CHECK(cudaMemsetAsync(grid.start.p, 0x7f, (ncell + 1) * sizeof(int32_t), s));
     unsigned* dc = ks.d_count.ensure(1);
-    unsigned* hc = ks.h_count.ensure(1);
     PCR_CUDA_CHECK(cudaMemsetAsync(dc, 0, sizeof(unsigned), s));
     grid_scatter_start_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(pts, ks.keys, ks.vals, n, grid.g.ncell, grid.pts.p, grid.start.p, dc);
-    PCR_CUDA_CHECK(cudaMemcpyAsync(hc, dc, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     auto rit = thrust::make_reverse_iterator(grid.start.p + ncell + 1);
     size_t bytes = 0;
     cub::DeviceScan::InclusiveScan(nullptr, bytes, rit, rit, MinOp(), int(ncell + 1), s);
     ks.tmp.ensure(bytes);
     PCR_CUDA_CHECK(cub::DeviceScan::InclusiveScan(ks.tmp.p, bytes, rit, rit, MinOp(), int(ncell + 1), s));
-    PCR_CUDA_CHECK(cudaStreamSynchronize(s));
-    grid.occupied = *hc;
-    grid.has_start = true;
+    grid.has_start = true;  // no read-back here: the build stays queued on the stream (callers synchronise once, at the end)
   } else {
     grid.range.ensure(ncell);
     PCR_CUDA_CHECK(cudaMemsetAsync(grid.range.p, 0, ncell * sizeof(int2), s));

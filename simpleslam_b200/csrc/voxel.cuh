@@ -79,8 +79,13 @@ inline CellGridView view_of(const CellGrid& grid) {
 }
 // Returns PCR error code (0 ok, -5 grid too large).
 // start_table: build `start` (LOAM row-run lookups) instead of `range`.
+// bbox (nullable): min[3], max[3] of the finite points if the caller has them already (saves the bounding-box pass + sync).
 int build_cell_grid(const float4* pts, size_t n, float cell, CellGrid& grid, KeySort& ks, BBoxWork& bw, cudaStream_t s,
-                    bool start_table = false);
+                    bool start_table = false, const float* bbox = nullptr);
+// number of occupied cells of the grid `g` would have over `pts` (bitmap + popcount, no sort): lets a caller pick the cell
+// size from the density BEFORE building the index. Blocking (one read-back).
+size_t count_occupied_cells(const float4* pts, size_t n, const GridSpec& g, DevBuf<unsigned char>& tmp, DevBuf<unsigned>& d_count,
+                            PinBuf<unsigned>& h_count, cudaStream_t s);
 // float rounding of x * inv_leaf moves a point by at most ~|cell index| * 2^-23 cells across a cell face: slack (in cells)
 // that exactness arguments about "every point outside the scanned cells is farther than ..." have to subtract
 double grid_slack_cells(const GridSpec& g);

@@ -90,12 +90,12 @@ def _big_map(sc, extent, spacing, seed=7, strips=16):
 C4_TILES, C4_SPACING = 4, 0.24
 
 
-def c4_map(downsample, tiles=C4_TILES, spacing=C4_SPACING):
+def c4_map(downsample, tiles=C4_TILES, spacing=C4_SPACING, keep_raw=False):
     """the static map of C4: surfaces of tiles x tiles 200 m tiles sampled at `spacing`, voxel-downsampled at 0.2 m (~20M points)"""
     sc = synth.Scene(seed=SEED, tiles=(tiles, tiles))
     raw = _big_map(sc, 200.0 * tiles, spacing)
     dst = downsample(raw, 0.2)
-    return dst, len(raw)
+    return (dst, raw) if keep_raw else (dst, len(raw))
 
 
 def c4_scans(method, downsample, lo, hi, n_total, seed_offset=0, tiles=C4_TILES, workers=8):
