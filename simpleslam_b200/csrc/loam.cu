@@ -1,4 +1,6 @@
-// LOAM scan-to-map: one fused kernel per Gauss-Newton iteration. A warp owns a tile of up to 32 query points.
+// LOAM scan-to-map. Small problems (a single scan): one FUSED kernel per Gauss-Newton iteration, described here; large
+// batches: a search kernel + a fit kernel per iteration (see "Batch path" below). Fused kernel: a warp owns a tile of up to
+// 32 query points.
 //   phase 1: exact 5-NN on a uniform grid whose cells are HALF the gate radius wide (gate: 5th neighbour closer than 1 m,
 //     LoamRegister.cpp:59). LPQ lanes (1, 2, 4 or 8, picked from the problem size) co-operate on one query: the 3x3 x-rows
 //     of the 27-cell ring are contiguous runs of the cell-sorted map (two loads of the dense `start` table per row), the
@@ -44,19 +46,113 @@ __device__ __forceinline__ Cand cand_sel(bool p, const Cand& a, const Cand& b) {
 __constant__ signed char c_row_dy[25] = {0, 1, -1, 0, 0, 1, 1, -1, -1, 2, -2, 0, 0, 2, 2, -2, -2, 1, -1, 1, -1, 2, 2, -2, -2};
 __constant__ signed char c_row_dz[25] = {0, 0, 0, 1, -1, 1, -1, 1, -1, 0, 0, 2, -2, 1, -1, 1, -1, 2, 2, -2, -2, 2, -2, 2, -2};
 
-// MODE 0: fused iteration (search + fit + solve) — small problems, one launch per iteration keeps the latency short.
-// MODE 1: search only: no shared-memory accumulators, half the registers -> twice the resident warps to hide the
-//         dependent load chains of the neighbour search; the five winners (+ counters) of every query go to `knn_buf`
-//         (seven int planes of `knn_stride` entries).   MODE 2: fit + solve from `knn_buf`. Large batches run 1 then 2.
-constexpr int kModeFused = 0, kModeSearch = 1, kModeFit = 2;
+// Fused iteration (search + fit + solve) — small problems, one launch per iteration keeps the latency short.
+// A5-A7 for one query whose five neighbours are known (ascending (d2, index) order): gate, 5x3 column-pivoted QR plane fit,
+// validity / weight gates, residual E and SE(3) Jacobian row J (LoamRegister.cpp:29-72, 141-160), all FP64 with the
+// reference's float range term. Returns the status (0 gate, 1 plane invalid, 2 weight, 3 accepted); J, E valid for 3.
+__device__ __forceinline__ int loam_point_residual(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5], bool five, double d5,
+                                                   double q0, double q1, double q2, const float4& po, const LoamParams& prm, double (&J)[6],
+                                                   double& E) {
+  // LoamRegister.cpp:59 gate: squared distance of the 5th neighbour < 1.0
+  if (!(five && d5 < prm.max_knn_d2)) return 0;
+  double A[5][3], b[5], x[3];
+#pragma unroll
+  for (int k = 0; k < 5; k++) { A[k][0] = double(nx[k]); A[k][1] = double(ny[k]); A[k][2] = double(nz[k]); b[k] = -1.0; }
+  cpqr5x3_solve(A, b, x);
+  const double xn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  bool valid = true;
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    double v = x[0] * double(nx[k]) + x[1] * double(ny[k]) + x[2] * double(nz[k]);
+    if (fabs(v + 1.0) > prm.plane_thresh * xn) valid = false;
+  }
+  if (!valid) return 1;
+  const double dist = ((q0 * x[0] + q1 * x[1] + q2 * x[2]) + 1.0) / xn;
+  // :147-148 float range term: sqrt(sqrt(x*x + y*y + z*z)) with float products, sums and roots
+  const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(po.x, po.x), __fmul_rn(po.y, po.y)), __fmul_rn(po.z, po.z));
+  const float rr = __fsqrt_rn(__fsqrt_rn(r2));
+  const double s = 1.0 - 0.9 * fabs(dist) / double(rr);
+  if (!(s > prm.point_thresh)) return 2;
+  E = s * dist;
+  const double sn0 = s * (x[0] / xn), sn1 = s * (x[1] / xn), sn2 = s * (x[2] / xn);
+  J[0] = sn0; J[1] = sn1; J[2] = sn2;
+  J[3] = sn1 * (-q2) + sn2 * q1;
+  J[4] = sn0 * q2 + sn2 * (-q0);
+  J[5] = sn0 * (-q1) + sn1 * q0;
+  return 3;
+}
 
-template <int LPQ, bool DEBUG, int MODE>
-__global__ void __launch_bounds__(kLoamBlock, MODE == kModeSearch ? 4 : (MODE == kModeFit ? 3 : 2))
+// A8 + A9 by one warp once the 30 sums of a scan are complete (stot): normal equations -> warp-parallel 6x6 LDLT ->
+// convergence test -> T <- exp(x) T, iteration log (LoamRegister.cpp:171-220). sT = the pose this iteration linearised at.
+struct SolveScratch { double sJ[36], sF[36], sy[6], sE[16]; int str[6]; };
+__device__ __forceinline__ void loam_solve_step(const double* stot, const double* sT, LoamState* st, pcr_loam_iter_log* logs, int scan,
+                                                const LoamParams& prm, int apply_update, uint32_t ns, int lane, SolveScratch& sc) {
+  const long long n = (long long)(stot[27] + 0.5);
+  const int it = st->iters;
+  pcr_loam_iter_log* lg = logs ? logs + size_t(scan) * prm.max_iters + it : nullptr;
+  for (int e = lane; e < 36; e += 32) {
+    const int r = e / 6, cidx = e % 6, a = min(r, cidx), b = max(r, cidx);
+    const double v = stot[a * 6 - a * (a - 1) / 2 + (b - a)];  // index of (a, b), a <= b, in the packed upper triangle
+    sc.sJ[e] = v;
+    sc.sF[e] = v;
+    if (lg) lg->JtJ[e] = v;
+  }
+  if (lane < 6) {
+    sc.sy[lane] = -stot[21 + lane];
+    if (lg) { lg->JtE[lane] = stot[21 + lane]; lg->x[lane] = 0.0; }
+  }
+  if (lg && lane < 16) lg->T_before[lane] = sT[lane];
+  if (lg && lane == 0) { lg->n = n; lg->converged = 0; lg->pad = 0; }
+  __syncwarp();
+  bool done = false, conv = false;
+  if (n < 6) {  // LoamRegister.cpp:173-176
+    done = true;
+  } else {
+    ldlt6_solve_warp(sc.sF, sc.sy, sc.str, lane);  // x -> sy
+    const double x0 = sc.sy[0], x1 = sc.sy[1], x2 = sc.sy[2], x3 = sc.sy[3], x4 = sc.sy[4], x5 = sc.sy[5];
+    if (lg && lane < 6) lg->x[lane] = sc.sy[lane];
+    const double np = sqrt(x0 * x0 + x1 * x1 + x2 * x2);
+    const double nr = sqrt(x3 * x3 + x4 * x4 + x5 * x5);
+    if (np <= prm.pos_conv && nr <= prm.rot_conv) {  // :202-206 — converge BEFORE applying x
+      conv = true;
+      done = true;
+    } else if (apply_update) {
+      if (lane == 0) {
+        const double xv[6] = {x0, x1, x2, x3, x4, x5};
+        double E[16];
+        se3_exp(xv, E);
+#pragma unroll
+        for (int q = 0; q < 16; q++) sc.sE[q] = E[q];
+      }
+      __syncwarp();
+      if (lane < 16) {  // T <- exp(x) * T   (column-major)
+        const int r = lane & 3, cidx = lane >> 2;
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) v += sc.sE[q * 4 + r] * sT[cidx * 4 + q];
+        st->T[lane] = v;
+      }
+      if (it + 1 >= prm.max_iters) done = true;
+    }
+  }
+  if (lane == 0) {
+    st->ticket = 0;
+    st->iters = it + 1;
+    st->n_last = int(n);
+    st->cand_total += (long long)(stot[28] + 0.5);
+    st->rows_total += (long long)(stot[29] + 0.5);
+    st->pt_evals += (long long)ns;
+    if (conv) { st->converged = 1; if (lg) lg->converged = 1; }
+    if (done || !apply_update) st->done = 1;
+  }
+}
+
+template <int LPQ, bool DEBUG>
+__global__ void __launch_bounds__(kLoamBlock, 2)
 loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, GridView grid, LoamParams prm,
                  LoamState* __restrict__ states, double* __restrict__ partials, int max_blocks,
                  pcr_loam_iter_log* __restrict__ logs, int apply_update, int tile, double slack, int max_ring,
-                 int32_t* __restrict__ dbg_knn, int32_t* __restrict__ dbg_status, int32_t* __restrict__ knn_buf, size_t knn_stride,
-                 const uint32_t* __restrict__ qperm) {
+                 int32_t* __restrict__ dbg_knn, int32_t* __restrict__ dbg_status) {
   // LPQ = lanes co-operating on one query, G = 32 / LPQ queries searched concurrently by a warp.
   // `tile` (multiple of G, <= 32) = queries a warp owns per pass: 32 for throughput on large batches, smaller when there
   // are too few queries to fill the machine (a single scan), trading phase-2 lane utilisation for shorter latency chains.
@@ -76,10 +172,8 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
   __shared__ double stot[kNV];
   __shared__ int s_last;
   if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
-  if (MODE != kModeSearch) {
 #pragma unroll
-    for (int k = 0; k < kNV; k++) sacc[k * kLoamBlock + threadIdx.x] = 0.0;
-  }
+  for (int k = 0; k < kNV; k++) sacc[k * kLoamBlock + threadIdx.x] = 0.0;
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -117,16 +211,9 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     int wj[5] = {-1, -1, -1, -1, -1};  // cell-sorted positions of my query's five nearest neighbours
     int my_ncand = 0, my_nrows = 0;
 
-    if (MODE == kModeFit && have) {  // winners of the search kernel
-#pragma unroll
-      for (int q = 0; q < 5; q++) wj[q] = knn_buf[size_t(q) * knn_stride + i];
-      my_ncand = knn_buf[5 * knn_stride + i];
-      my_nrows = knn_buf[6 * knn_stride + i];
-    }
-
     // ---- phase 1: G queries of the tile are searched per round, LPQ lanes each
-    const unsigned todo = MODE == kModeFit ? 0u : __ballot_sync(FULL, have && near);
-    const int rounds = MODE == kModeFit ? 0 : (tile + G - 1) / G;
+    const unsigned todo = __ballot_sync(FULL, have && near);
+    const int rounds = (tile + G - 1) / G;
     for (int r = 0; r < rounds; r++) {
       const unsigned round_bits = (G == 32 ? todo : ((todo >> (r * G)) & ((1u << G) - 1u)));
       if (round_bits == 0) continue;  // warp-uniform
@@ -252,23 +339,12 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
       if (lane / G == r) { my_ncand = nc; my_nrows = nr; }
     }
 
-    if (MODE == kModeSearch) {
-      if (have) {
-#pragma unroll
-        for (int q = 0; q < 5; q++) knn_buf[size_t(q) * knn_stride + i] = wj[q];
-        knn_buf[5 * knn_stride + i] = my_ncand;
-        knn_buf[6 * knn_stride + i] = my_nrows;
-      }
-      continue;
-    }
-
     // ---- phase 2: one query per lane
     if (have) {
-      int status = 0;
       const double q0 = double(pmf[0]), q1 = double(pmf[1]), q2 = double(pmf[2]);
       float nx[5], ny[5], nz[5];
       int nidx[5];
-      bool five = wj[4] >= 0;
+      const bool five = wj[4] >= 0;
 #pragma unroll
       for (int k = 0; k < 5; k++) {
         const float4 m = five ? __ldg(grid.pts + wj[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -276,84 +352,31 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
       }
       double d5 = DBL_MAX;
       if (five) {
-        if (MODE == kModeFit) {
-          // the search kernel selects the five winners on the FP32 metric (the SET is exact, see loam_search_kernel): order
-          // them here by the exact FP64 (d2, original index) key, the order nanoflann returns them in
-          unsigned long long ek[5];
-#pragma unroll
-          for (int k = 0; k < 5; k++) {
-            const double dx = q0 - double(nx[k]), dyy = q1 - double(ny[k]), dzz = q2 - double(nz[k]);
-            ek[k] = (unsigned long long)__double_as_longlong(dx * dx + dyy * dyy + dzz * dzz);
-          }
-          auto cswap = [&](int a, int b) {  // compare-exchange, a < b
-            const bool sw = ek[b] < ek[a] || (ek[b] == ek[a] && nidx[b] < nidx[a]);
-            const unsigned long long te = sw ? ek[a] : ek[b]; ek[a] = sw ? ek[b] : ek[a]; ek[b] = te;
-            const float tx = sw ? nx[a] : nx[b]; nx[a] = sw ? nx[b] : nx[a]; nx[b] = tx;
-            const float ty = sw ? ny[a] : ny[b]; ny[a] = sw ? ny[b] : ny[a]; ny[b] = ty;
-            const float tz = sw ? nz[a] : nz[b]; nz[a] = sw ? nz[b] : nz[a]; nz[b] = tz;
-            const int ti = sw ? nidx[a] : nidx[b]; nidx[a] = sw ? nidx[b] : nidx[a]; nidx[b] = ti;
-          };
-          cswap(0, 1); cswap(3, 4); cswap(2, 4); cswap(2, 3); cswap(0, 3); cswap(0, 2); cswap(1, 4); cswap(1, 3); cswap(1, 2);  // 9-exchange network
-          d5 = __longlong_as_double((long long)ek[4]);
-        } else {
-          const double dx = q0 - double(nx[4]), dyy = q1 - double(ny[4]), dzz = q2 - double(nz[4]);
-          d5 = dx * dx + dyy * dyy + dzz * dzz;
-        }
+        const double dx = q0 - double(nx[4]), dyy = q1 - double(ny[4]), dzz = q2 - double(nz[4]);
+        d5 = dx * dx + dyy * dyy + dzz * dzz;
       }
-      // LoamRegister.cpp:59 gate: squared distance of the 5th neighbour < 1.0
-      const bool gate = five && (d5 < prm.max_knn_d2);
-      const uint32_t iq = qperm ? __ldg(qperm + i) : i;  // original position of this query (queries may be spatially re-ordered)
+      double J[6], E = 0.0;
+      const int status = loam_point_residual(nx, ny, nz, five, d5, q0, q1, q2, po, prm, J, E);
       if (DEBUG && dbg_knn) {
 #pragma unroll
-        for (int k = 0; k < 5; k++) dbg_knn[size_t(iq) * 5 + k] = gate ? nidx[k] : -1;
+        for (int k = 0; k < 5; k++) dbg_knn[size_t(i) * 5 + k] = status >= 1 ? nidx[k] : -1;
       }
-      if (gate) {
-        status = 1;
-        double A[5][3], b[5], x[3];
+      if (status == 3) {
+        int k = 0;
 #pragma unroll
-        for (int k = 0; k < 5; k++) { A[k][0] = double(nx[k]); A[k][1] = double(ny[k]); A[k][2] = double(nz[k]); b[k] = -1.0; }
-        cpqr5x3_solve(A, b, x);
-        const double xn = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
-        bool valid = true;
+        for (int r = 0; r < 6; r++)
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-          double v = x[0] * double(nx[k]) + x[1] * double(ny[k]) + x[2] * double(nz[k]);
-          if (fabs(v + 1.0) > prm.plane_thresh * xn) valid = false;
-        }
-        if (valid) {
-          status = 2;
-          const double dist = ((q0 * x[0] + q1 * x[1] + q2 * x[2]) + 1.0) / xn;
-          // :147-148 float range term: sqrt(sqrt(x*x + y*y + z*z)) with float products, sums and roots
-          const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(po.x, po.x), __fmul_rn(po.y, po.y)), __fmul_rn(po.z, po.z));
-          const float rr = __fsqrt_rn(__fsqrt_rn(r2));
-          const double s = 1.0 - 0.9 * fabs(dist) / double(rr);
-          if (s > prm.point_thresh) {
-            status = 3;
-            const double E = s * dist;
-            const double sn0 = s * (x[0] / xn), sn1 = s * (x[1] / xn), sn2 = s * (x[2] / xn);
-            double J[6];
-            J[0] = sn0; J[1] = sn1; J[2] = sn2;
-            J[3] = sn1 * (-q2) + sn2 * q1;
-            J[4] = sn0 * q2 + sn2 * (-q0);
-            J[5] = sn0 * (-q1) + sn1 * q0;
-            int k = 0;
+          for (int cc = r; cc < 6; cc++) { acc[k * kLoamBlock] += J[r] * J[cc]; k++; }
 #pragma unroll
-            for (int r = 0; r < 6; r++)
-#pragma unroll
-              for (int cc = r; cc < 6; cc++) { acc[k * kLoamBlock] += J[r] * J[cc]; k++; }
-#pragma unroll
-            for (int r = 0; r < 6; r++) acc[(21 + r) * kLoamBlock] += J[r] * E;
-            acc[27 * kLoamBlock] += 1.0;
-          }
-        }
+        for (int r = 0; r < 6; r++) acc[(21 + r) * kLoamBlock] += J[r] * E;
+        acc[27 * kLoamBlock] += 1.0;
       }
       acc[28 * kLoamBlock] += double(my_ncand);
       acc[29 * kLoamBlock] += double(my_nrows);
-      if (DEBUG && dbg_status) dbg_status[iq] = status;
+      if (DEBUG && dbg_status) dbg_status[i] = status;
     }
   }
 
-  if (MODE == kModeSearch) return;
 
   // ---- block reduction straight out of shared memory, fixed order: warp w owns components w, w+8, ...
   __syncthreads();
@@ -400,73 +423,20 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
   __syncthreads();
   if (warp != 0) return;
   // ---- warp-parallel epilogue (warp 0 of the last block): normal equations -> LDLT solve -> convergence -> exp-map update
-  __shared__ double sJ[36], sF[36], sy[6], sE[16];
-  __shared__ int str[6];
-  const long long n = (long long)(stot[27] + 0.5);
-  const int it = st->iters;
-  pcr_loam_iter_log* lg = logs ? logs + size_t(scan) * prm.max_iters + it : nullptr;
-  for (int e = lane; e < 36; e += 32) {
-    const int r = e / 6, cidx = e % 6, a = min(r, cidx), b = max(r, cidx);
-    const double v = stot[a * 6 - a * (a - 1) / 2 + (b - a)];  // index of (a, b), a <= b, in the packed upper triangle
-    sJ[e] = v;
-    sF[e] = v;
-    if (lg) lg->JtJ[e] = v;
-  }
-  if (lane < 6) {
-    sy[lane] = -stot[21 + lane];
-    if (lg) { lg->JtE[lane] = stot[21 + lane]; lg->x[lane] = 0.0; }
-  }
-  if (lg && lane < 16) lg->T_before[lane] = sT[lane];
-  if (lg && lane == 0) { lg->n = n; lg->converged = 0; lg->pad = 0; }
-  __syncwarp();
-  bool done = false, conv = false, update = false;
-  if (n < 6) {  // LoamRegister.cpp:173-176
-    done = true;
-  } else {
-    ldlt6_solve_warp(sF, sy, str, lane);  // x -> sy
-    const double x0 = sy[0], x1 = sy[1], x2 = sy[2], x3 = sy[3], x4 = sy[4], x5 = sy[5];
-    if (lg && lane < 6) lg->x[lane] = sy[lane];
-    const double np = sqrt(x0 * x0 + x1 * x1 + x2 * x2);
-    const double nr = sqrt(x3 * x3 + x4 * x4 + x5 * x5);
-    if (np <= prm.pos_conv && nr <= prm.rot_conv) {  // :202-206 — converge BEFORE applying x
-      conv = true;
-      done = true;
-    } else if (apply_update) {
-      update = true;
-      if (lane == 0) {
-        const double xv[6] = {x0, x1, x2, x3, x4, x5};
-        double E[16];
-        se3_exp(xv, E);
-#pragma unroll
-        for (int q = 0; q < 16; q++) sE[q] = E[q];
-      }
-      __syncwarp();
-      if (lane < 16) {  // T <- exp(x) * T   (column-major)
-        const int r = lane & 3, cidx = lane >> 2;
-        double v = 0.0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) v += sE[q * 4 + r] * sT[cidx * 4 + q];
-        st->T[lane] = v;
-      }
-      if (it + 1 >= prm.max_iters) done = true;
-    }
-  }
-  if (lane == 0) {
-    st->ticket = 0;
-    st->iters = it + 1;
-    st->n_last = int(n);
-    st->cand_total += (long long)(stot[28] + 0.5);
-    st->rows_total += (long long)(stot[29] + 0.5);
-    st->pt_evals += (long long)ns;
-    if (conv) { st->converged = 1; if (lg) lg->converged = 1; }
-    if (done || !apply_update) st->done = 1;
-  }
-  (void)update;
+  __shared__ SolveScratch sc;
+  loam_solve_step(stot, sT, st, logs, scan, prm, apply_update, ns, lane, sc);
 }
 
 // ================================================================================================================
-// Batched search kernel (one lane per query, queries in Morton order of their scan-frame position so that the 32 lanes of
-// a warp walk neighbouring rows of the map: similar trip counts, shared cache lines).
+// Batch path (>= ~150 k queries per iteration): every Gauss-Newton iteration is two kernels.
+//
+// loam_search_kernel — one lane per query, queries in Morton order of their scan-frame position (neighbouring lanes walk
+// neighbouring rows of the map). Two stages per ring:
+//   stage 1 (convergent, unrolled): the geometry of all 9 (ring 2: 16) x-rows of the neighbourhood and ALL their start-table
+//     entries are issued together — one memory latency instead of one per row — and the rows that actually hold map points
+//     are appended to the lane's own row list in shared memory (column = thread: conflict-free);
+//   stage 2: the lane walks its OWN list (no iterations wasted on empty or out-of-range rows, so the lanes of a warp stay
+//     busy together), pruning rows against the current bound and scanning the candidates four float4 at a time.
 // Selection runs on the FP32 metric f (|f - e| <= 3e-7 e against the exact FP64 metric e of the reference, both taken on
 // the same float coordinates): a lane keeps its five smallest (f, position) pairs and the smallest f that was looked at but
 // is NOT among them (f_out). Candidates and rows are pruned against thr = 1.00001 * min(gate, current 5th f), so whatever
@@ -474,6 +444,13 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
 // kept candidates are exactly the reference's five nearest (as a set; the fit kernel orders them by the exact (e, index)
 // key). Otherwise — a near tie between the 5th and the 6th, e.g. on quantised clouds — the query is searched again by
 // exact_search_one with the FP64 (e, index) order throughout.
+// The five winners leave the kernel as COORDINATES (five float4 planes, w = original map index): they are cache-hot here,
+// and the fit kernel then reads them coalesced instead of chasing five pointers per query.
+//
+// loam_fit_kernel — one query per thread, FP64: exact ordering of the five, gate, pivoted QR plane fit, residual, Jacobian.
+// No block barrier and no per-thread accumulators: a warp reduces its 32 contributions through a transposed shared-memory
+// tile (lane p owns one of the 28 sums), writes one partial per warp, and the warp that takes the last ticket of the scan
+// sums the partials in fixed order and runs the solve (bit-reproducible run to run).
 // ================================================================================================================
 struct RowGeom {  // per-query constants of the row walk (cells; same float key math as the build)
   int cx, cy, cz;
@@ -555,21 +532,40 @@ __device__ __noinline__ void exact_search_one(const GridView& grid, float qf0, f
   for (int k = 0; k < 5; k++) wj[k] = best[k].j;
 }
 
+constexpr int kRing1Rows = 9, kRing2Rows = 16;
+constexpr int kSearchRows = 16;  // row-list slots per thread (ring 1 uses 9 of them, ring 2 reuses all 16)
+constexpr size_t kSearchDynSmem = size_t(kSearchRows) * kLoamBlock * (sizeof(int4) + sizeof(float));
+
+// geometry of row k for a query: squared distance bound of the row, its (y, z) cell, validity
+__device__ __forceinline__ bool row_of(const GridSpec& g, const RowGeom& q, int k, float& row2, int& y, int& z) {
+  const int dy = c_row_dy[k], dz = c_row_dz[k];
+  // squared distance from the query to the row's (y, z) slab, shrunk by the cell-assignment slack
+  const float ay = fmaxf((dy == 0 ? 0.f : (dy > 0 ? float(dy) - q.fy : q.fy + float(-dy - 1))) - q.slk, 0.f);
+  const float az = fmaxf((dz == 0 ? 0.f : (dz > 0 ? float(dz) - q.fz : q.fz + float(-dz - 1))) - q.slk, 0.f);
+  row2 = (ay * ay + az * az) * q.h2;
+  y = q.cy + dy; z = q.cz + dz;
+  return y >= 0 && y < g.div_b[1] && z >= 0 && z < g.div_b[2];
+}
+
 __global__ void __launch_bounds__(kLoamBlock, 4)
 loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, GridView grid, LoamParams prm,
-                   const LoamState* __restrict__ states, double slack, int max_ring, int32_t* __restrict__ knn_buf, size_t knn_stride, int warm) {
+                   const LoamState* __restrict__ states, double slack, int max_ring, float4* __restrict__ nb_out, int2* __restrict__ cnt_out,
+                   size_t stride) {
   const int scan = blockIdx.y;
   const uint32_t begin = offs[scan], end = offs[scan + 1];
   const LoamState* st = states + scan;
   if (st->done) return;
   __shared__ double sT[16];
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  int4* s_run = reinterpret_cast<int4*>(s_dyn);                                         // [kSearchRows][kLoamBlock]: lo_wide, lo_narrow, hi_narrow, hi_wide
+  float* s_r2 = reinterpret_cast<float*>(s_dyn + size_t(kSearchRows) * kLoamBlock * sizeof(int4));  // [kSearchRows][kLoamBlock]
   if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
   __syncthreads();
+  const int tid = threadIdx.x;
   const GridSpec& g = grid.g;
   const double leaf = double(g.leaf[0]);
   const float gate_thr = float(prm.max_knn_d2) * 1.00001f;
-  const int NR = (2 * max_ring + 1) * (2 * max_ring + 1);
-  for (uint32_t i = begin + blockIdx.x * kLoamBlock + threadIdx.x; i < end; i += gridDim.x * kLoamBlock) {
+  for (uint32_t i = begin + blockIdx.x * kLoamBlock + tid; i < end; i += gridDim.x * kLoamBlock) {
     const float4 po = __ldg(src + i);
     // LoamRegister.cpp:128-130: ori = res * ori (double, ((R0 x + R1 y) + R2 z) + t*1), pointInMap = ori.cast<float>()
     const double ox = double(po.x), oy = double(po.y), oz = double(po.z);
@@ -585,20 +581,19 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
       const float fc = __fsub_rn(floorf(__fmul_rn(pmf[a], g.inv_leaf[a])), float(g.min_b[a]));
       if (!(fc >= float(-max_ring) && fc <= float(g.div_b[a] - 1 + max_ring))) near = false;  // the rings would not touch the grid
     }
-    int wj[5] = {-1, -1, -1, -1, -1};
+    int bj[5] = {-1, -1, -1, -1, -1};
     int ncand = 0, nrows = 0;
     if (near) {
       const float qf0 = pmf[0], qf1 = pmf[1], qf2 = pmf[2];
       const RowGeom q = row_geom(g, qf0, qf1, qf2, leaf, slack);
+      const float axh = q.ax2 * q.ax2 * q.h2;  // a row whose bound is below thr - axh only needs one x-cell either side
       float bf[5] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};  // five smallest f, ascending
-      int bj[5] = {-1, -1, -1, -1, -1};
       float f_out = INFINITY;  // smallest f that was examined but is not among the five
       float thr = gate_thr;
       auto consider = [&](const float4& m, int j) {
         const float ax = qf0 - m.x, ay = qf1 - m.y, az = qf2 - m.z;
         const float f = fmaf(az, az, fmaf(ay, ay, ax * ax));
         if (f <= thr) {
-          if (j == bj[0] || j == bj[1] || j == bj[2] || j == bj[3] || j == bj[4]) return;  // already kept (warm start)
           if (f < bf[4]) {  // branch-free sorted insertion; the old 5th drops out
             f_out = fminf(f_out, bf[4]);
             const bool p3 = f < bf[3], p2 = f < bf[2], p1 = f < bf[1], p0 = f < bf[0];
@@ -613,48 +608,233 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
           }
         }
       };
-      if (warm) {
-        // the five winners of the previous Gauss-Newton iteration (the pose moved a little): with them the bound starts at
-        // about the true 5th distance, so most rows are pruned before their table entries are even read. They are ordinary
-        // candidates — the kept set, its exactness test and the fallback are unaffected by where candidates come from.
-        int pj[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) pj[k] = knn_buf[size_t(k) * knn_stride + i];
-#pragma unroll
-        for (int k = 0; k < 5; k++)
-          if (pj[k] >= 0) { consider(__ldg(grid.pts + pj[k]), pj[k]); ncand++; }
-      }
+      // stage 2 of a ring: walk my own list of non-empty rows
+      auto walk = [&](int cnt) {
 #pragma unroll 1
-      for (int k = 0; k < NR; k++) {
-        if (k >= 9 && thr < q.ring2_min2) break;
-        int lo, hi;
-        if (!row_run(grid, q, k, thr, max_ring, lo, hi)) continue;
-        ncand += hi - lo;
-        nrows++;
+        for (int r = 0; r < cnt; r++) {
+          const float row2 = s_r2[r * kLoamBlock + tid];
+          if (row2 > thr) continue;  // every point of this row is farther than the current bound
+          const int4 e = s_run[r * kLoamBlock + tid];
+          const bool narrow = thr < row2 + axh;
+          const int lo = narrow ? e.y : e.x, hi = narrow ? e.z : e.w;
+          ncand += hi - lo;
+          nrows++;
 #pragma unroll 1
-        for (int j = lo; j < hi; j += 4) {  // four independent float4 loads in flight
-          const int rem = hi - j;
-          const float4 far = make_float4(INFINITY, 0.f, 0.f, 0.f);  // f = inf: never considered
-          const float4 m0 = __ldg(grid.pts + j);
-          const float4 m1 = rem > 1 ? __ldg(grid.pts + j + 1) : far;
-          const float4 m2 = rem > 2 ? __ldg(grid.pts + j + 2) : far;
-          const float4 m3 = rem > 3 ? __ldg(grid.pts + j + 3) : far;
-          consider(m0, j); consider(m1, j + 1); consider(m2, j + 2); consider(m3, j + 3);
+          for (int j = lo; j < hi; j += 4) {  // four independent float4 loads in flight
+            const int rem = hi - j;
+            const float4 far = make_float4(INFINITY, 0.f, 0.f, 0.f);  // f = inf: never considered
+            const float4 m0 = __ldg(grid.pts + j);
+            const float4 m1 = rem > 1 ? __ldg(grid.pts + j + 1) : far;
+            const float4 m2 = rem > 2 ? __ldg(grid.pts + j + 2) : far;
+            const float4 m3 = rem > 3 ? __ldg(grid.pts + j + 3) : far;
+            consider(m0, j); consider(m1, j + 1); consider(m2, j + 2); consider(m3, j + 3);
+          }
+        }
+      };
+      // x-extents of a row: wide = max_ring cells either side of the query's cell, narrow = one cell either side
+      const int xw0 = max(q.cx - max_ring, 0), xw1 = min(q.cx + max_ring, g.div_b[0] - 1);
+      const int xn0 = max(q.cx - 1, 0), xn1 = min(q.cx + 1, g.div_b[0] - 1);
+      const bool x_ok = xw0 <= xw1;
+      // ---- ring 1, stage 1: all nine rows' table entries in flight together
+      int cnt = 0;
+      if (x_ok) {
+        int4 e[kRing1Rows];
+        float r2[kRing1Rows];
+        bool ok[kRing1Rows];
+#pragma unroll
+        for (int k = 0; k < kRing1Rows; k++) {
+          int y, z;
+          ok[k] = row_of(g, q, k, r2[k], y, z) && r2[k] <= thr;
+          e[k] = make_int4(0, 0, 0, 0);
+          if (ok[k]) {
+            const int32_t* row = grid.start + ((long long)y * g.mul[1] + (long long)z * g.mul[2]);
+            e[k].x = __ldg(row + xw0); e[k].w = __ldg(row + xw1 + 1);
+            if (max_ring > 1 && xn0 <= xn1) { e[k].y = __ldg(row + xn0); e[k].z = __ldg(row + xn1 + 1); }
+            else { e[k].y = e[k].x; e[k].z = e[k].w; }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kRing1Rows; k++) {
+          if (ok[k] && e[k].w > e[k].x) {  // rows without a single map point never enter the list
+            s_run[cnt * kLoamBlock + tid] = e[k];
+            s_r2[cnt * kLoamBlock + tid] = r2[k];
+            cnt++;
+          }
         }
       }
+      walk(cnt);
+      // ---- ring 2 (half-gate cells only): needed while the bound still reaches past the first ring
+      if (max_ring > 1 && x_ok && !(thr < q.ring2_min2)) {
+        cnt = 0;
+        int2 e2[kRing2Rows];
+        float r2[kRing2Rows];
+        bool ok[kRing2Rows];
 #pragma unroll
-      for (int k = 0; k < 5; k++) wj[k] = bj[k];
+        for (int k = 0; k < kRing2Rows; k++) {
+          int y, z;
+          ok[k] = row_of(g, q, kRing1Rows + k, r2[k], y, z) && r2[k] <= thr;
+          e2[k] = make_int2(0, 0);
+          if (ok[k]) {
+            const int32_t* row = grid.start + ((long long)y * g.mul[1] + (long long)z * g.mul[2]);
+            const bool narrow = thr < r2[k] + axh && xn0 <= xn1;
+            e2[k].x = __ldg(row + (narrow ? xn0 : xw0));
+            e2[k].y = __ldg(row + (narrow ? xn1 : xw1) + 1);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kRing2Rows; k++) {
+          if (ok[k] && e2[k].y > e2[k].x) {
+            s_run[cnt * kLoamBlock + tid] = make_int4(e2[k].x, e2[k].x, e2[k].y, e2[k].y);
+            s_r2[cnt * kLoamBlock + tid] = r2[k];
+            cnt++;
+          }
+        }
+        walk(cnt);
+      }
       // a 6th candidate within 1e-6 (relative) of the 5th: the FP32 metric cannot tell which of them the reference keeps
       if (bj[4] >= 0 && !(f_out > bf[4] * 1.000001f)) {
         ncand = 0; nrows = 0;
-        exact_search_one(grid, qf0, qf1, qf2, leaf, slack, max_ring, gate_thr, wj, ncand, nrows);
+        exact_search_one(grid, qf0, qf1, qf2, leaf, slack, max_ring, gate_thr, bj, ncand, nrows);
       }
     }
+    // the winners' coordinates (cache-hot) + original map index; w = -1 marks an empty slot
 #pragma unroll
-    for (int k = 0; k < 5; k++) knn_buf[size_t(k) * knn_stride + i] = wj[k];
-    knn_buf[5 * knn_stride + i] = ncand;
-    knn_buf[6 * knn_stride + i] = nrows;
+    for (int k = 0; k < 5; k++) {
+      float4 m = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      if (bj[k] >= 0) m = __ldg(grid.pts + bj[k]);
+      nb_out[size_t(k) * stride + i] = m;
+    }
+    cnt_out[i] = make_int2(ncand, nrows);
   }
+}
+
+constexpr int kFitRow = 33;  // padded row of the transposed tile: lanes reading different rows hit different banks
+struct FitWarpTile { double v[7][kFitRow]; };
+
+template <bool DEBUG>
+__global__ void __launch_bounds__(kLoamBlock, 3)
+loam_fit_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, const float4* __restrict__ nb, const int2* __restrict__ cnt_in,
+                size_t stride, LoamParams prm, LoamState* __restrict__ states, double* __restrict__ partials, int max_warps,
+                pcr_loam_iter_log* __restrict__ logs, int apply_update, int32_t* __restrict__ dbg_knn, int32_t* __restrict__ dbg_status,
+                const uint32_t* __restrict__ qperm) {
+  const int scan = blockIdx.y;
+  const uint32_t begin = offs[scan], end = offs[scan + 1];
+  const uint32_t ns = end - begin;
+  LoamState* st = states + scan;
+  if (st->done) return;
+  __shared__ double sT[16];
+  __shared__ FitWarpTile s_tile[kLoamWarps];
+  __shared__ double stot[kNV];
+  __shared__ SolveScratch sc;
+  if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
+  __syncthreads();  // the only block barrier: warps are independent from here on
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t w0 = begin + (blockIdx.x * kLoamWarps + warp) * 32u;  // first query of this warp
+  if (w0 >= end) return;  // warps without a query take no ticket
+  const int n_warps = int((ns + 31) / 32);
+  const int gw = blockIdx.x * kLoamWarps + warp;  // warp index within the scan
+  const uint32_t i = w0 + lane;
+  const bool have = i < end;
+  double J[6] = {0, 0, 0, 0, 0, 0}, E = 0.0;
+  int status = -1;
+  int2 cn = make_int2(0, 0);
+  if (have) {
+    const float4 po = __ldg(src + i);
+    cn = __ldg(cnt_in + i);
+    double qd[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      // the same transform as the search kernel (LoamRegister.cpp:128-130), then the float cast and back
+      const double v = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(sT[r], double(po.x)), __dmul_rn(sT[4 + r], double(po.y))), __dmul_rn(sT[8 + r], double(po.z))), sT[12 + r]);
+      qd[r] = double(__double2float_rn(v));
+    }
+    float nx[5], ny[5], nz[5];
+    int nidx[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const float4 m = __ldg(nb + size_t(k) * stride + i);
+      nx[k] = m.x; ny[k] = m.y; nz[k] = m.z; nidx[k] = __float_as_int(m.w);
+    }
+    const bool five = nidx[4] >= 0;
+    double d5 = DBL_MAX;
+    if (five) {
+      // the search kernel selected the five on the FP32 metric (the SET is exact): order them by the exact FP64
+      // (d2, original index) key, the order nanoflann returns them in
+      unsigned long long ek[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const double dx = qd[0] - double(nx[k]), dyy = qd[1] - double(ny[k]), dzz = qd[2] - double(nz[k]);
+        ek[k] = (unsigned long long)__double_as_longlong(dx * dx + dyy * dyy + dzz * dzz);
+      }
+      auto cswap = [&](int a, int b) {  // compare-exchange, a < b
+        const bool sw = ek[b] < ek[a] || (ek[b] == ek[a] && nidx[b] < nidx[a]);
+        const unsigned long long te = sw ? ek[a] : ek[b]; ek[a] = sw ? ek[b] : ek[a]; ek[b] = te;
+        const float tx = sw ? nx[a] : nx[b]; nx[a] = sw ? nx[b] : nx[a]; nx[b] = tx;
+        const float ty = sw ? ny[a] : ny[b]; ny[a] = sw ? ny[b] : ny[a]; ny[b] = ty;
+        const float tz = sw ? nz[a] : nz[b]; nz[a] = sw ? nz[b] : nz[a]; nz[b] = tz;
+        const int ti = sw ? nidx[a] : nidx[b]; nidx[a] = sw ? nidx[b] : nidx[a]; nidx[b] = ti;
+      };
+      cswap(0, 1); cswap(3, 4); cswap(2, 4); cswap(2, 3); cswap(0, 3); cswap(0, 2); cswap(1, 4); cswap(1, 3); cswap(1, 2);  // 9-exchange network
+      d5 = __longlong_as_double((long long)ek[4]);
+    }
+    status = loam_point_residual(nx, ny, nz, five, d5, qd[0], qd[1], qd[2], po, prm, J, E);
+    if (DEBUG) {
+      const uint32_t iq = qperm ? __ldg(qperm + i) : i;  // original position of this query (queries are spatially re-ordered)
+      if (dbg_knn) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) dbg_knn[size_t(iq) * 5 + k] = status >= 1 ? nidx[k] : -1;
+      }
+      if (dbg_status) dbg_status[iq] = status;
+    }
+  }
+  // ---- warp reduction through the transposed tile: lane p owns sum p (21 J J^T, 6 J E, count, candidates, rows)
+  FitWarpTile& tl = s_tile[warp];
+  const bool acc = status == 3;
+#pragma unroll
+  for (int r = 0; r < 6; r++) tl.v[r][lane] = acc ? J[r] : 0.0;
+  tl.v[6][lane] = acc ? E : 0.0;
+  __syncwarp();
+  double sum = 0.0;
+  if (lane < 27) {
+    int ra, rb;
+    if (lane < 21) {  // packed upper triangle index -> (row, col)
+      int p = lane, r = 0;
+      while (p >= 6 - r) { p -= 6 - r; r++; }
+      ra = r; rb = r + p;
+    } else { ra = lane - 21; rb = 6; }
+    const double* a = tl.v[ra];
+    const double* b = tl.v[rb];
+#pragma unroll 8
+    for (int l = 0; l < 32; l++) sum += a[l] * b[l];
+  }
+  const unsigned n_acc = __popc(__ballot_sync(0xffffffffu, acc));
+  if (lane == 27) sum = double(n_acc);
+  const unsigned c_cand = __reduce_add_sync(0xffffffffu, unsigned(cn.x)), c_rows = __reduce_add_sync(0xffffffffu, unsigned(cn.y));
+  if (lane == 28) sum = double(c_cand);
+  if (lane == 29) sum = double(c_rows);
+  double* my = partials + (size_t(scan) * max_warps + gw) * kNV;
+  if (lane < kNV) my[lane] = sum;
+  __threadfence();
+  __syncwarp();
+  unsigned t = 0;
+  if (lane == 0) t = atomicAdd(&st->ticket, 1u);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t != unsigned(n_warps - 1)) return;
+  // ---- the last warp of the scan: fixed-order sum over the warp partials, then the solve
+  __threadfence();
+  if (lane < kNV) {
+    const double* base = partials + size_t(scan) * max_warps * kNV + lane;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // four interleaved chains, combined in a fixed order
+    int w = 0;
+    for (; w + 4 <= n_warps; w += 4) {
+      a0 += __ldcg(base + size_t(w) * kNV); a1 += __ldcg(base + size_t(w + 1) * kNV);
+      a2 += __ldcg(base + size_t(w + 2) * kNV); a3 += __ldcg(base + size_t(w + 3) * kNV);
+    }
+    for (; w < n_warps; w++) a0 += __ldcg(base + size_t(w) * kNV);
+    stot[lane] = (a0 + a1) + (a2 + a3);
+  }
+  __syncwarp();
+  loam_solve_step(stot, sT, st, logs, scan, prm, apply_update, ns, lane, sc);
 }
 
 // ---- query re-ordering: Morton code of the scan-frame position (0.25 m cells, +-128 m), scan index on top -----------
@@ -698,7 +878,7 @@ __global__ void loam_finalize_kernel(LoamState* states, int n_scans) {
 
 template <int LPQ, bool DEBUG>
 static void opt_in_one() {
-  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<LPQ, DEBUG, kModeFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
+  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<LPQ, DEBUG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
 }
 static void loam_opt_in_smem() {
   static bool done_dev[64] = {false};
@@ -708,8 +888,7 @@ static void loam_opt_in_smem() {
   if (done) return;
   opt_in_one<1, false>(); opt_in_one<2, false>(); opt_in_one<4, false>(); opt_in_one<8, false>();
   opt_in_one<1, true>(); opt_in_one<2, true>(); opt_in_one<4, true>(); opt_in_one<8, true>();
-  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<1, false, kModeFit>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
-  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_iter_kernel<1, true, kModeFit>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kLoamDynSmem)));
+  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSearchDynSmem)));
   done = true;
 }
 
@@ -737,8 +916,8 @@ static void launch_iter(int lpq, dim3 grid, cudaStream_t s, const float4* src, c
                         LoamState* states, double* partials, int max_blocks, pcr_loam_iter_log* logs, int apply, int tile, double slack,
                         int max_ring, int32_t* dbg_knn, int32_t* dbg_status) {
 #define PCR_LOAM_LAUNCH(L)                                                                                                                      \
-  loam_iter_kernel<L, DEBUG, kModeFused><<<grid, kLoamBlock, kLoamDynSmem, s>>>(src, offs, view, prm, states, partials, max_blocks, logs, apply, tile, \
-                                                                                slack, max_ring, dbg_knn, dbg_status, nullptr, 0, nullptr)
+  loam_iter_kernel<L, DEBUG><<<grid, kLoamBlock, kLoamDynSmem, s>>>(src, offs, view, prm, states, partials, max_blocks, logs, apply, tile, slack, \
+                                                                    max_ring, dbg_knn, dbg_status)
   switch (lpq) {
     case 1: PCR_LOAM_LAUNCH(1); break;
     case 2: PCR_LOAM_LAUNCH(2); break;
@@ -830,14 +1009,14 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
   const size_t per_block = size_t(kLoamWarps) * tile;
   int max_blocks = int((max_pts + per_block - 1) / per_block);
   max_blocks = std::max(1, std::min(max_blocks, int(size_t(kNumSMs) * 2 / n_scans)));  // all scans' blocks resident in one wave
-  // large batches (one lane per query, full tiles): search and fit as two kernels per iteration, see kModeSearch
+  // large batches (one lane per query, full tiles): search and fit as two kernels per iteration ("Batch path" above)
   const bool split = lpq == 1 && tile == 32 && env_int("PCR_LOAM_SPLIT", 1) != 0;
-  // the fit kernel is a long dependent FP64 chain per query (pivoted QR: ~9 us): one query per thread over as many blocks
-  // as it takes, instead of a single resident wave in which every thread walks through a dozen queries one after the other
-  if (split) max_blocks = std::max(1, int((max_pts + per_block - 1) / per_block));
+  // the fit kernel: one query per thread, one partial per warp
+  const int fit_blocks = std::max(1, int((max_pts + kLoamBlock - 1) / kLoamBlock));
+  const int max_warps = fit_blocks * kLoamWarps;
   states.ensure(n_scans);
   offsets.ensure(n_scans + 1);
-  partials.ensure(n_scans * size_t(max_blocks) * kNV);
+  partials.ensure(n_scans * size_t(split ? max_warps : max_blocks) * kNV);
   logs.ensure(n_scans * size_t(prm.max_iters));
   PCR_CUDA_CHECK(cudaMemcpyAsync(states.p, hs, n_scans * sizeof(LoamState), cudaMemcpyHostToDevice, s));
   PCR_CUDA_CHECK(cudaMemcpyAsync(offsets.p, ho, (n_scans + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
@@ -852,17 +1031,18 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     const float4* q = src;
     const uint32_t* perm = nullptr;
     if (split) {
-      knn_buf.ensure(7 * total_q);
+      nb_buf.ensure(5 * total_q);
+      cnt_buf.ensure(total_q);
       q = sort_queries(src, offsets.p, n_scans, total_q, max_pts, &perm, s);
     }
     const size_t search_pb = size_t(kLoamWarps) * 32;
     const dim3 sgrid(unsigned((max_pts + search_pb - 1) / search_pb), unsigned(n_scans));
+    const dim3 fgrid(static_cast<unsigned>(fit_blocks), static_cast<unsigned>(n_scans));
     for (int it = 0; it < prm.max_iters; it++) {
       if (split) {
-        loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, knn_buf.p, total_q,
-                                                        (it > 0 && env_int("PCR_LOAM_WARM", 1) != 0) ? 1 : 0);
-        loam_iter_kernel<1, false, kModeFit><<<gridDim, kLoamBlock, kLoamDynSmem, s>>>(q, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 1,
-                                                                                      32, slack, grid.max_ring, nullptr, nullptr, knn_buf.p, total_q, perm);
+        loam_search_kernel<<<sgrid, kLoamBlock, kSearchDynSmem, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
+        loam_fit_kernel<false><<<fgrid, kLoamBlock, 0, s>>>(q, offsets.p, nb_buf.p, cnt_buf.p, total_q, prm, states.p, partials.p, max_warps, logs.p, 1,
+                                                            nullptr, nullptr, perm);
         launches += 2;
       } else {
         launch_iter<false>(lpq, gridDim, s, src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 1, tile, slack, grid.max_ring, nullptr, nullptr);
@@ -922,14 +1102,17 @@ int LoamDriver::linearize(const float4* src, size_t ns, const CellGrid& grid, co
   if (ns > 0 && grid.built && grid.has_start) {
     GridView view = make_view(grid);
     if (split) {
-      knn_buf.ensure(7 * ns);
+      nb_buf.ensure(5 * ns);
+      cnt_buf.ensure(ns);
       const uint32_t* perm = nullptr;
       const float4* q = sort_queries(src, offsets.p, 1, ns, ns, &perm, s);
       const size_t search_pb = size_t(kLoamWarps) * 32;
       const dim3 sgrid(unsigned((ns + search_pb - 1) / search_pb), 1);
-      loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, knn_buf.p, ns, 0);
-      loam_iter_kernel<1, true, kModeFit><<<dim3(max_blocks, 1), kLoamBlock, kLoamDynSmem, s>>>(q, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p,
-                                                                                               0, 32, slack, grid.max_ring, dbg_knn.p, dbg_status.p, knn_buf.p, ns, perm);
+      const int fit_blocks = std::max(1, int((ns + kLoamBlock - 1) / kLoamBlock));
+      partials.ensure(size_t(fit_blocks) * kLoamWarps * kNV);
+      loam_search_kernel<<<sgrid, kLoamBlock, kSearchDynSmem, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, ns);
+      loam_fit_kernel<true><<<dim3(fit_blocks, 1), kLoamBlock, 0, s>>>(q, offsets.p, nb_buf.p, cnt_buf.p, ns, prm, states.p, partials.p, fit_blocks * kLoamWarps,
+                                                                       logs.p, 0, dbg_knn.p, dbg_status.p, perm);
       last_split = true;
     } else {
       launch_iter<true>(lpq, dim3(max_blocks, 1), s, src, offsets.p, view, prm, states.p, partials.p, max_blocks, logs.p, 0, tile, slack,

@@ -32,7 +32,8 @@ struct LoamDriver {
   DevBuf<pcr_loam_iter_log> logs;
   DevBuf<uint32_t> offsets;
   DevBuf<int32_t> dbg_knn, dbg_status;
-  DevBuf<int32_t> knn_buf;  // split mode: 5 winners + 2 counters per query (seven planes)
+  DevBuf<float4> nb_buf;    // batch path: the five winners of every query as coordinates (five planes, w = original map index)
+  DevBuf<int2> cnt_buf;     // batch path: candidates examined / rows walked per query
   // split mode: queries re-ordered along a Morton curve of their scan-frame position (once per call)
   DevBuf<unsigned long long> q_keys0, q_keys1;
   DevBuf<uint32_t> q_vals0, q_vals1;
