@@ -9,8 +9,10 @@
 
 #if defined(__CUDACC__)
 #define PCR_HM __host__ __device__ inline
+#define PCR_HM_NOINLINE inline __host__ __device__ __noinline__  // own register allocation on the device (single-thread tails)
 #else
 #define PCR_HM inline
+#define PCR_HM_NOINLINE inline
 #endif
 
 namespace pcr {
@@ -45,11 +47,11 @@ PCR_HM float atan2_f32(float y, float x) {
 #endif
 }
 
-// Eigen::AngleAxisf(angle, UnitAxis).toRotationMatrix(), float (Eigen/src/Geometry/AngleAxis.h algorithm)
-PCR_HM void axis_rotation_f32(float angle, int axis, float R[9]) {
+// Eigen::AngleAxisf(angle, UnitAxis).toRotationMatrix(), float (Eigen/src/Geometry/AngleAxis.h algorithm), from the sine and
+// cosine of the angle (so that the device can evaluate the six trigonometric functions of a pose in parallel lanes)
+PCR_HM void axis_rotation_sc_f32(float sn, float cs, int axis, float R[9]) {
   float u[3] = {0.f, 0.f, 0.f};
   u[axis] = 1.f;
-  const float sn = sin_f32(angle), cs = cos_f32(angle);
   float su[3], cu[3];
   for (int i = 0; i < 3; i++) { su[i] = sn * u[i]; cu[i] = (1.f - cs) * u[i]; }
   float t;
@@ -58,6 +60,7 @@ PCR_HM void axis_rotation_f32(float angle, int axis, float R[9]) {
   t = cu[1] * u[2]; R[1 * 3 + 2] = t - su[0]; R[2 * 3 + 1] = t + su[0];
   for (int i = 0; i < 3; i++) R[i * 3 + i] = cu[i] * u[i] + cs;
 }
+PCR_HM void axis_rotation_f32(float angle, int axis, float R[9]) { axis_rotation_sc_f32(sin_f32(angle), cos_f32(angle), axis, R); }
 
 PCR_HM void mul3_f32(const float* A, const float* B, float* C) {
   float t[9];
@@ -67,12 +70,12 @@ PCR_HM void mul3_f32(const float* A, const float* B, float* C) {
 }
 
 // (Translation3f(p0,p1,p2) * AngleAxisf(p3, X) * AngleAxisf(p4, Y) * AngleAxisf(p5, Z)).matrix() — ndt_omp_impl.hpp:827-830.
-// M: column-major float[16].
-PCR_HM void ndt_pose_matrix_f32(const double p[6], float M[16]) {
+// M: column-major float[16]. sc = {sin p3, cos p3, sin p4, cos p4, sin p5, cos p5} of the angles cast to float.
+PCR_HM void ndt_pose_matrix_sc_f32(const double p[6], const float sc[6], float M[16]) {
   float Rx[9], Ry[9], Rz[9], L[9];
-  axis_rotation_f32(static_cast<float>(p[3]), 0, Rx);
-  axis_rotation_f32(static_cast<float>(p[4]), 1, Ry);
-  axis_rotation_f32(static_cast<float>(p[5]), 2, Rz);
+  axis_rotation_sc_f32(sc[0], sc[1], 0, Rx);
+  axis_rotation_sc_f32(sc[2], sc[3], 1, Ry);
+  axis_rotation_sc_f32(sc[4], sc[5], 2, Rz);
   mul3_f32(Rx, Ry, L);
   mul3_f32(L, Rz, L);
   for (int i = 0; i < 16; i++) M[i] = 0.f;
@@ -81,6 +84,11 @@ PCR_HM void ndt_pose_matrix_f32(const double p[6], float M[16]) {
     M[12 + r] = static_cast<float>(p[r]);
   }
   M[15] = 1.f;
+}
+PCR_HM void ndt_pose_matrix_f32(const double p[6], float M[16]) {
+  float sc[6];
+  for (int a = 0; a < 3; a++) { const float ang = static_cast<float>(p[3 + a]); sc[2 * a] = sin_f32(ang); sc[2 * a + 1] = cos_f32(ang); }
+  ndt_pose_matrix_sc_f32(p, sc, M);
 }
 
 // Matrix3f::eulerAngles(0,1,2), Eigen 3.3 convention (first angle in [0, pi] before the final sign flip).
@@ -102,45 +110,52 @@ PCR_HM void euler_xyz_f32(const float R[9], float e[3]) {
 }
 
 // computeAngleDerivatives (ndt_omp_impl.hpp:289-395). jf/hf: float tables used by computeDerivatives (hf row 6 has
-// +sy, :383); jd/hd: double tables used by computeHessian (-sy, :361).
+// +sy, :383); jd/hd: double tables used by computeHessian (-sy, :361). The sine / cosine of an angle below 10e-5 are
+// replaced by 0 / 1 (:293-322): ndt_angle_trig applies that rule, ndt_angle_tables_trig builds the tables from the six values.
+PCR_HM void ndt_angle_trig(double angle, double& c, double& s) {
+  if (fabs(angle) < 10e-5) { c = 1.0; s = 0.0; } else { c = cos(angle); s = sin(angle); }
+}
+PCR_HM void ndt_angle_tables_trig(double cx, double cy, double cz, double sx, double sy, double sz, float jf[8][3], float hf[15][3], double jd[8][3],
+                                  double hd[15][3]) {
+#define PCR_ROW(T, r, a, b, c) { const double v0 = (a), v1 = (b), v2 = (c); T##d[r][0] = v0; T##d[r][1] = v1; T##d[r][2] = v2; \
+                                 T##f[r][0] = static_cast<float>(v0); T##f[r][1] = static_cast<float>(v1); T##f[r][2] = static_cast<float>(v2); }
+  PCR_ROW(j, 0, (-sx * sz + cx * sy * cz), (-sx * cz - cx * sy * sz), (-cx * cy))
+  PCR_ROW(j, 1, (cx * sz + sx * sy * cz), (cx * cz - sx * sy * sz), (-sx * cy))
+  PCR_ROW(j, 2, (-sy * cz), sy * sz, cy)
+  PCR_ROW(j, 3, sx * cy * cz, (-sx * cy * sz), sx * sy)
+  PCR_ROW(j, 4, (-cx * cy * cz), cx * cy * sz, (-cx * sy))
+  PCR_ROW(j, 5, (-cy * sz), (-cy * cz), 0.0)
+  PCR_ROW(j, 6, (cx * cz - sx * sy * sz), (-cx * sz - sx * sy * cz), 0.0)
+  PCR_ROW(j, 7, (sx * cz + cx * sy * sz), (cx * sy * cz - sx * sz), 0.0)
+  PCR_ROW(h, 0, (-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), sx * cy)     // a2
+  PCR_ROW(h, 1, (-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), (-cx * cy))  // a3
+  PCR_ROW(h, 2, (cx * cy * cz), (-cx * cy * sz), (cx * sy))                        // b2
+  PCR_ROW(h, 3, (sx * cy * cz), (-sx * cy * sz), (sx * sy))                        // b3
+  PCR_ROW(h, 4, (-sx * cz - cx * sy * sz), (sx * sz - cx * sy * cz), 0.0)          // c2
+  PCR_ROW(h, 5, (cx * cz - sx * sy * sz), (-sx * sy * cz - cx * sz), 0.0)          // c3
+  PCR_ROW(h, 6, (-cy * cz), (cy * sz), (-sy))                                      // d1 (double table)
+  PCR_ROW(h, 7, (-sx * sy * cz), (sx * sy * sz), (sx * cy))                        // d2
+  PCR_ROW(h, 8, (cx * sy * cz), (-cx * sy * sz), (-cx * cy))                       // d3
+  PCR_ROW(h, 9, (sy * sz), (sy * cz), 0.0)                                         // e1
+  PCR_ROW(h, 10, (-sx * cy * sz), (-sx * cy * cz), 0.0)                            // e2
+  PCR_ROW(h, 11, (cx * cy * sz), (cx * cy * cz), 0.0)                              // e3
+  PCR_ROW(h, 12, (-cy * cz), (cy * sz), 0.0)                                       // f1
+  PCR_ROW(h, 13, (-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), 0.0)        // f2
+  PCR_ROW(h, 14, (-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), 0.0)        // f3
+#undef PCR_ROW
+  hf[6][2] = static_cast<float>(sy);
+}
 PCR_HM void ndt_angle_tables(const double p[6], float jf[8][3], float hf[15][3], double jd[8][3], double hd[15][3]) {
   double cx, cy, cz, sx, sy, sz;
-  if (fabs(p[3]) < 10e-5) { cx = 1.0; sx = 0.0; } else { cx = cos(p[3]); sx = sin(p[3]); }
-  if (fabs(p[4]) < 10e-5) { cy = 1.0; sy = 0.0; } else { cy = cos(p[4]); sy = sin(p[4]); }
-  if (fabs(p[5]) < 10e-5) { cz = 1.0; sz = 0.0; } else { cz = cos(p[5]); sz = sin(p[5]); }
-  const double j[8][3] = {{(-sx * sz + cx * sy * cz), (-sx * cz - cx * sy * sz), (-cx * cy)},
-                          {(cx * sz + sx * sy * cz), (cx * cz - sx * sy * sz), (-sx * cy)},
-                          {(-sy * cz), sy * sz, cy},
-                          {sx * cy * cz, (-sx * cy * sz), sx * sy},
-                          {(-cx * cy * cz), cx * cy * sz, (-cx * sy)},
-                          {(-cy * sz), (-cy * cz), 0},
-                          {(cx * cz - sx * sy * sz), (-cx * sz - sx * sy * cz), 0},
-                          {(sx * cz + cx * sy * sz), (cx * sy * cz - sx * sz), 0}};
-  const double h[15][3] = {{(-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), sx * cy},    // a2
-                           {(-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), (-cx * cy)}, // a3
-                           {(cx * cy * cz), (-cx * cy * sz), (cx * sy)},                       // b2
-                           {(sx * cy * cz), (-sx * cy * sz), (sx * sy)},                       // b3
-                           {(-sx * cz - cx * sy * sz), (sx * sz - cx * sy * cz), 0},           // c2
-                           {(cx * cz - sx * sy * sz), (-sx * sy * cz - cx * sz), 0},           // c3
-                           {(-cy * cz), (cy * sz), (-sy)},                                     // d1 (double table)
-                           {(-sx * sy * cz), (sx * sy * sz), (sx * cy)},                       // d2
-                           {(cx * sy * cz), (-cx * sy * sz), (-cx * cy)},                      // d3
-                           {(sy * sz), (sy * cz), 0},                                          // e1
-                           {(-sx * cy * sz), (-sx * cy * cz), 0},                              // e2
-                           {(cx * cy * sz), (cx * cy * cz), 0},                                // e3
-                           {(-cy * cz), (cy * sz), 0},                                         // f1
-                           {(-cx * sz - sx * sy * cz), (-cx * cz + sx * sy * sz), 0},          // f2
-                           {(-sx * sz + cx * sy * cz), (-cx * sy * sz - sx * cz), 0}};         // f3
-  for (int r = 0; r < 8; r++)
-    for (int c = 0; c < 3; c++) { jd[r][c] = j[r][c]; jf[r][c] = static_cast<float>(j[r][c]); }
-  for (int r = 0; r < 15; r++)
-    for (int c = 0; c < 3; c++) { hd[r][c] = h[r][c]; hf[r][c] = static_cast<float>(h[r][c]); }
-  hf[6][2] = static_cast<float>(sy);
+  ndt_angle_trig(p[3], cx, sx);
+  ndt_angle_trig(p[4], cy, sy);
+  ndt_angle_trig(p[5], cz, sz);
+  ndt_angle_tables_trig(cx, cy, cz, sx, sy, sz, jf, hf, jd, hd);
 }
 
 // x = V_r S_r^-1 U_r^T b of a 6x6 matrix via one-sided Jacobi SVD with Eigen's rank threshold —
 // Eigen::JacobiSVD<Matrix6d>(H, FullU|FullV).solve(b) at ndt_omp_impl.hpp:127-129.
-PCR_HM void svd6_solve(const double* Arow, const double* b, double* x) {
+PCR_HM_NOINLINE void svd6_solve(const double* Arow, const double* b, double* x) {
   const int N = 6;
   double U[6][6], V[6][6];
   for (int i = 0; i < N; i++)
@@ -195,33 +210,48 @@ PCR_HM void svd6_solve(const double* Arow, const double* b, double* x) {
 // elimination above 1e-10 of the largest one — Eigen's truncation only starts at singular values below 6 eps of the
 // largest) JacobiSVD::solve is H^-1 b, which the elimination delivers in ~150 dependent flops instead of ~10^4; a
 // (near-)singular H falls back to the Jacobi SVD above, truncation rule included.
-PCR_HM void solve6_newton(const double* Arow, const double* b, double* x) {
+PCR_HM_NOINLINE void solve6_newton(const double* Arow, const double* b, double* x) {
+  // fully unrolled with static indices (partial pivoting through conditional row swaps): everything stays in registers
   double M[6][7];
   double amax = 0.0;
+#pragma unroll
   for (int i = 0; i < 6; i++) {
+#pragma unroll
     for (int j = 0; j < 6; j++) { M[i][j] = Arow[i * 6 + j]; const double a = fabs(M[i][j]); amax = a > amax ? a : amax; }
     M[i][6] = b[i];
   }
   bool ok = amax > 0.0 && amax == amax && amax < DBL_MAX;
-  for (int k = 0; k < 6 && ok; k++) {
-    int piv = k;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
     double pv = fabs(M[k][k]);
-    for (int i = k + 1; i < 6; i++) { const double a = fabs(M[i][k]); if (a > pv) { pv = a; piv = i; } }
-    if (!(pv > 1e-10 * amax)) { ok = false; break; }
-    if (piv != k)
-      for (int j = k; j < 7; j++) { const double t = M[k][j]; M[k][j] = M[piv][j]; M[piv][j] = t; }
+#pragma unroll
+    for (int i = k + 1; i < 6; i++) {  // bring the largest remaining entry of column k into row k (first maximum wins)
+      const double a = fabs(M[i][k]);
+      const bool sw = a > pv;
+      pv = sw ? a : pv;
+#pragma unroll
+      for (int j = k; j < 7; j++) { const double t = M[k][j]; M[k][j] = sw ? M[i][j] : t; M[i][j] = sw ? t : M[i][j]; }
+    }
+    if (!(pv > 1e-10 * amax)) ok = false;
     const double inv = 1.0 / M[k][k];
+#pragma unroll
     for (int i = k + 1; i < 6; i++) {
       const double f = M[i][k] * inv;
+#pragma unroll
       for (int j = k + 1; j < 7; j++) M[i][j] -= f * M[k][j];
     }
   }
   if (!ok) { svd6_solve(Arow, b, x); return; }
+  double y[6];
+#pragma unroll
   for (int i = 5; i >= 0; i--) {
     double v = M[i][6];
-    for (int j = i + 1; j < 6; j++) v -= M[i][j] * x[j];
-    x[i] = v / M[i][i];
+#pragma unroll
+    for (int j = i + 1; j < 6; j++) v -= M[i][j] * y[j];
+    y[i] = v / M[i][i];
   }
+#pragma unroll
+  for (int i = 0; i < 6; i++) x[i] = y[i];
 }
 
 // ---- More-Thuente helpers (ndt_omp_impl.hpp:649-769, ndt_omp.h:430-447) ----

@@ -152,9 +152,18 @@ __device__ __forceinline__ void knn_scan_run(WarpKnn& st, const float4* __restri
       idx = __float_as_int(m.w);
       pass = d2 < st.td || (d2 == st.td && idx < st.ti);
     }
+    if (st.cnt == 0 && hi - base <= k) {
+      // first chunk of a search and it fits: the lanes simply keep their own candidates (the kept set is unsorted anyway)
+      const int valid = hi - base;
+      st.cnt = valid;
+      st.bd = lane < valid ? d2 : INFINITY;
+      st.bi = lane < valid ? idx : 0x7fffffff;
+      if (valid == k) knn_refresh_threshold(st, k, lane);
+      continue;
+    }
     if (st.cnt == 0) {
-      // first chunk of a search: the list is empty, so instead of up to 32 serial insertions sort the chunk with a warp
-      // bitonic network on (d2, index) and adopt its k smallest
+      // first chunk of a search, more candidates than slots: instead of up to 32 serial insertions sort the chunk with a
+      // warp bitonic network on (d2, index) and adopt its k smallest
       float d = j < hi ? d2 : INFINITY;
       int id = j < hi ? idx : 0x7fffffff;
       knn_bitonic_sort(d, id, lane);

@@ -533,8 +533,11 @@ __device__ __noinline__ void exact_search_one(const GridView& grid, float qf0, f
 }
 
 constexpr int kRing1Rows = 9, kRing2Rows = 16;
-constexpr int kSearchRows = 16;  // row-list slots per thread (ring 1 uses 9 of them, ring 2 reuses all 16)
-constexpr size_t kSearchDynSmem = size_t(kSearchRows) * kLoamBlock * (sizeof(int4) + sizeof(float));
+// row list of a thread in shared memory: per row the run [lo, hi) of the wide x-extent and, for half-gate grids, of the narrow
+// one (two int2 slots); ring 2 (16 rows, one extent each) reuses the same slots. 53 KB per block: four blocks per SM.
+constexpr int kSearchRunSlots = 2 * kRing1Rows;  // >= kRing2Rows
+constexpr int kSearchR2Slots = kRing2Rows;
+constexpr size_t kSearchDynSmem = size_t(kLoamBlock) * (kSearchRunSlots * sizeof(int2) + kSearchR2Slots * sizeof(float));
 
 // geometry of row k for a query: squared distance bound of the row, its (y, z) cell, validity
 __device__ __forceinline__ bool row_of(const GridSpec& g, const RowGeom& q, int k, float& row2, int& y, int& z) {
@@ -557,8 +560,8 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
   if (st->done) return;
   __shared__ double sT[16];
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  int4* s_run = reinterpret_cast<int4*>(s_dyn);                                         // [kSearchRows][kLoamBlock]: lo_wide, lo_narrow, hi_narrow, hi_wide
-  float* s_r2 = reinterpret_cast<float*>(s_dyn + size_t(kSearchRows) * kLoamBlock * sizeof(int4));  // [kSearchRows][kLoamBlock]
+  int2* s_run = reinterpret_cast<int2*>(s_dyn);                                                          // [slot][kLoamBlock]
+  float* s_r2 = reinterpret_cast<float*>(s_dyn + size_t(kSearchRunSlots) * kLoamBlock * sizeof(int2));   // [row][kLoamBlock]
   if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
   __syncthreads();
   const int tid = threadIdx.x;
@@ -608,15 +611,15 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
           }
         }
       };
-      // stage 2 of a ring: walk my own list of non-empty rows
-      auto walk = [&](int cnt) {
+      // stage 2 of a ring: walk my own list of non-empty rows. two_runs: slot 2r = wide run, slot 2r + 1 = narrow run
+      auto walk = [&](int cnt, bool two_runs) {
 #pragma unroll 1
         for (int r = 0; r < cnt; r++) {
           const float row2 = s_r2[r * kLoamBlock + tid];
           if (row2 > thr) continue;  // every point of this row is farther than the current bound
-          const int4 e = s_run[r * kLoamBlock + tid];
-          const bool narrow = thr < row2 + axh;
-          const int lo = narrow ? e.y : e.x, hi = narrow ? e.z : e.w;
+          const int slot = two_runs ? 2 * r + ((thr < row2 + axh) ? 1 : 0) : r;
+          const int2 e = s_run[slot * kLoamBlock + tid];
+          const int lo = e.x, hi = e.y;
           ncand += hi - lo;
           nrows++;
 #pragma unroll 1
@@ -656,13 +659,18 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
 #pragma unroll
         for (int k = 0; k < kRing1Rows; k++) {
           if (ok[k] && e[k].w > e[k].x) {  // rows without a single map point never enter the list
-            s_run[cnt * kLoamBlock + tid] = e[k];
+            if (max_ring > 1) {
+              s_run[(2 * cnt) * kLoamBlock + tid] = make_int2(e[k].x, e[k].w);
+              s_run[(2 * cnt + 1) * kLoamBlock + tid] = make_int2(e[k].y, e[k].z);
+            } else {
+              s_run[cnt * kLoamBlock + tid] = make_int2(e[k].x, e[k].w);
+            }
             s_r2[cnt * kLoamBlock + tid] = r2[k];
             cnt++;
           }
         }
       }
-      walk(cnt);
+      walk(cnt, max_ring > 1);
       // ---- ring 2 (half-gate cells only): needed while the bound still reaches past the first ring
       if (max_ring > 1 && x_ok && !(thr < q.ring2_min2)) {
         cnt = 0;
@@ -684,12 +692,12 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
 #pragma unroll
         for (int k = 0; k < kRing2Rows; k++) {
           if (ok[k] && e2[k].y > e2[k].x) {
-            s_run[cnt * kLoamBlock + tid] = make_int4(e2[k].x, e2[k].x, e2[k].y, e2[k].y);
+            s_run[cnt * kLoamBlock + tid] = e2[k];
             s_r2[cnt * kLoamBlock + tid] = r2[k];
             cnt++;
           }
         }
-        walk(cnt);
+        walk(cnt, false);
       }
       // a 6th candidate within 1e-6 (relative) of the 5th: the FP32 metric cannot tell which of them the reference keeps
       if (bj[4] >= 0 && !(f_out > bf[4] * 1.000001f)) {

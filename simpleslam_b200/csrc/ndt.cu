@@ -317,7 +317,36 @@ __device__ __forceinline__ void ndt_pair_f64(const NdtTargetView& tgt, int id, c
 // ================================================================================================================
 constexpr int kNdtMaxBatch = 2048;  // scans per driver chunk (request list lives in shared memory)
 
+static_assert(sizeof(NdtScanState) % 16 == 0, "NdtScanState is copied as uint4 words");
+
 __device__ __noinline__ void ndt_state_step(NdtScanState* st, const double* totals, NdtCfg cfg) { ndt_logic::on_result(*st, totals, cfg); }
+
+// ndt_logic::fill_request by the lanes of one warp: the six double and six float sines / cosines of the next evaluation's
+// angles are evaluated by twelve lanes at once, then one lane assembles the angular derivative tables and another the float
+// pose matrix — the same host_math.hpp functions on the same values as the serial version, a few microseconds shorter per
+// evaluation round (the tail of the last block is on the critical path of every round).
+__device__ __forceinline__ void ndt_fill_request_warp(NdtScanState* st, double* trig /* shared, 12 doubles */, int lane) {
+  if (st->pend == NDT_PEND_NONE) return;  // warp-uniform (shared state)
+  if (lane < 3) {
+    double c, s;
+    hm::ndt_angle_trig(st->eval_p[3 + lane], c, s);
+    trig[lane] = c; trig[3 + lane] = s;
+  } else if (lane < 6 && st->fill_matrix) {
+    const float ang = static_cast<float>(st->eval_p[lane]);  // lane 3..5 -> angle index 3..5
+    trig[6 + 2 * (lane - 3)] = double(hm::sin_f32(ang));
+    trig[7 + 2 * (lane - 3)] = double(hm::cos_f32(ang));
+  }
+  __syncwarp();
+  if (lane == 0) {
+    hm::ndt_angle_tables_trig(trig[0], trig[1], trig[2], trig[3], trig[4], trig[5], st->next.j_ang, st->next.h_ang, st->next.j_ang_d, st->next.h_ang_d);
+  } else if (lane == 1 && st->fill_matrix) {
+    const float sc[6] = {float(trig[6]), float(trig[7]), float(trig[8]), float(trig[9]), float(trig[10]), float(trig[11])};
+    hm::ndt_pose_matrix_sc_f32(st->eval_p, sc, st->final_T);
+  }
+  __syncwarp();
+  if (lane < 16) st->next.Tf[lane] = st->final_T[lane];
+  __syncwarp();
+}
 
 template <int SEARCH, bool DOUBLE_PATH>
 __global__ void __launch_bounds__(kNdtBlock, DOUBLE_PATH ? 2 : 5)
@@ -334,6 +363,7 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
   __shared__ __align__(16) NdtScanState s_state;
   __shared__ double sacc[kNdtNV * kNdtBlock];
   __shared__ double s_tot[kNdtNV + 1];
+  __shared__ double s_trig[12];
   __shared__ unsigned short s_list[kNdtMaxBatch];
   __shared__ int s_warp_cnt[kNdtBlock / 32];
   __shared__ int s_last;
@@ -511,7 +541,11 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     if (tid == 0) {
       tickets[scan] = 0;
       atomicAdd(reinterpret_cast<unsigned long long*>(&counters->point_evals), (unsigned long long)(end - begin));
-      if (step) ndt_state_step(&s_state, s_tot, cfg);
+    }
+    if (step && warp == 0) {
+      if (lane == 0) ndt_state_step(&s_state, s_tot, cfg);  // decides the next evaluation ...
+      __syncwarp();
+      ndt_fill_request_warp(&s_state, s_trig, lane);          // ... whose transform and derivative tables the warp fills in
     }
     __syncthreads();
     if (step) {
@@ -553,6 +587,7 @@ __global__ void ndt_init_kernel(const double* __restrict__ guesses, const uint32
     for (int k = 0; k < kNdtNV; k++) zeros[k] = 0.0;
     while (st.pend != NDT_PEND_NONE) ndt_logic::on_result(st, zeros, cfg);
   }
+  ndt_logic::fill_request(st);
   states[s] = st;
   if (st.pend == NDT_PEND_NONE) {
     float_round[s] = -1;

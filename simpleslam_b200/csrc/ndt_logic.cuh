@@ -39,8 +39,9 @@ struct NdtScanState {
   int step_iterations;
   int interval_converged, open_interval;
   int n_evals, n_hess;
-  int pad;
+  int fill_matrix;       // the pending request's transform has to be rebuilt from eval_p (a line-search trial), see fill_request
   long long n_pairs;
+  double eval_p[6];      // transform vector of the pending evaluation
   double p[6];
   double score;
   double g[6];
@@ -55,12 +56,22 @@ namespace ndt_logic {
 constexpr double kMu = 1.e-4, kNu = 0.9;   // ndt_omp_impl.hpp:800-802
 constexpr int kMaxStepIterations = 10;      // :786
 
-PCR_HM void request(NdtScanState& st, const float* T, const double* p, int kind, int hess) {
-  for (int i = 0; i < 16; i++) st.next.Tf[i] = T[i];
-  hm::ndt_angle_tables(p, st.next.j_ang, st.next.h_ang, st.next.j_ang_d, st.next.h_ang_d);
+// The control flow only DECIDES the next evaluation (its transform vector, kind, flags); the trigonometry behind its float
+// pose matrix and its angular derivative tables is done by fill_request — serially here (host, tests), by parallel lanes in
+// the kernel tail (ndt.cu: ndt_fill_request_warp, same functions on the same values).
+PCR_HM void request(NdtScanState& st, const double* p, int kind, int hess, int rebuild_matrix) {
+  for (int i = 0; i < 6; i++) st.eval_p[i] = p[i];
+  st.fill_matrix = rebuild_matrix;
   st.next.compute_hessian = hess;
   st.next.kind = kind;
   st.pend = kind == 0 ? NDT_PEND_FLOAT : NDT_PEND_DOUBLE;
+}
+
+PCR_HM void fill_request(NdtScanState& st) {
+  if (st.pend == NDT_PEND_NONE) return;
+  if (st.fill_matrix) hm::ndt_pose_matrix_f32(st.eval_p, st.final_T);  // :827-830 / :866-869 final_transformation_ of the trial
+  for (int i = 0; i < 16; i++) st.next.Tf[i] = st.final_T[i];
+  hm::ndt_angle_tables(st.eval_p, st.next.j_ang, st.next.h_ang, st.next.j_ang_d, st.next.h_ang_d);
 }
 
 PCR_HM void finish(NdtScanState& st) {
@@ -94,7 +105,7 @@ PCR_HM void start(NdtScanState& st, const double* Tguess, int scan) {
   st.phase = NDT_INIT_EVAL;
   st.next.scan = scan;
   st.next.pad = 0;
-  request(st, st.final_T, st.p, 0, 1);
+  request(st, st.p, 0, 1, 0);  // the first evaluation runs at the guess itself (:95-101), not at a matrix rebuilt from p
 }
 
 PCR_HM void take(NdtScanState& st, const double* v, bool with_hessian) {
@@ -109,7 +120,6 @@ PCR_HM void set_trial(NdtScanState& st, const NdtCfg& cfg) {
   st.a_t = hm::std_min(st.a_t, cfg.step_size);      // :822-823 (NaN trial values pass through, as in the reference)
   st.a_t = hm::std_max(st.a_t, cfg.trans_eps / 2);
   for (int i = 0; i < 6; i++) st.x_t[i] = st.p[i] + st.step_dir[i] * st.a_t;
-  hm::ndt_pose_matrix_f32(st.x_t, st.final_T);
 }
 
 PCR_HM void begin_outer(NdtScanState& st, const NdtCfg& cfg);
@@ -164,7 +174,7 @@ PCR_HM void begin_outer(NdtScanState& st, const NdtCfg& cfg) {
   st.a_t = nrm;
   set_trial(st, cfg);
   st.phase = NDT_LS_FIRST;
-  request(st, st.final_T, st.x_t, 0, 1);
+  request(st, st.x_t, 0, 1, 1);
 }
 
 PCR_HM void after_eval(NdtScanState& st) {
@@ -182,12 +192,12 @@ PCR_HM void ls_continue(NdtScanState& st, const NdtCfg& cfg) {
     else st.a_t = hm::mt_trial_value(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, st.phi_t, st.d_phi_t);
     set_trial(st, cfg);
     st.phase = NDT_LS_LOOP;
-    request(st, st.final_T, st.x_t, 0, 0);
+    request(st, st.x_t, 0, 0, 1);
     return;
   }
   if (st.step_iterations) {  // :928-929 computeHessian
     st.phase = NDT_LS_HESSIAN;
-    request(st, st.final_T, st.x_t, 1, 1);
+    request(st, st.x_t, 1, 1, 0);  // same x_t as the last trial: final_T already belongs to it
     return;
   }
   end_outer(st, cfg, st.a_t);

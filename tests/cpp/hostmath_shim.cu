@@ -42,18 +42,21 @@ void shim_angle_tables(const double* p, float* jf, float* hf, double* jd, double
 void shim_solve6_newton(const double* A, const double* b, double* x) { pcr::hm::solve6_newton(A, b, x); }
 // NDT Newton / More-Thuente state machine (ndt_logic.cuh), the code the evaluation kernels' tails run on the device
 size_t shim_ndt_state_size() { return sizeof(pcr::NdtScanState); }
-void shim_ndt_start(void* st, const double* Tguess) { pcr::ndt_logic::start(*static_cast<pcr::NdtScanState*>(st), Tguess, 0); }
+void shim_ndt_start(void* st, const double* Tguess) {
+  pcr::ndt_logic::start(*static_cast<pcr::NdtScanState*>(st), Tguess, 0);
+  pcr::ndt_logic::fill_request(*static_cast<pcr::NdtScanState*>(st));
+}
 void shim_ndt_on_result(void* st, const double* v29, double step_size, double trans_eps, int max_iters) {
   pcr::NdtCfg cfg{step_size, trans_eps, max_iters, 0};
   pcr::ndt_logic::on_result(*static_cast<pcr::NdtScanState*>(st), v29, cfg);
+  pcr::ndt_logic::fill_request(*static_cast<pcr::NdtScanState*>(st));
 }
 // pending request: pend (0 none, 1 float derivatives, 2 double Hessian), compute_hessian, p[6] of the evaluation, Tf[16]
 void shim_ndt_pending(const void* stv, int* pend, int* hess, double* p, float* Tf) {
   const pcr::NdtScanState& st = *static_cast<const pcr::NdtScanState*>(stv);
   *pend = st.pend;
   *hess = st.next.compute_hessian;
-  const double* src = st.phase == pcr::NDT_INIT_EVAL ? st.p : st.x_t;
-  for (int i = 0; i < 6; i++) p[i] = src[i];
+  for (int i = 0; i < 6; i++) p[i] = st.eval_p[i];
   for (int i = 0; i < 16; i++) Tf[i] = st.next.Tf[i];
 }
 void shim_ndt_result(const void* stv, float* final_T, int* converged, int* nr_iterations, int* n_evals, int* n_hess, double* score) {
