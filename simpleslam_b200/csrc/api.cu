@@ -1384,7 +1384,7 @@ extern "C" int pcr_gicp_covariances(pcr_ctx* c, const void* pts, size_t n, size_
   if (rc) return fail(c, rc, "grid too large");
   c->vgd.src_covs.ensure(n * 6);
   int32_t* dk = c->vgd.knn_dbg.ensure(n * size_t(k));
-  gicp_covariances(d, n, grid, k, c->vgd.src_covs.p, dk, c->stream);
+  gicp_covariances(d, n, grid, k, c->vgd.src_covs.p, dk, c->stream, nullptr, knn_idx != nullptr);
   PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   PCR_CUDA_CHECK(cudaGetLastError());
   if (covs) {

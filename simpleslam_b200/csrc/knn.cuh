@@ -139,20 +139,32 @@ __device__ __forceinline__ void knn_sort_result(WarpKnn& st, int lane) { knn_bit
 // lives UNSORTED in the lanes (lane < k): a candidate that beats the threshold replaces the largest kept entry and the new
 // largest is found with redux.sync — ~15 warp instructions per accepted candidate instead of a ballot / shuffle-up sorted
 // insertion (~28). The (d2, index) order is total, so the kept SET is the same whatever the arrival order.
-__device__ __forceinline__ void knn_scan_run(WarpKnn& st, const float4* __restrict__ pts, int lo, int hi, float qx, float qy, float qz,
-                                             int k, int lane) {
+// `seen` (level >= 0): the 27 cells around (cx, cy, cz) of that level were examined already by the finer attempt of the same
+// search; their points are skipped (they are kept, or were rejected against a bound that has only shrunk since).
+struct KnnSeen { int level, cx, cy, cz; };
+
+__device__ __forceinline__ void knn_scan_run(WarpKnn& st, const MortonView& g, int lo, int hi, float qx, float qy, float qz,
+                                             int k, int lane, const KnnSeen& seen) {
+  const float4* __restrict__ pts = g.pts;
   for (int base = lo; base < hi; base += 32) {
     const int j = base + lane;
     float d2 = 0.f;
     int idx = 0;
     bool pass = false;
-    if (j < hi) {
+    bool valid = j < hi;
+    if (valid) {
       const float4 m = __ldg(pts + j);
       d2 = dist2_f32(qx, qy, qz, m);
       idx = __float_as_int(m.w);
-      pass = d2 < st.td || (d2 == st.td && idx < st.ti);
+      if (seen.level >= 0) {  // the candidate's cell at the finer level, by the build's own quantisation
+        const int ax = min(max(int(floorf(knn_scaled(m.x, g.mn[0], g.inv_h0))), 0), g.dim0[0] - 1) >> seen.level;
+        const int ay = min(max(int(floorf(knn_scaled(m.y, g.mn[1], g.inv_h0))), 0), g.dim0[1] - 1) >> seen.level;
+        const int az = min(max(int(floorf(knn_scaled(m.z, g.mn[2], g.inv_h0))), 0), g.dim0[2] - 1) >> seen.level;
+        if (abs(ax - seen.cx) <= 1 && abs(ay - seen.cy) <= 1 && abs(az - seen.cz) <= 1) valid = false;
+      }
+      pass = valid && (d2 < st.td || (d2 == st.td && idx < st.ti));
     }
-    if (st.cnt == 0 && hi - base <= k) {
+    if (st.cnt == 0 && seen.level < 0 && hi - base <= k) {
       // first chunk of a search and it fits: the lanes simply keep their own candidates (the kept set is unsorted anyway)
       const int valid = hi - base;
       st.cnt = valid;
@@ -161,7 +173,7 @@ __device__ __forceinline__ void knn_scan_run(WarpKnn& st, const float4* __restri
       if (valid == k) knn_refresh_threshold(st, k, lane);
       continue;
     }
-    if (st.cnt == 0) {
+    if (st.cnt == 0 && seen.level < 0) {
       // first chunk of a search, more candidates than slots: instead of up to 32 serial insertions sort the chunk with a
       // warp bitonic network on (d2, index) and adopt its k smallest
       float d = j < hi ? d2 : INFINITY;
@@ -219,6 +231,8 @@ static __constant__ unsigned char c_knn_nb[27] = {
 __device__ __forceinline__ WarpKnn knn_warp_morton(const MortonView& g, float qx, float qy, float qz, int k, int min_pop, int lane) {
   WarpKnn st;
   knn_reset(st);
+  KnnSeen seen{-1, 0, 0, 0};
+  const KnnSeen none{-1, 0, 0, 0};
   // Level-0 scaled coordinates of the query. A query outside the cloud's bounding box is searched from its projection q'
   // onto the box: for every point p of the (convex) box |p - q|^2 >= |p - q'|^2 + |q' - q|^2, so all "everything outside
   // the visited cube is farther than ..." bounds are taken around q' and get extra2 = |q' - q|^2 added. Distances
@@ -285,14 +299,16 @@ __device__ __forceinline__ WarpKnn knn_warp_morton(const MortonView& g, float qx
       const int rlo = __shfl_sync(kFull, lo, sl), rhi = __shfl_sync(kFull, hi, sl);
       const float cm = __shfl_sync(kFull, cmin2, sl);
       if (st.cnt == k && cm > st.td) continue;  // cannot hold anything better than the current k-th
-      knn_scan_run(st, g.pts, rlo, rhi, qx, qy, qz, k, lane);
+      knn_scan_run(st, g, rlo, rhi, qx, qy, qz, k, lane, seen);
     }
     // every point outside the 27 cells is farther than reach
     const float reach = (1.f + margin - slack) * h;
     if (st.cnt == k && reach > 0.f && st.td < reach * reach * 0.99999f + extra2) return st;
-    if (level < kKnnLevels - 1) {  // climb one level and start over (the coarser cube contains the finer one)
+    if (level < kKnnLevels - 1) {
+      // climb one level (the coarser cube contains the finer one) and KEEP what was found: the points of the cube examined so
+      // far are skipped at the next level, everything else competes against the bound already reached
+      seen.level = level; seen.cx = c[0]; seen.cy = c[1]; seen.cz = c[2];
       level++;
-      knn_reset(st);
       continue;
     }
     // ---- top level: grow the cube ring by ring (Chebyshev shells) until the k-th distance is inside it or the grid is exhausted
@@ -333,7 +349,7 @@ __device__ __forceinline__ WarpKnn knn_warp_morton(const MortonView& g, float qx
         while (cl) {
           const int sl = __ffs(cl) - 1;
           cl &= cl - 1;
-          knn_scan_run(st, g.pts, __shfl_sync(kFull, l2, sl), __shfl_sync(kFull, h2, sl), qx, qy, qz, k, lane);
+          knn_scan_run(st, g, __shfl_sync(kFull, l2, sl), __shfl_sync(kFull, h2, sl), qx, qy, qz, k, lane, none);
         }
       }
       if (st.cnt == k) {

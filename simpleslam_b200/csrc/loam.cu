@@ -431,12 +431,11 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
 // Batch path (>= ~150 k queries per iteration): every Gauss-Newton iteration is two kernels.
 //
 // loam_search_kernel — one lane per query, queries in Morton order of their scan-frame position (neighbouring lanes walk
-// neighbouring rows of the map). Two stages per ring:
-//   stage 1 (convergent, unrolled): the geometry of all 9 (ring 2: 16) x-rows of the neighbourhood and ALL their start-table
-//     entries are issued together — one memory latency instead of one per row — and the rows that actually hold map points
-//     are appended to the lane's own row list in shared memory (column = thread: conflict-free);
-//   stage 2: the lane walks its OWN list (no iterations wasted on empty or out-of-range rows, so the lanes of a warp stay
-//     busy together), pruning rows against the current bound and scanning the candidates four float4 at a time.
+// neighbouring rows of the map: similar trip counts, shared cache lines). Rows are visited nearest first and pruned against
+// the current bound, candidates are read four float4 at a time. (Measured and rejected, profiles/README.md: issuing all
+// rows' table entries up front and walking a per-lane list of non-empty rows from shared memory — fewer instructions,
+// better lane utilisation, but 1.5x slower: the extra table sectors of rows the bound would have pruned cost more than
+// the saved latency; warm-starting the bound from the previous iteration's winners — no change.)
 // Selection runs on the FP32 metric f (|f - e| <= 3e-7 e against the exact FP64 metric e of the reference, both taken on
 // the same float coordinates): a lane keeps its five smallest (f, position) pairs and the smallest f that was looked at but
 // is NOT among them (f_out). Candidates and rows are pruned against thr = 1.00001 * min(gate, current 5th f), so whatever
@@ -532,24 +531,6 @@ __device__ __noinline__ void exact_search_one(const GridView& grid, float qf0, f
   for (int k = 0; k < 5; k++) wj[k] = best[k].j;
 }
 
-constexpr int kRing1Rows = 9, kRing2Rows = 16;
-// row list of a thread in shared memory: per row the run [lo, hi) of the wide x-extent and, for half-gate grids, of the narrow
-// one (two int2 slots); ring 2 (16 rows, one extent each) reuses the same slots. 53 KB per block: four blocks per SM.
-constexpr int kSearchRunSlots = 2 * kRing1Rows;  // >= kRing2Rows
-constexpr int kSearchR2Slots = kRing2Rows;
-constexpr size_t kSearchDynSmem = size_t(kLoamBlock) * (kSearchRunSlots * sizeof(int2) + kSearchR2Slots * sizeof(float));
-
-// geometry of row k for a query: squared distance bound of the row, its (y, z) cell, validity
-__device__ __forceinline__ bool row_of(const GridSpec& g, const RowGeom& q, int k, float& row2, int& y, int& z) {
-  const int dy = c_row_dy[k], dz = c_row_dz[k];
-  // squared distance from the query to the row's (y, z) slab, shrunk by the cell-assignment slack
-  const float ay = fmaxf((dy == 0 ? 0.f : (dy > 0 ? float(dy) - q.fy : q.fy + float(-dy - 1))) - q.slk, 0.f);
-  const float az = fmaxf((dz == 0 ? 0.f : (dz > 0 ? float(dz) - q.fz : q.fz + float(-dz - 1))) - q.slk, 0.f);
-  row2 = (ay * ay + az * az) * q.h2;
-  y = q.cy + dy; z = q.cz + dz;
-  return y >= 0 && y < g.div_b[1] && z >= 0 && z < g.div_b[2];
-}
-
 __global__ void __launch_bounds__(kLoamBlock, 4)
 loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, GridView grid, LoamParams prm,
                    const LoamState* __restrict__ states, double slack, int max_ring, float4* __restrict__ nb_out, int2* __restrict__ cnt_out,
@@ -559,9 +540,6 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
   const LoamState* st = states + scan;
   if (st->done) return;
   __shared__ double sT[16];
-  extern __shared__ __align__(16) unsigned char s_dyn[];
-  int2* s_run = reinterpret_cast<int2*>(s_dyn);                                                          // [slot][kLoamBlock]
-  float* s_r2 = reinterpret_cast<float*>(s_dyn + size_t(kSearchRunSlots) * kLoamBlock * sizeof(int2));   // [row][kLoamBlock]
   if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
   __syncthreads();
   const int tid = threadIdx.x;
@@ -589,7 +567,6 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
     if (near) {
       const float qf0 = pmf[0], qf1 = pmf[1], qf2 = pmf[2];
       const RowGeom q = row_geom(g, qf0, qf1, qf2, leaf, slack);
-      const float axh = q.ax2 * q.ax2 * q.h2;  // a row whose bound is below thr - axh only needs one x-cell either side
       float bf[5] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};  // five smallest f, ascending
       float f_out = INFINITY;  // smallest f that was examined but is not among the five
       float thr = gate_thr;
@@ -611,93 +588,24 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
           }
         }
       };
-      // stage 2 of a ring: walk my own list of non-empty rows. two_runs: slot 2r = wide run, slot 2r + 1 = narrow run
-      auto walk = [&](int cnt, bool two_runs) {
+      const int NR = (2 * max_ring + 1) * (2 * max_ring + 1);
 #pragma unroll 1
-        for (int r = 0; r < cnt; r++) {
-          const float row2 = s_r2[r * kLoamBlock + tid];
-          if (row2 > thr) continue;  // every point of this row is farther than the current bound
-          const int slot = two_runs ? 2 * r + ((thr < row2 + axh) ? 1 : 0) : r;
-          const int2 e = s_run[slot * kLoamBlock + tid];
-          const int lo = e.x, hi = e.y;
-          ncand += hi - lo;
-          nrows++;
+      for (int k = 0; k < NR; k++) {  // rows nearest first; each row is one contiguous run of the cell-sorted map
+        if (k >= 9 && thr < q.ring2_min2) break;
+        int lo, hi;
+        if (!row_run(grid, q, k, thr, max_ring, lo, hi)) continue;
+        ncand += hi - lo;
+        nrows++;
 #pragma unroll 1
-          for (int j = lo; j < hi; j += 4) {  // four independent float4 loads in flight
-            const int rem = hi - j;
-            const float4 far = make_float4(INFINITY, 0.f, 0.f, 0.f);  // f = inf: never considered
-            const float4 m0 = __ldg(grid.pts + j);
-            const float4 m1 = rem > 1 ? __ldg(grid.pts + j + 1) : far;
-            const float4 m2 = rem > 2 ? __ldg(grid.pts + j + 2) : far;
-            const float4 m3 = rem > 3 ? __ldg(grid.pts + j + 3) : far;
-            consider(m0, j); consider(m1, j + 1); consider(m2, j + 2); consider(m3, j + 3);
-          }
+        for (int j = lo; j < hi; j += 4) {  // four independent float4 loads in flight
+          const int rem = hi - j;
+          const float4 far = make_float4(INFINITY, 0.f, 0.f, 0.f);  // f = inf: never considered
+          const float4 m0 = __ldg(grid.pts + j);
+          const float4 m1 = rem > 1 ? __ldg(grid.pts + j + 1) : far;
+          const float4 m2 = rem > 2 ? __ldg(grid.pts + j + 2) : far;
+          const float4 m3 = rem > 3 ? __ldg(grid.pts + j + 3) : far;
+          consider(m0, j); consider(m1, j + 1); consider(m2, j + 2); consider(m3, j + 3);
         }
-      };
-      // x-extents of a row: wide = max_ring cells either side of the query's cell, narrow = one cell either side
-      const int xw0 = max(q.cx - max_ring, 0), xw1 = min(q.cx + max_ring, g.div_b[0] - 1);
-      const int xn0 = max(q.cx - 1, 0), xn1 = min(q.cx + 1, g.div_b[0] - 1);
-      const bool x_ok = xw0 <= xw1;
-      // ---- ring 1, stage 1: all nine rows' table entries in flight together
-      int cnt = 0;
-      if (x_ok) {
-        int4 e[kRing1Rows];
-        float r2[kRing1Rows];
-        bool ok[kRing1Rows];
-#pragma unroll
-        for (int k = 0; k < kRing1Rows; k++) {
-          int y, z;
-          ok[k] = row_of(g, q, k, r2[k], y, z) && r2[k] <= thr;
-          e[k] = make_int4(0, 0, 0, 0);
-          if (ok[k]) {
-            const int32_t* row = grid.start + ((long long)y * g.mul[1] + (long long)z * g.mul[2]);
-            e[k].x = __ldg(row + xw0); e[k].w = __ldg(row + xw1 + 1);
-            if (max_ring > 1 && xn0 <= xn1) { e[k].y = __ldg(row + xn0); e[k].z = __ldg(row + xn1 + 1); }
-            else { e[k].y = e[k].x; e[k].z = e[k].w; }
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < kRing1Rows; k++) {
-          if (ok[k] && e[k].w > e[k].x) {  // rows without a single map point never enter the list
-            if (max_ring > 1) {
-              s_run[(2 * cnt) * kLoamBlock + tid] = make_int2(e[k].x, e[k].w);
-              s_run[(2 * cnt + 1) * kLoamBlock + tid] = make_int2(e[k].y, e[k].z);
-            } else {
-              s_run[cnt * kLoamBlock + tid] = make_int2(e[k].x, e[k].w);
-            }
-            s_r2[cnt * kLoamBlock + tid] = r2[k];
-            cnt++;
-          }
-        }
-      }
-      walk(cnt, max_ring > 1);
-      // ---- ring 2 (half-gate cells only): needed while the bound still reaches past the first ring
-      if (max_ring > 1 && x_ok && !(thr < q.ring2_min2)) {
-        cnt = 0;
-        int2 e2[kRing2Rows];
-        float r2[kRing2Rows];
-        bool ok[kRing2Rows];
-#pragma unroll
-        for (int k = 0; k < kRing2Rows; k++) {
-          int y, z;
-          ok[k] = row_of(g, q, kRing1Rows + k, r2[k], y, z) && r2[k] <= thr;
-          e2[k] = make_int2(0, 0);
-          if (ok[k]) {
-            const int32_t* row = grid.start + ((long long)y * g.mul[1] + (long long)z * g.mul[2]);
-            const bool narrow = thr < r2[k] + axh && xn0 <= xn1;
-            e2[k].x = __ldg(row + (narrow ? xn0 : xw0));
-            e2[k].y = __ldg(row + (narrow ? xn1 : xw1) + 1);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < kRing2Rows; k++) {
-          if (ok[k] && e2[k].y > e2[k].x) {
-            s_run[cnt * kLoamBlock + tid] = e2[k];
-            s_r2[cnt * kLoamBlock + tid] = r2[k];
-            cnt++;
-          }
-        }
-        walk(cnt, false);
       }
       // a 6th candidate within 1e-6 (relative) of the 5th: the FP32 metric cannot tell which of them the reference keeps
       if (bj[4] >= 0 && !(f_out > bf[4] * 1.000001f)) {
@@ -896,7 +804,6 @@ static void loam_opt_in_smem() {
   if (done) return;
   opt_in_one<1, false>(); opt_in_one<2, false>(); opt_in_one<4, false>(); opt_in_one<8, false>();
   opt_in_one<1, true>(); opt_in_one<2, true>(); opt_in_one<4, true>(); opt_in_one<8, true>();
-  PCR_CUDA_CHECK(cudaFuncSetAttribute(loam_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSearchDynSmem)));
   done = true;
 }
 
@@ -1048,7 +955,7 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     const dim3 fgrid(static_cast<unsigned>(fit_blocks), static_cast<unsigned>(n_scans));
     for (int it = 0; it < prm.max_iters; it++) {
       if (split) {
-        loam_search_kernel<<<sgrid, kLoamBlock, kSearchDynSmem, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
+        loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
         loam_fit_kernel<false><<<fgrid, kLoamBlock, 0, s>>>(q, offsets.p, nb_buf.p, cnt_buf.p, total_q, prm, states.p, partials.p, max_warps, logs.p, 1,
                                                             nullptr, nullptr, perm);
         launches += 2;
@@ -1118,7 +1025,7 @@ int LoamDriver::linearize(const float4* src, size_t ns, const CellGrid& grid, co
       const dim3 sgrid(unsigned((ns + search_pb - 1) / search_pb), 1);
       const int fit_blocks = std::max(1, int((ns + kLoamBlock - 1) / kLoamBlock));
       partials.ensure(size_t(fit_blocks) * kLoamWarps * kNV);
-      loam_search_kernel<<<sgrid, kLoamBlock, kSearchDynSmem, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, ns);
+      loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, ns);
       loam_fit_kernel<true><<<dim3(fit_blocks, 1), kLoamBlock, 0, s>>>(q, offsets.p, nb_buf.p, cnt_buf.p, ns, prm, states.p, partials.p, fit_blocks * kLoamWarps,
                                                                        logs.p, 0, dbg_knn.p, dbg_status.p, perm);
       last_split = true;

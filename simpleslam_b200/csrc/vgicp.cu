@@ -17,6 +17,9 @@ constexpr int kMaxK = kKnnMaxK;
 // mean-centred neighbours (FP64), PLANE regularisation U diag(1,1,1e-3) V^T.
 // Two kernels: warp-per-query k-NN writes the neighbour indices, then one thread per point does the 3x3 algebra.
 // ================================================================================================================
+// SORT: neighbours written in ascending (d2, index) order (what the parity tests compare); the covariance itself does not
+// depend on the order beyond FP64 rounding, so the registration path skips the final sort.
+template <bool SORT>
 __global__ void __launch_bounds__(256)
 gicp_knn_kernel(size_t n, MortonView grid, int k, int min_pop, int32_t* __restrict__ knn_idx) {
   // one warp per query; queries are taken in Morton order (the sorted copy), so neighbouring warps touch the same cells
@@ -25,7 +28,7 @@ gicp_knn_kernel(size_t n, MortonView grid, int k, int min_pop, int32_t* __restri
   for (size_t i = size_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
     const float4 q = __ldg(grid.pts + i);
     WarpKnn st = knn_warp_morton(grid, q.x, q.y, q.z, k, min_pop, lane);
-    knn_sort_result(st, lane);  // ascending (d2, index): the order pcl::search::KdTree::nearestKSearch returns
+    if (SORT) knn_sort_result(st, lane);  // ascending (d2, index): the order pcl::search::KdTree::nearestKSearch returns
     const size_t orig = size_t(__float_as_int(q.w));
     if (lane < k) knn_idx[orig * k + lane] = lane < st.cnt ? st.bi : -1;
   }
@@ -101,13 +104,15 @@ void KnnProfile::collect() {
 }
 
 // knn_idx: device scratch of n*k ints (always needed)
-void gicp_covariances(const float4* pts, size_t n, const MortonGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s, KnnProfile* prof) {
+void gicp_covariances(const float4* pts, size_t n, const MortonGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s, KnnProfile* prof,
+                      bool sorted_idx) {
   if (n == 0) return;
   const unsigned blocks = unsigned(std::min<size_t>((n + 7) / 8, size_t(kNumSMs) * 64));
   static const int min_pop_env = std::getenv("PCR_KNN_MINPOP") ? std::atoi(std::getenv("PCR_KNN_MINPOP")) : 0;  // tuning knob
   const int min_pop = min_pop_env > 0 ? min_pop_env : std::max(1, (k * 3) / 4);
   if (prof) prof->begin(s);
-  gicp_knn_kernel<<<blocks, 256, 0, s>>>(n, view_of(grid), k, min_pop, knn_idx);
+  if (sorted_idx) gicp_knn_kernel<true><<<blocks, 256, 0, s>>>(n, view_of(grid), k, min_pop, knn_idx);
+  else gicp_knn_kernel<false><<<blocks, 256, 0, s>>>(n, view_of(grid), k, min_pop, knn_idx);
   if (prof) prof->end(s, n);
   gicp_cov_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(pts, n, k, knn_idx, covs);
 }

@@ -94,7 +94,7 @@ struct VgicpDriver {
 // exact k-NN (float metric, (d2, idx) order) + PLANE-regularised covariance for every point of `pts` using `grid` built over it.
 // covs: 6 doubles per point. knn_idx: device scratch/output, k ints per point.
 void gicp_covariances(const float4* pts, size_t n, const MortonGrid& grid, int k, double* covs, int32_t* knn_idx, cudaStream_t s,
-                      KnnProfile* prof = nullptr);
+                      KnnProfile* prof = nullptr, bool sorted_idx = false);
 
 int vgicp_build_target(const float4* pts, size_t n, const pcr_params& prm, VgicpTarget& tgt, KeySort& ks, BBoxWork& bw, cudaStream_t s);
 
