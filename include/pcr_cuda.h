@@ -167,6 +167,13 @@ int pcr_target_blob_size(pcr_ctx* c, size_t* bytes);
 int pcr_target_export(pcr_ctx* c, void* dev_blob, size_t cap);
 int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes);
 
+/* Logging (the reference logs through its spdlog singleton, common/utils/Logger.hpp:16-76: `lg->error(...)` at LoamRegister.cpp:174,
+ * `lg->warn(...)` at LidarOdometry.cpp:199). Every error text this library produces (what pcr_last_error returns) and its warnings
+ * are also handed to the process-wide callback: level 0 = debug, 1 = info, 2 = warning, 3 = error. Default (cb == NULL): errors and
+ * warnings go to stderr. The callback may be invoked from any thread that uses a context. */
+typedef void (*pcr_log_fn)(int32_t level, const char* message, void* user);
+void pcr_set_logger(pcr_log_fn cb, void* user);
+
 /* Device allocations released by contexts are parked in a process-wide, mutex-protected cache (cudaMalloc / cudaFree cost
  * milliseconds inside host-driven loops). A long-running caller can hand the parked buffers back to the driver at a quiet
  * moment: *freed_bytes (nullable) = bytes returned. Buffers owned by live contexts are not touched. */

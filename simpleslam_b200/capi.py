@@ -25,7 +25,7 @@ SYMBOLS = [
     "pcr_gicp_covariances", "pcr_vgicp_num_voxels", "pcr_vgicp_get_voxels", "pcr_vgicp_evaluate",
     "pcr_submap_build", "pcr_submap_cache_clear", "pcr_submap_cache_budget", "pcr_submap_cache_info", "pcr_target_save", "pcr_target_load", "pcr_read_pcd", "pcr_static_map_load",
     "pcr_scancontext_make", "pcr_scancontext_distance", "pcr_loam_last_shape",
-    "pcr_multi_create", "pcr_multi_destroy", "pcr_multi_last_error", "pcr_multi_set_target", "pcr_multi_batch_align", "pcr_multi_get_broadcast", "pcr_trim_device_cache",
+    "pcr_multi_create", "pcr_multi_destroy", "pcr_multi_last_error", "pcr_multi_set_target", "pcr_multi_batch_align", "pcr_multi_get_broadcast", "pcr_trim_device_cache", "pcr_set_logger",
 ]
 
 
@@ -140,6 +140,22 @@ def default_params(method, device=0):
     lib().pcr_default_params(int(method), ctypes.byref(p))
     p.device = device
     return p
+
+
+LOG_FN = ctypes.CFUNCTYPE(None, ctypes.c_int32, ctypes.c_char_p, ctypes.c_void_p)
+_log_keepalive = None
+
+
+def set_logger(fn):
+    """fn(level, message) receives the library's log lines (3 = error, 2 = warning); None restores the stderr default"""
+    global _log_keepalive
+    if fn is None:
+        _log_keepalive = None
+        lib().pcr_set_logger(None, None)
+        return
+    cb = LOG_FN(lambda level, msg, user: fn(int(level), msg.decode(errors="replace")))
+    _log_keepalive = cb   # the C side keeps the pointer
+    lib().pcr_set_logger(cb, None)
 
 
 def trim_device_cache():

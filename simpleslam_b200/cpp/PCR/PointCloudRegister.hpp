@@ -128,12 +128,28 @@ class VgicpRegister : public CudaRegister {
   }
 };
 
+// The same factory straight from the reference's configuration object (config::Params::getInstance(), an nlohmann::json):
+// reads cfg["frontend"]["pcr"] (frontend/src/LidarOdometry.cpp:44), cfg["cores"] (PointCloudRegister.hpp:30-31, kept for
+// compatibility) and the new optional key cfg["gpu"]["device"]. Any json type with operator[], contains()
+// and get<T>() works; nothing is included here.
+template <class Json>
+inline std::shared_ptr<PointCloudRegister> makeRegisterFromConfig(const Json& cfg);
+
 // cfg["frontend"]["pcr"] -> register, as frontend/src/LidarOdometry.cpp:44-53 (unknown string -> runtime_error)
 inline PointCloudRegister::Ptr makeRegister(const std::string& pcr_type, int cores = 4, int device = 0) {
   if (pcr_type == "loam") return std::make_shared<LoamRegister>(cores, device);
   if (pcr_type == "ndt") return std::make_shared<NdtRegister>(cores, device);
   if (pcr_type == "vgicp") return std::make_shared<VgicpRegister>(cores, device);
   throw std::runtime_error("such pcr type(" + pcr_type + ") is not exist, please implemented your self!");
+}
+
+template <class Json>
+inline std::shared_ptr<PointCloudRegister> makeRegisterFromConfig(const Json& cfg) {
+  const std::string type = cfg["frontend"]["pcr"].template get<std::string>();
+  const int cores = cfg.contains("cores") ? cfg["cores"].template get<int>() : 4;
+  int device = 0;
+  if (cfg.contains("gpu") && cfg["gpu"].contains("device")) device = cfg["gpu"]["device"].template get<int>();
+  return makeRegister(type, cores, device);
 }
 
 }  // namespace PCR

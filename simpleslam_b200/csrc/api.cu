@@ -76,6 +76,26 @@ struct pcr_ctx {
 
 static thread_local std::string g_create_error;
 
+// process-wide logger (pcr_set_logger); default: warnings and errors to stderr
+static std::mutex g_log_mu;
+static pcr_log_fn g_log_cb = nullptr;
+static void* g_log_user = nullptr;
+static void pcr_log(int level, const std::string& msg) {
+  pcr_log_fn cb;
+  void* user;
+  {
+    std::lock_guard<std::mutex> lk(g_log_mu);
+    cb = g_log_cb; user = g_log_user;
+  }
+  if (cb) cb(level, msg.c_str(), user);
+  else if (level >= 2) std::fprintf(stderr, "[pcr %s] %s\n", level >= 3 ? "error" : "warning", msg.c_str());
+}
+extern "C" void pcr_set_logger(pcr_log_fn cb, void* user) {
+  std::lock_guard<std::mutex> lk(g_log_mu);
+  g_log_cb = cb;
+  g_log_user = user;
+}
+
 static LoamParams loam_params(const pcr_params& p) {
   LoamParams lp;
   lp.max_knn_d2 = double(p.loam_max_knn_d2);
@@ -95,16 +115,19 @@ static LoamParams loam_params(const pcr_params& p) {
   }                                                        \
   catch (const CudaError& e) {                             \
     (c)->err = e.what();                                   \
+    pcr_log(3, (c)->err);                                  \
     cudaGetLastError();                                    \
     return PCR_ERR_CUDA;                                   \
   }                                                        \
   catch (const std::exception& e) {                        \
     (c)->err = e.what();                                   \
+    pcr_log(3, (c)->err);                                  \
     return PCR_ERR_INVALID;                                \
   }
 
 static int fail(pcr_ctx* c, int code, const char* msg) {
   c->err = msg;
+  pcr_log(3, c->err);
   return code;
 }
 
@@ -146,6 +169,7 @@ extern "C" int pcr_create(const pcr_params* p, pcr_ctx** out) {
   if (e != cudaSuccess || ndev == 0) {
     cudaGetLastError();
     g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback";
+    pcr_log(3, g_create_error);
     return PCR_ERR_NO_DEVICE;
   }
   if (p->device < 0 || p->device >= ndev) { g_create_error = "device ordinal out of range"; return PCR_ERR_NO_DEVICE; }

@@ -530,12 +530,17 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     if (!s_last) continue;  // block-uniform
     // ---- 4. last block of the request: totals, then the scan's state machine
     __threadfence();
-    if (tid < kNdtNV) {
-      const double* pb = partials + size_t(req) * bpr * kNdtNV + tid;
+    // four slices of the block partials per component, combined in a fixed order (a single scan owns the whole wave: 740
+    // partials — one thread per component would walk them one dependent add after the other)
+    if (tid < 4 * kNdtNV) {
+      const int comp = tid % kNdtNV, slice = tid / kNdtNV;
+      const double* pb = partials + size_t(req) * bpr * kNdtNV + comp;
       double tsum = 0.0;
-      for (int b = 0; b < nb; b++) tsum += __ldcg(pb + size_t(b) * kNdtNV);
-      s_tot[tid] = tsum;
+      for (int b = slice; b < nb; b += 4) tsum += __ldcg(pb + size_t(b) * kNdtNV);
+      sacc[slice * kNdtNV + comp] = tsum;  // the accumulators are free again
     }
+    __syncthreads();
+    if (tid < kNdtNV) s_tot[tid] = (sacc[tid] + sacc[kNdtNV + tid]) + (sacc[2 * kNdtNV + tid] + sacc[3 * kNdtNV + tid]);
     __syncthreads();
     if (tid < 30) outs[scan].v[tid] = tid < kNdtNV ? s_tot[tid] : 0.0;
     if (tid == 0) {

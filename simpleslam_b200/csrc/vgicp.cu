@@ -109,7 +109,7 @@ void gicp_covariances(const float4* pts, size_t n, const MortonGrid& grid, int k
   if (n == 0) return;
   const unsigned blocks = unsigned(std::min<size_t>((n + 7) / 8, size_t(kNumSMs) * 64));
   static const int min_pop_env = std::getenv("PCR_KNN_MINPOP") ? std::atoi(std::getenv("PCR_KNN_MINPOP")) : 0;  // tuning knob
-  const int min_pop = min_pop_env > 0 ? min_pop_env : std::max(1, (k * 3) / 4);
+  const int min_pop = min_pop_env > 0 ? min_pop_env : std::max(1, k / 2);  // sweep on C3 (profiles/README.md): flat from k/2.5 to 0.6 k
   if (prof) prof->begin(s);
   if (sorted_idx) gicp_knn_kernel<true><<<blocks, 256, 0, s>>>(n, view_of(grid), k, min_pop, knn_idx);
   else gicp_knn_kernel<false><<<blocks, 256, 0, s>>>(n, view_of(grid), k, min_pop, knn_idx);

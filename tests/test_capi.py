@@ -49,3 +49,23 @@ def test_unknown_register_type_raises_like_reference():
     # frontend/src/LidarOdometry.cpp:49-53: unknown config string -> runtime_error
     with pytest.raises(RuntimeError, match="is not exist"):
         registers.make_register("icp")
+
+
+def test_logger_callback_receives_errors():
+    """a logger callback in the C ABI (the reference logs through its spdlog singleton); default = stderr"""
+    import torch
+    got = []
+    capi.set_logger(lambda level, msg: got.append((level, msg)))
+    try:
+        if torch.cuda.is_available():
+            c = capi.Context(capi.PCR_LOAM)
+            with pytest.raises(capi.PcrError):
+                c.align([[0.0, 0.0, 0.0]], [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])   # no target set
+            c.close()
+            assert any(level == 3 and "no target" in msg for level, msg in got), got
+        else:
+            with pytest.raises(capi.PcrError):
+                capi.Context(capi.PCR_LOAM)
+            assert any(level == 3 and "no CPU fallback" in msg for level, msg in got), got
+    finally:
+        capi.set_logger(None)

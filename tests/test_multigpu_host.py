@@ -65,3 +65,23 @@ def test_two_rank_gloo(tmp_path):
     mp.spawn(_worker, args=(world, port, 11, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(str(tmp_path), "rank%d.ok" % r)).read() == "1"
+
+
+def test_job_scans_do_not_depend_on_the_sharding():
+    """bench.py's fixed C4 job: every rank raycasts only its contiguous shard, and scan k (points, truth, guess) must be the
+    same whatever the number of ranks — otherwise the N-GPU runs would not measure the same job"""
+    from simpleslam_b200 import synth, workloads
+    synth.build()
+    n_total = 12
+    ident = lambda pts, leaf: pts  # noqa: E731  (no downsample: host-only check)
+    whole, wt, wg = workloads.c4_scans("ndt", ident, 0, n_total, n_total, tiles=1, workers=4)
+    for world in (2, 4):
+        got, gt, gg = [], [], []
+        for r in range(world):
+            lo, hi = multigpu.shard(n_total, r, world)
+            s, t, g = workloads.c4_scans("ndt", ident, lo, hi, n_total, tiles=1, workers=2)
+            got += s; gt += t; gg += g
+        assert len(got) == n_total
+        for a, b in zip(whole, got):
+            assert np.array_equal(a, b)
+        assert all(np.array_equal(a, b) for a, b in zip(wt, gt)) and all(np.array_equal(a, b) for a, b in zip(wg, gg))
