@@ -18,6 +18,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <condition_variable>
 #include <thread>
 #include <vector>
 
@@ -65,6 +66,11 @@ struct pcr_ctx {
   DevBuf<float4> sub_concat;
   DevBuf<unsigned char> sub_meta;
   PinBuf<unsigned char> sub_meta_h;
+
+  // pcr_batch_align of a large host batch: uploads of later chunks overlap the registration of earlier ones
+  cudaStream_t copy_stream = nullptr;
+  DevBuf<unsigned char> raw_chunk[2];
+  std::vector<cudaEvent_t> ev_up;
 
   KnnProfile knn_prof;  // VGICP k-NN kernel timing while profiling is on (target build + source covariances)
 
@@ -198,6 +204,8 @@ extern "C" int pcr_create(const pcr_params* p, pcr_ctx** out) {
 extern "C" void pcr_destroy(pcr_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  for (cudaEvent_t e : c->ev_up) cudaEventDestroy(e);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -420,6 +428,18 @@ extern "C" int pcr_scan2map(pcr_ctx* c, const void* src, size_t ns, size_t sstri
   return pcr_align(c, src, ns, sstride, T, converged);
 }
 
+// Large host batches (loc.cpp mode: hundreds of scans per call) are cut into chunks of whole scans: while chunk k registers
+// on the context's stream, chunks k+1 and k+2 cross PCIe on a copy stream (two staging buffers) and are packed into their
+// slice of the resident float4 array. Results and statistics are those of one call.
+static void merge_stats(pcr_stats& acc, const pcr_stats& s, bool first) {
+  if (first) { acc = s; return; }
+  acc.evaluations += s.evaluations; acc.hessian_evals += s.hessian_evals;
+  acc.n_source += s.n_source;
+  acc.kernel_launches += s.kernel_launches; acc.n_pairs += s.n_pairs; acc.n_point_evals += s.n_point_evals; acc.n_index_reads += s.n_index_reads;
+  acc.ms_total += s.ms_total; acc.ms_hot_kernel += s.ms_hot_kernel; acc.hot_kernel_launches += s.hot_kernel_launches;
+  acc.ms_aux_kernel += s.ms_aux_kernel; acc.aux_kernel_launches += s.aux_kernel_launches; acc.n_aux_items += s.n_aux_items;
+}
+
 extern "C" int pcr_batch_align(pcr_ctx* c, const void* src, const size_t* offsets, size_t n_scans, size_t stride, double* T,
                                int32_t* converged) {
   PCR_API_BEGIN(c)
@@ -427,8 +447,82 @@ extern "C" int pcr_batch_align(pcr_ctx* c, const void* src, const size_t* offset
   if (n_scans == 0) return PCR_OK;
   const size_t n = offsets[n_scans] - offsets[0];
   const unsigned char* base = static_cast<const unsigned char*>(src) + offsets[0] * stride;
-  const float4* d = upload_points(c, base, n, stride, c->raw_src, c->src);
-  return align_packed(c, d, offsets, n_scans, T, converged);
+  const char* chunk_env = std::getenv("PCR_BATCH_CHUNK_MB");  // tuning / test knob
+  const size_t chunk_bytes = size_t(chunk_env ? std::max(1, std::atoi(chunk_env)) : 256) << 20;
+  if (n_scans < 8 || n * stride < 2 * chunk_bytes || !c->has_target) {
+    const float4* d = upload_points(c, base, n, stride, c->raw_src, c->src);
+    return align_packed(c, d, offsets, n_scans, T, converged);
+  }
+  // ---- chunks of whole scans, about chunk_bytes each
+  std::vector<size_t> cut(1, 0);
+  for (size_t i = 1; i <= n_scans; i++)
+    if (i == n_scans || (offsets[i] - offsets[cut.back()]) * stride >= chunk_bytes) cut.push_back(i);
+  const size_t nc = cut.size() - 1;
+  size_t max_bytes = 0;
+  for (size_t k = 0; k < nc; k++) max_bytes = std::max(max_bytes, (offsets[cut[k + 1]] - offsets[cut[k]]) * stride);
+  if (!c->copy_stream) PCR_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  while (c->ev_up.size() < nc) {
+    cudaEvent_t e;
+    PCR_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->ev_up.push_back(e);
+  }
+  c->src.ensure(n + 1);
+  c->raw_chunk[0].ensure(max_bytes);
+  c->raw_chunk[1].ensure(max_bytes);
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));  // nothing of an earlier call still reads c->src
+  auto upload = [&](size_t k) {
+    const size_t p0 = offsets[cut[k]] - offsets[0], pn = offsets[cut[k + 1]] - offsets[cut[k]];
+    if (pn) {
+      PCR_CUDA_CHECK(cudaMemcpyAsync(c->raw_chunk[k & 1].p, base + p0 * stride, pn * stride, cudaMemcpyHostToDevice, c->copy_stream));
+      pack_points(c->raw_chunk[k & 1].p, pn, stride, c->src.p + p0, c->copy_stream);  // the copy stream is in order: buffer k & 1 is free again afterwards
+    }
+    PCR_CUDA_CHECK(cudaEventRecord(c->ev_up[k], c->copy_stream));
+  };
+  // the uploads run on their own host thread: a copy from pageable memory blocks its caller while the driver stages it, and
+  // that must not stall the thread that drives the registrations
+  std::mutex mu;
+  std::condition_variable cv;
+  size_t uploaded = 0;
+  std::string up_err;
+  std::thread uploader([&]() {
+    try {
+      PCR_CUDA_CHECK(cudaSetDevice(c->device));
+      for (size_t k = 0; k < nc; k++) {
+        upload(k);
+        { std::lock_guard<std::mutex> lk(mu); uploaded = k + 1; }
+        cv.notify_all();
+      }
+    } catch (const std::exception& e) {
+      { std::lock_guard<std::mutex> lk(mu); up_err = e.what(); uploaded = nc; }
+      cv.notify_all();
+    }
+  });
+  pcr_stats total{};
+  int rc = PCR_OK;
+  for (size_t k = 0; k < nc && rc == PCR_OK; k++) {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return uploaded > k; });
+      if (!up_err.empty()) { rc = PCR_ERR_CUDA; c->err = up_err; break; }
+    }
+    const size_t p0 = offsets[cut[k]] - offsets[0];
+    try {
+      PCR_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_up[k], 0));
+      rc = align_packed(c, c->src.p + p0, offsets + cut[k], cut[k + 1] - cut[k], T + 16 * cut[k], converged ? converged + cut[k] : nullptr);
+    } catch (const std::exception& e) {
+      c->err = e.what();
+      rc = PCR_ERR_CUDA;
+    }
+    if (rc == PCR_OK) {
+      merge_stats(total, c->stats, k == 0);
+      if (c->prm.method == PCR_VGICP) c->last_off += p0;  // getFitnessScore looks the last scan up in the whole staging array
+    }
+  }
+  uploader.join();
+  if (rc != PCR_OK) { cudaStreamSynchronize(c->copy_stream); cudaGetLastError(); pcr_log(3, c->err); return rc; }
+  PCR_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream));
+  if (rc == PCR_OK) c->stats = total;
+  return rc;
   PCR_API_END(c)
 }
 

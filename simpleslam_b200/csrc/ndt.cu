@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kNdtBlock, DOUBLE_PATH ? 2 : 5)
 ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, NdtTargetView tgt, NdtScanState* __restrict__ states,
                  NdtScanOut* __restrict__ outs, int32_t* __restrict__ float_round, int32_t* __restrict__ hess_round, int n_scans, int round,
                  int step, NdtCfg cfg, double* __restrict__ partials, unsigned* __restrict__ tickets, NdtProgress* progress,
-                 NdtCounters* __restrict__ counters, int* __restrict__ round_flags) {
+                 NdtCounters* __restrict__ counters, int* __restrict__ round_flags, int max_bpr) {
   constexpr int NNB = NbTraits<SEARCH>::N;
   // round_flags[r]: bit 0 = some scan wants a float evaluation in round r, bit 1 = a double-path Hessian. Written only by
   // tails of EARLIER kernels (or, for bit 1 of this round, by the float kernel that has completed): a launch without
@@ -396,8 +396,23 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
   if (n_active == 0) return;
   __syncthreads();
 
-  // ---- 2. my items
-  const int bpr = max(1, int(gridDim.x) / n_active);  // blocks per request
+  // ---- 2. my items. Every active scan is cut into `bpr` equal items; item t goes to block t mod gridDim. bpr is the split
+  // (up to ~6 items per block) that leaves the fewest blocks idle in the last pass: n_active * bpr / gridDim just below an
+  // integer. With bpr = gridDim / n_active alone a batch of ~500 scans would keep a third of the wave idle, and 1024 scans
+  // would make a quarter of the blocks do twice the work of the others.
+  int bpr = 1;
+  {
+    const int G = int(gridDim.x);
+    const int cap = max(1, min(max_bpr, (6 * G + n_active - 1) / n_active));
+    float best = 0.f;
+    for (int m = 1; m <= 6; m++) {  // candidates: the largest split that still fits m passes of the wave
+      const int b = min(cap, (m * G) / n_active);
+      if (b < 1) continue;
+      const float load = float(n_active) * float(b) / float(G);
+      const float eff = load / ceilf(load);
+      if (eff > best + 0.03f) { best = eff; bpr = b; }  // more, smaller items only when they balance clearly better
+    }
+  }
   const int n_items = n_active * bpr;
   const GridSpec& g = tgt.g;
   SmemAcc acc{sacc + tid};
@@ -621,7 +636,7 @@ void NdtDriver::ensure_progress() {
 void NdtDriver::prepare(size_t n_scans, int grid_blocks, cudaStream_t s) {
   ensure_progress();
   states.ensure(n_scans); outs.ensure(n_scans); stamps.ensure(2 * n_scans);
-  partials.ensure(std::max<size_t>(size_t(grid_blocks), n_scans) * kNdtNV);
+  partials.ensure((size_t(7) * size_t(std::max(grid_blocks, 1)) + 2 * n_scans + 64) * kNdtNV);  // items <= 6 * grid + n_active (+ slack)
   counters.ensure(1);
   if (tickets.cap < n_scans) {
     tickets.ensure(n_scans);
@@ -646,11 +661,11 @@ static NdtTargetView make_view(const NdtTarget& tgt) {
 template <int SEARCH>
 static void launch_round_t(bool dbl, int grid, cudaStream_t s, const float4* src, const uint32_t* offs, const NdtTargetView& v, NdtScanState* states,
                            NdtScanOut* outs, int32_t* fr, int32_t* hr, int n, int round, int step, const NdtCfg& cfg, double* partials,
-                           unsigned* tickets, NdtProgress* prog, NdtCounters* cnt, int* flags) {
+                           unsigned* tickets, NdtProgress* prog, NdtCounters* cnt, int* flags, int max_bpr) {
   if (dbl)  // 218 registers: two blocks per SM, one resident wave
-    ndt_round_kernel<SEARCH, true><<<std::min(grid, kNumSMs * 2), kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt, flags);
+    ndt_round_kernel<SEARCH, true><<<std::min(grid, kNumSMs * 2), kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt, flags, max_bpr);
   else
-    ndt_round_kernel<SEARCH, false><<<grid, kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt, flags);
+    ndt_round_kernel<SEARCH, false><<<grid, kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt, flags, max_bpr);
 }
 
 void NdtDriver::launch_round(const float4* src, const NdtTarget& tgt, int search, int n, int round, int step, const NdtCfg& cfg, int grid_blocks,
@@ -664,10 +679,10 @@ void NdtDriver::launch_round(const float4* src, const NdtTarget& tgt, int search
     if (part == 0 ? !float_kernel : !double_kernel) continue;
     const bool dbl = part == 1;
     switch (search) {
-      case PCR_NDT_DIRECT1: launch_round_t<PCR_NDT_DIRECT1>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p); break;
-      case PCR_NDT_DIRECT26: launch_round_t<PCR_NDT_DIRECT26>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p); break;
-      case PCR_NDT_KDTREE: launch_round_t<PCR_NDT_KDTREE>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p); break;
-      default: launch_round_t<PCR_NDT_DIRECT7>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p); break;
+      case PCR_NDT_DIRECT1: launch_round_t<PCR_NDT_DIRECT1>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_); break;
+      case PCR_NDT_DIRECT26: launch_round_t<PCR_NDT_DIRECT26>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_); break;
+      case PCR_NDT_KDTREE: launch_round_t<PCR_NDT_KDTREE>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_); break;
+      default: launch_round_t<PCR_NDT_DIRECT7>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_); break;
     }
     launches++;
   }
@@ -684,6 +699,7 @@ void NdtDriver::evaluate_one(const float4* src, size_t ns, const NdtTarget& tgt,
   for (int k = 0; k < 30; k++) out.v[k] = 0.0;
   if (tgt.overflow || tgt.nleaves == 0 || ns == 0) return;  // no block would contribute
   const int grid = wave_blocks(1, ns);
+  max_bpr_ = int((ns + kNdtBlock - 1) / kNdtBlock);
   prepare(1, grid, s);
   uint32_t* ho = h_offsets.ensure(2);
   ho[0] = 0; ho[1] = uint32_t(ns);
@@ -734,6 +750,7 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
     size_t max_pts = 0;
     for (size_t i = 0; i < n; i++) max_pts = std::max(max_pts, size_t(offs[c0 + i + 1] - offs[c0 + i]));
     const int grid = wave_blocks(n, std::max<size_t>(max_pts, 1));
+    max_bpr_ = std::max(1, int((max_pts + kNdtBlock - 1) / kNdtBlock));
     prepare(n, grid, s);
     uint32_t* ho = h_offsets.ensure(n + 1);
     double* hg = h_guesses.ensure(n * 16);

@@ -64,6 +64,7 @@ struct NdtDriver {
   DevBuf<NdtCounters> counters;
   DevBuf<int> round_flags;  // per round: which kinds of evaluation are wanted (lets idle launches return at once)
   static constexpr int max_rounds_cap = 4096;
+  int max_bpr_ = 1;         // blocks a single scan can use at most: ceil(points / block)
   PinBuf<NdtScanOut> h_outs;
   PinBuf<NdtScanState> h_state;
   PinBuf<uint32_t> h_offsets;

@@ -80,3 +80,33 @@ def test_device_resident_inputs():
     m = c.voxel_downsample_device(raw.data_ptr(), raw.shape[0], 32, 0.5, out.data_ptr(), raw.shape[0])
     assert np.array_equal(out[:m].cpu().numpy(), c.voxel_downsample(case["raw"], 0.5))
     c.close()
+
+
+@pytest.mark.parametrize("method,case_fn", [(capi.PCR_LOAM, data.loam_case), (capi.PCR_NDT, data.ndt_case), (capi.PCR_VGICP, data.vgicp_case)])
+def test_chunked_host_batch_equals_one_piece(method, case_fn):
+    """pcr_batch_align cuts a large HOST batch into chunks of whole scans whose uploads overlap the registration of earlier
+    chunks (uploader thread + copy stream). Forced here with a 1 MB chunk size: same poses / flags as the one-piece call,
+    from pinned and from pageable memory, and getFitnessScore still finds the last scan."""
+    import os
+    case = case_fn()
+    c = capi.Context(method)
+    c.set_target(case["dst"])
+    srcs, Ts, offs = _scans(case, 12 if method != capi.PCR_VGICP else 8, 5)
+    cat = np.ascontiguousarray(np.concatenate(srcs))
+    assert cat.nbytes > 3 * (1 << 20)
+    ref_T, ref_conv = c.batch_align(cat, offs, Ts)
+    ref_fit = c.fitness() if method == capi.PCR_VGICP else None
+    os.environ["PCR_BATCH_CHUNK_MB"] = "1"
+    try:
+        pinned = torch.from_numpy(cat).pin_memory().numpy()
+        for host in (cat, pinned):
+            T, conv = c.batch_align(host, offs, Ts)
+            st = c.stats()
+            assert st["n_source"] == len(cat)
+            for a, b, ca, cb in zip(ref_T, T, ref_conv, conv):
+                assert ca == cb and np.allclose(a, b, rtol=0, atol=1e-6 if method == capi.PCR_NDT else 1e-9)
+            if method == capi.PCR_VGICP:
+                assert c.fitness() == ref_fit
+    finally:
+        os.environ.pop("PCR_BATCH_CHUNK_MB", None)
+    c.close()
