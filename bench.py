@@ -799,7 +799,9 @@ def measure_c4_job(args, method, rank, world, local_rank, dist, dev, cpu=True):
         e0.record()
         for _ in range(n_steps):
             flush.zero_()
+            ws = time.perf_counter()
             last = job_step(**kw)
+            step_log.append((1e3 * (time.perf_counter() - ws), last[4]["ms_total"] if last[4] else 0.0))
             launches += last[4]["kernel_launches"] if last[4] else 0
         e1.record()
         torch.cuda.synchronize()
@@ -813,9 +815,11 @@ def measure_c4_job(args, method, rank, world, local_rank, dist, dev, cpu=True):
         return t_dev, wall, launches, last
 
     ctx.set_profiling(False)
+    step_log = []
     for _ in range(args.warmup):
         job_step()
     t_dev, wall, launches, last = timed(args.steps)
+    resident_steps = list(step_log)
     value = args.steps * n_job / t_dev
     allT, allc, myT, myconv, st_last = last
 
@@ -896,6 +900,7 @@ def measure_c4_job(args, method, rank, world, local_rank, dist, dev, cpu=True):
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpub, "parity": par,
             "setup": setup, "wall_s_timed_region": wall, "map_kernels": idx_roof,
             "job": {"converged": int(np.sum(allc)), "of": int(n_job)},
+            "rank0_steps_ms": {"wall": [round(a, 3) for a, _ in resident_steps], "library_events": [round(b, 3) for _, b in resident_steps]},
             "pose_error_vs_truth": {"median_m": float(np.median([pose_err(T, Tt)[0] for T, Tt in zip(myT, truths)])) if n_local else None},
         }
     ctx.close()

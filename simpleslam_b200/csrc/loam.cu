@@ -589,11 +589,34 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
         }
       };
       const int NR = (2 * max_ring + 1) * (2 * max_ring + 1);
-#pragma unroll 1
-      for (int k = 0; k < NR; k++) {  // rows nearest first; each row is one contiguous run of the cell-sorted map
-        if (k >= 9 && thr < q.ring2_min2) break;
-        int lo, hi;
-        if (!row_run(grid, q, k, thr, max_ring, lo, hi)) continue;
+      // rows nearest first; each row is one contiguous run of the cell-sorted map. The table entries of the NEXT row are
+      // requested before the candidates of the current one are scanned (two register sets, A and B, taking turns), so
+      // that one of the two dependent loads per row overlaps with work. A row chosen with the looser, earlier bound is
+      // tested against the current bound again before it is scanned.
+      int k = 0;
+      auto next_row = [&](int& lo, int& hi, float& row2) -> bool {
+        for (; k < NR; k++) {
+          if (k >= 9 && thr < q.ring2_min2) { k = NR; return false; }
+          const int dy = c_row_dy[k], dz = c_row_dz[k];
+          const float ay = fmaxf((dy == 0 ? 0.f : (dy > 0 ? float(dy) - q.fy : q.fy + float(-dy - 1))) - q.slk, 0.f);
+          const float az = fmaxf((dz == 0 ? 0.f : (dz > 0 ? float(dz) - q.fz : q.fz + float(-dz - 1))) - q.slk, 0.f);
+          row2 = (ay * ay + az * az) * q.h2;
+          if (row2 > thr) continue;  // every point of this row is farther than the current bound
+          const int y = q.cy + dy, z = q.cz + dz;
+          if (y < 0 || y >= g.div_b[1] || z < 0 || z >= g.div_b[2]) continue;
+          const int rx = (max_ring > 1 && thr < row2 + q.ax2 * q.ax2 * q.h2) ? 1 : max_ring;
+          const int x0 = max(q.cx - rx, 0), x1 = min(q.cx + rx, g.div_b[0] - 1);
+          if (x0 > x1) continue;
+          const long long key0 = (long long)x0 + (long long)y * g.mul[1] + (long long)z * g.mul[2];
+          lo = __ldg(grid.start + key0);
+          hi = __ldg(grid.start + key0 + (x1 - x0) + 1);
+          k++;
+          return true;
+        }
+        return false;
+      };
+      auto scan = [&](int lo, int hi, float row2) {
+        if (row2 > thr) return;  // pruned by what was found since the row was chosen
         ncand += hi - lo;
         nrows++;
 #pragma unroll 1
@@ -606,6 +629,17 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
           const float4 m3 = rem > 3 ? __ldg(grid.pts + j + 3) : far;
           consider(m0, j); consider(m1, j + 1); consider(m2, j + 2); consider(m3, j + 3);
         }
+      };
+      int loA = 0, hiA = 0, loB = 0, hiB = 0;
+      float r2A = 0.f, r2B = 0.f;
+      bool haveA = next_row(loA, hiA, r2A);
+#pragma unroll 1
+      while (haveA) {
+        const bool haveB = next_row(loB, hiB, r2B);
+        scan(loA, hiA, r2A);
+        if (!haveB) break;
+        haveA = next_row(loA, hiA, r2A);
+        scan(loB, hiB, r2B);
       }
       // a 6th candidate within 1e-6 (relative) of the 5th: the FP32 metric cannot tell which of them the reference keeps
       if (bj[4] >= 0 && !(f_out > bf[4] * 1.000001f)) {

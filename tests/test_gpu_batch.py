@@ -93,7 +93,7 @@ def test_chunked_host_batch_equals_one_piece(method, case_fn):
     c.set_target(case["dst"])
     srcs, Ts, offs = _scans(case, 12 if method != capi.PCR_VGICP else 8, 5)
     cat = np.ascontiguousarray(np.concatenate(srcs))
-    assert cat.nbytes > 3 * (1 << 20)
+    assert cat.nbytes > 2 * (1 << 20)   # at least two 1 MB chunks (the call only chunks batches of >= 2 chunk sizes)
     ref_T, ref_conv = c.batch_align(cat, offs, Ts)
     ref_fit = c.fitness() if method == capi.PCR_VGICP else None
     os.environ["PCR_BATCH_CHUNK_MB"] = "1"
