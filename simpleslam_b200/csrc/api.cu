@@ -299,7 +299,8 @@ extern "C" int pcr_set_target_device(pcr_ctx* c, const void* dev_pts, size_t n, 
 }
 
 // ---- align ---------------------------------------------------------------------------------------------------------
-static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_t n_scans, double* T, int32_t* converged) {
+static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_t n_scans, double* T, int32_t* converged,
+                        const NdtArrivals* arrivals = nullptr) {
   if (!c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no target set");
   pcr_stats& st = c->stats;
   memset(&st, 0, sizeof(st));
@@ -327,7 +328,7 @@ static int align_packed(pcr_ctx* c, const float4* src, const size_t* offs, size_
     }
     case PCR_NDT: {
       std::vector<double> tp(n_scans, 0.0);
-      rc = c->ndtd.align(src, offs, n_scans, c->ndt, c->prm, T, conv.data(), iters.data(), tp.data(), c->profiling, c->stream);
+      rc = c->ndtd.align(src, offs, n_scans, c->ndt, c->prm, T, conv.data(), iters.data(), tp.data(), c->profiling, c->stream, arrivals);
       st.iterations = iters[0];
       st.evaluations = c->ndtd.total_evals;
       st.hessian_evals = c->ndtd.total_hess;
@@ -497,25 +498,39 @@ extern "C" int pcr_batch_align(pcr_ctx* c, const void* src, const size_t* offset
       cv.notify_all();
     }
   });
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{uploader};  // also on the exception paths
+  auto wait_enqueued = [&](size_t k) {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return uploaded > k; });
+    if (!up_err.empty()) throw CudaError(up_err);
+  };
   pcr_stats total{};
   int rc = PCR_OK;
-  for (size_t k = 0; k < nc && rc == PCR_OK; k++) {
-    {
-      std::unique_lock<std::mutex> lk(mu);
-      cv.wait(lk, [&] { return uploaded > k; });
-      if (!up_err.empty()) { rc = PCR_ERR_CUDA; c->err = up_err; break; }
-    }
-    const size_t p0 = offsets[cut[k]] - offsets[0];
-    try {
+  if (c->prm.method == PCR_NDT && n_scans <= NdtDriver::max_streaming_scans) {
+    // NDT: ONE batch; the scans of a chunk join the running evaluation rounds as soon as their points are on the device
+    NdtArrivals arr;
+    arr.n_groups = nc;
+    arr.first = cut.data();
+    arr.ready = [&](size_t k) {
+      { std::lock_guard<std::mutex> lk(mu); if (uploaded <= k) return false; if (!up_err.empty()) throw CudaError(up_err); }
+      const cudaError_t q = cudaEventQuery(c->ev_up[k]);
+      if (q != cudaSuccess && q != cudaErrorNotReady) PCR_CUDA_CHECK(q);
+      return q == cudaSuccess;
+    };
+    arr.wait = wait_enqueued;   // the registration stream itself then waits for the event
+    arr.event = [&](size_t k) { return c->ev_up[k]; };
+    rc = align_packed(c, c->src.p, offsets, n_scans, T, converged, &arr);
+    if (rc == PCR_OK) total = c->stats;
+  } else {
+    for (size_t k = 0; k < nc && rc == PCR_OK; k++) {
+      wait_enqueued(k);
+      const size_t p0 = offsets[cut[k]] - offsets[0];
       PCR_CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_up[k], 0));
       rc = align_packed(c, c->src.p + p0, offsets + cut[k], cut[k + 1] - cut[k], T + 16 * cut[k], converged ? converged + cut[k] : nullptr);
-    } catch (const std::exception& e) {
-      c->err = e.what();
-      rc = PCR_ERR_CUDA;
-    }
-    if (rc == PCR_OK) {
-      merge_stats(total, c->stats, k == 0);
-      if (c->prm.method == PCR_VGICP) c->last_off += p0;  // getFitnessScore looks the last scan up in the whole staging array
+      if (rc == PCR_OK) {
+        merge_stats(total, c->stats, k == 0);
+        if (c->prm.method == PCR_VGICP) c->last_off += p0;  // getFitnessScore looks the last scan up in the whole staging array
+      }
     }
   }
   uploader.join();

@@ -358,7 +358,10 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
   // round_flags[r]: bit 0 = some scan wants a float evaluation in round r, bit 1 = a double-path Hessian. Written only by
   // tails of EARLIER kernels (or, for bit 1 of this round, by the float kernel that has completed): a launch without
   // work returns at once (most double-path launches, and the rounds queued past the end of the registration)
-  if (blockIdx.x == 0 && threadIdx.x == 0 && !DOUBLE_PATH && progress) progress->round = round;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && !DOUBLE_PATH && progress) {
+    progress->finished = counters->finished;  // complete: every earlier kernel of the stream has ended
+    progress->round = round;
+  }
   if (step && !(round_flags[round] & (DOUBLE_PATH ? 2 : 1))) return;
   __shared__ __align__(16) NdtScanState s_state;
   __shared__ double sacc[kNdtNV * kNdtBlock];
@@ -595,16 +598,18 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
 // start of a registration: one thread per scan runs ndt_logic::start (guess -> p, first request). Empty scans and an
 // empty target evaluate to all-zero sums (no block would contribute), which the state machine digests right here.
 __global__ void ndt_init_kernel(const double* __restrict__ guesses, const uint32_t* __restrict__ offs, NdtScanState* __restrict__ states,
-                                NdtScanOut* __restrict__ outs, int32_t* __restrict__ float_round, int32_t* __restrict__ hess_round, int n_scans,
-                                int no_target, NdtCfg cfg, NdtProgress* progress, NdtCounters* __restrict__ counters, int* __restrict__ round_flags) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_scans) return;
+                                NdtScanOut* __restrict__ outs, int32_t* __restrict__ float_round, int32_t* __restrict__ hess_round, int first_scan,
+                                int count, int n_scans, int first_round, int no_target, NdtCfg cfg, NdtProgress* progress,
+                                NdtCounters* __restrict__ counters, int* __restrict__ round_flags) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int s = first_scan + k;
   NdtScanState st;
   ndt_logic::start(st, guesses + size_t(s) * 16, s);
   hess_round[s] = -1;
   if (no_target || offs[s + 1] == offs[s]) {
     double zeros[kNdtNV];
-    for (int k = 0; k < kNdtNV; k++) zeros[k] = 0.0;
+    for (int q = 0; q < kNdtNV; q++) zeros[q] = 0.0;
     while (st.pend != NDT_PEND_NONE) ndt_logic::on_result(st, zeros, cfg);
   }
   ndt_logic::fill_request(st);
@@ -618,8 +623,8 @@ __global__ void ndt_init_kernel(const double* __restrict__ guesses, const uint32
     const int f = atomicAdd(&counters->finished, 1) + 1;
     if (f == n_scans && progress) { __threadfence_system(); progress->all_done = 1; }
   } else {
-    float_round[s] = 0;
-    atomicOr(round_flags, 1);
+    float_round[s] = first_round;  // joins the batch in the next round to be launched
+    atomicOr(round_flags + first_round, 1);
   }
 }
 
@@ -645,8 +650,10 @@ void NdtDriver::prepare(size_t n_scans, int grid_blocks, cudaStream_t s) {
   PCR_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, sizeof(NdtCounters), s));
   round_flags.ensure(size_t(max_rounds_cap) + 2);
   PCR_CUDA_CHECK(cudaMemsetAsync(round_flags.p, 0, (size_t(max_rounds_cap) + 2) * sizeof(int), s));
+  PCR_CUDA_CHECK(cudaMemsetAsync(stamps.p, 0xff, 2 * n_scans * sizeof(int32_t), s));  // -1: not (yet) part of the batch
   progress->round = -1;
   progress->all_done = 0;
+  progress->finished = 0;
 }
 
 static NdtTargetView make_view(const NdtTarget& tgt) {
@@ -732,17 +739,19 @@ void NdtDriver::evaluate_one(const float4* src, size_t ns, const NdtTarget& tgt,
 // stops queueing when the last scan has finished. Kernels of rounds queued past that point find no request and return.
 // ================================================================================================================
 int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, const NdtTarget& tgt, const pcr_params& prm, double* T,
-                     int32_t* converged, int32_t* iters, double* trans_prob, bool profile, cudaStream_t s) {
+                     int32_t* converged, int32_t* iters, double* trans_prob, bool profile, cudaStream_t s, const NdtArrivals* arrivals) {
   launches = 0; hot_ms = 0.f; hot_launches = 0; total_evals = 0; total_hess = 0; total_pairs = 0; point_evals = 0; rounds = 0;
   if (n_scans == 0) return 0;
+  if (arrivals && n_scans > max_streaming_scans) throw CudaError("NDT: streaming admission supports at most 2048 scans per batch");
   NdtCfg cfg{};
   cfg.step_size = prm.ndt_step_size;
   cfg.trans_eps = prm.ndt_trans_eps;
   cfg.max_iters = prm.ndt_max_iters;
   const int no_target = (tgt.overflow || tgt.nleaves == 0) ? 1 : 0;
   static const int lookahead = [] { const char* v = std::getenv("PCR_NDT_LOOKAHEAD"); return v ? std::max(1, std::atoi(v)) : 3; }();
-  // every outer iteration costs at most 1 + kMaxStepIterations float evaluations (+ 1 double-path Hessian in the same round)
-  const int max_rounds = std::min((prm.ndt_max_iters + 3) * (ndt_logic::kMaxStepIterations + 2) + 2, max_rounds_cap);
+  // every outer iteration costs at most 1 + kMaxStepIterations float evaluations (+ 1 double-path Hessian in the same round);
+  // with arrivals the rounds go on for as long as scans keep joining
+  const int max_rounds = arrivals ? max_rounds_cap - 2 : std::min((prm.ndt_max_iters + 3) * (ndt_logic::kMaxStepIterations + 2) + 2, max_rounds_cap);
   if (profile && !ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
 
   for (size_t c0 = 0; c0 < n_scans; c0 += kNdtMaxBatch) {  // chunks of scans (request list size); normally a single chunk
@@ -762,14 +771,32 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
     PCR_CUDA_CHECK(cudaMemcpyAsync(guesses.p, hg, n * 16 * sizeof(double), cudaMemcpyHostToDevice, s));
     NdtProgress* dprog = nullptr;
     PCR_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dprog), progress, 0));
-    ndt_init_kernel<<<unsigned((n + 127) / 128), 128, 0, s>>>(guesses.p, offsets.p, states.p, outs.p, stamps.p, stamps.p + n, int(n), no_target, cfg,
-                                                              dprog, counters.p, round_flags.p);
-    launches++;
-    if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
     int r = 0;
+    size_t next_group = 0, admitted = 0;
+    const size_t n_groups = arrivals ? arrivals->n_groups : 1;
+    auto admit = [&](size_t k) {  // start the state machines of group k; they join in round r
+      const size_t a = arrivals ? arrivals->first[k] : 0, b = arrivals ? arrivals->first[k + 1] : n;
+      if (arrivals) PCR_CUDA_CHECK(cudaStreamWaitEvent(s, arrivals->event(k), 0));
+      if (b > a)
+        ndt_init_kernel<<<unsigned((b - a + 127) / 128), 128, 0, s>>>(guesses.p, offsets.p, states.p, outs.p, stamps.p, stamps.p + n, int(a), int(b - a),
+                                                                  int(n), r, no_target, cfg, dprog, counters.p, round_flags.p);
+      admitted = b;
+      launches++;
+    };
+    if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
+    if (arrivals) arrivals->wait(0);
+    admit(next_group++);
     unsigned spins = 0;
     bool stream_idle = false;
     while (r < max_rounds) {
+      // scans whose points have arrived meanwhile join the batch; if every admitted scan has finished, wait for the next group
+      while (next_group < n_groups) {
+        if (!arrivals->ready(next_group)) {
+          if (size_t(progress->finished) < admitted) break;
+          arrivals->wait(next_group);
+        }
+        admit(next_group++);
+      }
       // throttle: at most `lookahead` rounds queued ahead of the round the GPU is working on
       while (!progress->all_done && progress->round < r - lookahead) {
         if ((++spins & 0xfff) == 0) {  // safety net: the stream drained (or failed) without the expected progress
@@ -778,7 +805,11 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
           if (q != cudaErrorNotReady) PCR_CUDA_CHECK(q);
         }
       }
-      if (progress->all_done || stream_idle) break;
+      if (progress->all_done) break;
+      if (stream_idle) {
+        if (next_group >= n_groups) break;
+        stream_idle = false;  // the queue ran dry while groups are still outstanding: go on
+      }
       launch_round(src, tgt, prm.ndt_search, int(n), r, 1, cfg, grid, true, true, s);
       r++;
     }

@@ -6,6 +6,7 @@
 #include "voxel.cuh"
 #include "ndt_logic.cuh"
 #include "../../include/pcr_cuda.h"
+#include <functional>
 
 namespace pcr {
 
@@ -44,13 +45,25 @@ struct NdtScanOut {  // per scan, written by the tail that finishes the scan (or
 struct NdtProgress {  // host-mapped pinned memory: the only thing the host looks at while a registration runs
   volatile int round;     // round whose float kernel has started
   volatile int all_done;  // set by the tail that finishes the last scan
-  int pad[14];
+  volatile int finished;  // scans finished when the float kernel of `round` started
+  int pad[13];
 };
 
 struct NdtCounters {  // device
   int finished;
   int work_launches;      // kernel launches that had at least one request
   long long point_evals;  // source points pushed through the evaluation kernels
+};
+
+// Scans may JOIN a running batch: a group of scans becomes eligible when its points have arrived on the device (an upload
+// on another stream). ready(k) = group k can be admitted now (non-blocking); wait(k) = block until it can;
+// event(k) = the CUDA event the registration stream has to wait for before it touches the group's points.
+struct NdtArrivals {
+  size_t n_groups = 0;
+  const size_t* first = nullptr;   // [n_groups + 1] scan index boundaries of the groups
+  std::function<bool(size_t)> ready;
+  std::function<void(size_t)> wait;
+  std::function<cudaEvent_t(size_t)> event;
 };
 
 struct NdtDriver {
@@ -85,7 +98,8 @@ struct NdtDriver {
   void evaluate_one(const float4* src, size_t ns, const NdtTarget& tgt, int search, const NdtEvalParams& ep, NdtEvalResult& out, cudaStream_t s);
   // full registration of n_scans scans (offs: host offsets, n_scans+1)
   int align(const float4* src, const size_t* offs, size_t n_scans, const NdtTarget& tgt, const pcr_params& prm, double* T,
-            int32_t* converged, int32_t* iters, double* trans_prob, bool profile, cudaStream_t s);
+            int32_t* converged, int32_t* iters, double* trans_prob, bool profile, cudaStream_t s, const NdtArrivals* arrivals = nullptr);
+  static constexpr size_t max_streaming_scans = 2048;  // arrivals are supported for batches of up to this many scans
 
  private:
   void ensure_progress();
