@@ -240,21 +240,31 @@ __device__ __forceinline__ void xform_exact(const double* T, double x, double y,
     o[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[r], x), __dmul_rn(T[4 + r], y)), __dmul_rn(T[8 + r], z)), T[12 + r]);
 }
 
-__global__ void __launch_bounds__(kVgBlock)
+__device__ __noinline__ void vgicp_state_step(VgicpState* st, const double* totals, VgicpCfg cfg) { vgicp_logic::on_result(*st, totals, cfg); }
+
+// One evaluation (linearize, or the error of an LM trial) per launch and request. `states` (nullable): the request's parameters
+// come from the scan's state machine and the last block advances it by the result (vgicp_logic.cuh): the host only queues
+// launches. states == nullptr: explicit parameters (introspection entry point).
+__global__ void __launch_bounds__(kVgBlock, 4)
 vgicp_eval_kernel(const float4* __restrict__ src, const double* __restrict__ src_covs, const uint32_t* __restrict__ offs, VgTargetView tgt,
                   const VgicpEvalParams* __restrict__ params, VgicpEvalResult* __restrict__ results, double* __restrict__ partials,
-                  unsigned* __restrict__ tickets, int max_blocks) {
+                  unsigned* __restrict__ tickets, int max_blocks, VgicpState* __restrict__ states, VgicpCfg cfg, VgicpProgress* progress,
+                  int round) {
   const int req = blockIdx.y;
   __shared__ VgicpEvalParams sp;
   __shared__ double sred[kVgNV * (kVgBlock / 32)];
-  __shared__ int s_last;
+  __shared__ double s_tot[kVgNV + 1];
+  __shared__ int s_last, s_pend;
+  if (states && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && progress) progress->round = round;
   {
     const int nwords = sizeof(VgicpEvalParams) / 4;
-    const int* gp = reinterpret_cast<const int*>(params + req);
+    const int* gp = reinterpret_cast<const int*>(states ? &states[req].next : params + req);
     int* spw = reinterpret_cast<int*>(&sp);
     for (int k = threadIdx.x; k < nwords; k += kVgBlock) spw[k] = gp[k];
+    if (threadIdx.x == 0) s_pend = states ? states[req].pend : 1;
   }
   __syncthreads();
+  if (!s_pend) return;  // finished earlier: a launch queued past the end of the registration
   const uint32_t begin = offs[sp.scan], end = offs[sp.scan + 1];
   const int nb = min(int((end - begin + kVgBlock - 1) / kVgBlock), max_blocks);
   if (int(blockIdx.x) >= nb) return;
@@ -341,11 +351,38 @@ vgicp_eval_kernel(const float4* __restrict__ src, const double* __restrict__ src
     double tsum = 0.0;
     for (int b = 0; b < nb; b++) tsum += __ldcg(base + size_t(b) * kVgNV);
     results[req].v[threadIdx.x] = tsum;
+    s_tot[threadIdx.x] = tsum;
   }
+  __syncthreads();
   if (threadIdx.x == 0) tickets[req] = 0;
+  if (!states) return;
+  // every block of this request has read its parameters (they all took a ticket): the state may move on. It is staged in
+  // shared memory so that the single thread that runs the scalar control flow does not chase global memory.
+  __shared__ __align__(16) VgicpState s_state;
+  {
+    const int nwords = sizeof(VgicpState) / 16;
+    const uint4* gp = reinterpret_cast<const uint4*>(states + req);
+    uint4* sp4 = reinterpret_cast<uint4*>(&s_state);
+    for (int k = threadIdx.x; k < nwords; k += kVgBlock) sp4[k] = gp[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) vgicp_state_step(&s_state, s_tot, cfg);
+  __syncthreads();
+  {
+    const int nwords = sizeof(VgicpState) / 16;
+    uint4* gp = reinterpret_cast<uint4*>(states + req);
+    const uint4* sp4 = reinterpret_cast<const uint4*>(&s_state);
+    for (int k = threadIdx.x; k < nwords; k += kVgBlock) gp[k] = sp4[k];
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && s_state.pend == 0 && progress) { __threadfence_system(); progress->done = 1; }
 }
 
+static_assert(sizeof(VgicpState) % 16 == 0, "VgicpState is copied as uint4 words");
+
 VgicpDriver::~VgicpDriver() {
+  if (progress) cudaFreeHost(progress);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
 }
@@ -375,7 +412,7 @@ void VgicpDriver::evaluate(const float4* src, const double* covs, const uint32_t
       PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
     }
     vgicp_eval_kernel<<<dim3(max_blocks, count), kVgBlock, 0, s>>>(src, covs, d_offs, v, d_params.p, d_results.p, partials.p, tickets.p,
-                                                                   max_blocks);
+                                                                   max_blocks, nullptr, VgicpCfg{}, nullptr, 0);
     if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev1, s));
     launches++;
     hot_launches++;
@@ -406,110 +443,87 @@ int VgicpDriver::compute_source_covs(const float4* src, size_t ns, int k, KeySor
 // ================================================================================================================
 // V5. LsqRegistration::computeTransformation / step_lm / step_gn / is_converged (lsq_registration_impl.hpp:53-172)
 // ================================================================================================================
-namespace {
-void make_delta(const double* d, double* D) {  // delta.linear = so3_exp(d[0:3]), delta.translation = d[3:6]; column-major
-  double R[9];
-  hm::so3_exp_matrix(d, R);
-  for (int i = 0; i < 16; i++) D[i] = (i % 5 == 0) ? 1.0 : 0.0;
-  for (int r = 0; r < 3; r++) {
-    for (int c = 0; c < 3; c++) D[c * 4 + r] = R[r * 3 + c];
-    D[12 + r] = d[3 + r];
-  }
-}
-bool lsq_converged(const double* D, double rot_eps, double trans_eps) {
-  double m = 0;
-  for (int r = 0; r < 3; r++) {
-    for (int c = 0; c < 3; c++) m = std::max(m, 1.0 / rot_eps * std::fabs(D[c * 4 + r] - (r == c ? 1.0 : 0.0)));
-    m = std::max(m, 1.0 / trans_eps * std::fabs(D[12 + r]));
-  }
-  return m < 1;
-}
-void unpack(const VgicpEvalResult& r, double* H, double* b) {
-  int k = 1;
-  for (int a = 0; a < 6; a++)
-    for (int c = a; c < 6; c++) { H[a * 6 + c] = r.v[k]; H[c * 6 + a] = r.v[k]; k++; }
-  for (int a = 0; a < 6; a++) b[a] = r.v[22 + a];
-}
-}  // namespace
-
 int VgicpDriver::align(const float4* src, size_t ns, const VgicpTarget& tgt, const pcr_params& prm, double* T, int32_t* converged,
                        int32_t* iters, bool profile, cudaStream_t s) {
   hot_ms = 0.f; hot_launches = 0; n_linearize = 0; n_error = 0; total_corr = 0;
-  uint32_t* ho = h_offsets.ensure(2);
-  ho[0] = 0; ho[1] = uint32_t(ns);
-  offsets.ensure(2);
-  PCR_CUDA_CHECK(cudaMemcpyAsync(offsets.p, ho, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-  h_params.ensure(1);
-  double x0[16];
-  for (int i = 0; i < 16; i++) x0[i] = double(static_cast<float>(T[i]));  // VgicpRegister.cpp:36 cast<float>, lsq :54 cast<double>
-  double lm_lambda = -1.0;
-  bool conv = false;
-  int nr_iterations = 0;
-  auto eval = [&](const double* T0, const double* Ti, bool want) -> const VgicpEvalResult& {
-    VgicpEvalParams& ep = h_params.p[0];
-    std::memcpy(ep.T0, T0, sizeof(double) * 16);
-    std::memcpy(ep.Ti, Ti, sizeof(double) * 16);
-    ep.want_hb = want ? 1 : 0;
-    ep.scan = 0;
-    ep.pad[0] = ep.pad[1] = 0;
-    evaluate(src, src_covs.p, offsets.p, ns, tgt, 1, profile, s);
-    total_corr += (long long)(h_results.p[0].v[28] + 0.5);
-    return h_results.p[0];
-  };
-  for (int it = 0; it < prm.vgicp_max_iters && !conv; it++) {
-    nr_iterations = it;
-    double H[36], b[6], delta[16];
-    const VgicpEvalResult& r0 = eval(x0, x0, true);
-    n_linearize++;
-    const double y0 = r0.v[0];
-    last_cost = y0;
-    last_corr = int64_t(r0.v[28] + 0.5);
-    unpack(r0, H, b);
-    bool ok = false;
-    if (prm.vgicp_optimizer == PCR_LSQ_GN) {
-      double nb[6], d[6];
-      for (int a = 0; a < 6; a++) nb[a] = -b[a];
-      ldlt6_solve(H, nb, d);
-      make_delta(d, delta);
-      mat4_mul(delta, x0, x0);
-      ok = true;
-    } else {
-      if (lm_lambda < 0.0) {
-        double mx = 0;
-        for (int a = 0; a < 6; a++) mx = std::max(mx, std::fabs(H[a * 6 + a]));
-        lm_lambda = prm.vgicp_lm_init_lambda * mx;
-      }
-      double nu = 2.0;
-      for (int li = 0; li < prm.vgicp_lm_max_iters; li++) {
-        double A[36], nb[6], d[6], xi[16];
-        for (int a = 0; a < 36; a++) A[a] = H[a];
-        for (int a = 0; a < 6; a++) { A[a * 6 + a] += lm_lambda; nb[a] = -b[a]; }
-        ldlt6_solve(A, nb, d);
-        make_delta(d, delta);
-        mat4_mul(delta, x0, xi);
-        const double yi = eval(x0, xi, false).v[0];
-        n_error++;
-        double den = 0;
-        for (int a = 0; a < 6; a++) den += d[a] * (lm_lambda * d[a] - b[a]);
-        const double rho = (y0 - yi) / den;
-        if (rho < 0) {
-          if (lsq_converged(delta, prm.vgicp_rot_eps, prm.vgicp_trans_eps)) { ok = true; break; }
-          lm_lambda = nu * lm_lambda;
-          nu = 2 * nu;
-          continue;
-        }
-        std::memcpy(x0, xi, sizeof(xi));
-        lm_lambda = lm_lambda * std::max(1.0 / 3.0, 1 - std::pow(2 * rho - 1, 3));
-        ok = true;
-        break;
-      }
+  VgicpCfg cfg{};
+  cfg.optimizer = prm.vgicp_optimizer == PCR_LSQ_GN ? 1 : 0;
+  cfg.max_iters = prm.vgicp_max_iters;
+  cfg.lm_max_iters = prm.vgicp_lm_max_iters;
+  cfg.rot_eps = prm.vgicp_rot_eps; cfg.trans_eps = prm.vgicp_trans_eps; cfg.lm_init_lambda = prm.vgicp_lm_init_lambda;
+  VgicpState* hs = h_states.ensure(1);
+  memset(hs, 0, sizeof(VgicpState));
+  vgicp_logic::start(*hs, T, 0, cfg);
+  const bool run = tgt.nvox > 0 && ns > 0;
+  if (!run) {
+    // no voxel / no point: every evaluation is all zeros (no block would contribute) — the state machine digests them here
+    const double zeros[kVgNV + 1] = {0};
+    for (int guard = 0; hs->pend && guard < 100000; guard++) vgicp_logic::on_result(*hs, zeros, cfg);
+  } else {
+    if (!progress) PCR_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&progress), sizeof(VgicpProgress), cudaHostAllocMapped));
+    progress->round = -1;
+    progress->done = 0;
+    VgicpProgress* dprog = nullptr;
+    PCR_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dprog), progress, 0));
+    uint32_t* ho = h_offsets.ensure(2);
+    ho[0] = 0; ho[1] = uint32_t(ns);
+    offsets.ensure(2);
+    d_states.ensure(1);
+    d_results.ensure(1);
+    PCR_CUDA_CHECK(cudaMemcpyAsync(offsets.p, ho, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    PCR_CUDA_CHECK(cudaMemcpyAsync(d_states.p, hs, sizeof(VgicpState), cudaMemcpyHostToDevice, s));
+    // 4 blocks of 128 threads are resident per SM (126 registers): one resident wave
+    const int max_blocks = std::max(1, std::min(int((ns + kVgBlock - 1) / kVgBlock), kNumSMs * 4));
+    partials.ensure(size_t(max_blocks) * kVgNV);
+    if (tickets.cap < 1) {
+      tickets.ensure(1);
+      PCR_CUDA_CHECK(cudaMemsetAsync(tickets.p, 0, tickets.cap * sizeof(unsigned), s));
     }
-    if (!ok) break;  // "lm not converged!!" (lsq_registration_impl.hpp:69-72)
-    conv = lsq_converged(delta, prm.vgicp_rot_eps, prm.vgicp_trans_eps);
+    VgTargetView v;
+    v.vox = tgt.vox.p; v.table = tgt.table.p; v.res = tgt.resolution;
+    for (int a = 0; a < 3; a++) { v.cmin[a] = tgt.cmin[a]; v.cdim[a] = tgt.cdim[a]; }
+    if (profile) {
+      if (!ev0) { PCR_CUDA_CHECK(cudaEventCreate(&ev0)); PCR_CUDA_CHECK(cudaEventCreate(&ev1)); }
+      PCR_CUDA_CHECK(cudaEventRecord(ev0, s));
+    }
+    // The host only queues evaluation launches, a few ahead of the GPU (round counter and done flag in host-mapped memory);
+    // launches queued past the end return on their first instructions.
+    static const int lookahead = [] { const char* e = std::getenv("PCR_VGICP_LOOKAHEAD"); return e ? std::max(1, std::atoi(e)) : 3; }();
+    const int max_rounds = std::max(1, prm.vgicp_max_iters) * (std::max(0, prm.vgicp_lm_max_iters) + 1) + 2;
+    int r = 0;
+    unsigned spins = 0;
+    bool idle = false;
+    while (r < max_rounds) {
+      while (!progress->done && progress->round < r - lookahead) {
+        if ((++spins & 0xfff) == 0) {
+          const cudaError_t q = cudaStreamQuery(s);
+          if (q == cudaSuccess) { idle = true; break; }
+          if (q != cudaErrorNotReady) PCR_CUDA_CHECK(q);
+        }
+      }
+      if (progress->done || idle) break;
+      vgicp_eval_kernel<<<dim3(max_blocks, 1), kVgBlock, 0, s>>>(src, src_covs.p, offsets.p, v, nullptr, d_results.p, partials.p, tickets.p, max_blocks,
+                                                                 d_states.p, cfg, dprog, r);
+      launches++;
+      r++;
+    }
+    if (profile) PCR_CUDA_CHECK(cudaEventRecord(ev1, s));
+    PCR_CUDA_CHECK(cudaMemcpyAsync(hs, d_states.p, sizeof(VgicpState), cudaMemcpyDeviceToHost, s));
+    PCR_CUDA_CHECK(cudaStreamSynchronize(s));
+    PCR_CUDA_CHECK(cudaGetLastError());
+    if (hs->pend) throw CudaError("VGICP: the evaluation launches ended before the registration finished");
+    if (profile) {
+      float ms = 0.f;
+      PCR_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+      hot_ms += ms;
+    }
   }
-  for (int i = 0; i < 16; i++) T[i] = double(static_cast<float>(x0[i]));  // final_transformation_ = x0.cast<float>()
-  if (converged) *converged = conv ? 1 : 0;
-  if (iters) *iters = nr_iterations;
+  n_linearize = hs->n_linearize; n_error = hs->n_error; total_corr = hs->total_corr;
+  hot_launches = n_linearize + n_error;
+  last_cost = hs->last_cost; last_corr = hs->last_corr;
+  for (int i = 0; i < 16; i++) T[i] = double(static_cast<float>(hs->x0[i]));  // final_transformation_ = x0.cast<float>()
+  if (converged) *converged = hs->converged;
+  if (iters) *iters = hs->nr_iterations;
   return 0;
 }
 

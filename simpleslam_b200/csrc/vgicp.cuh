@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "voxel.cuh"
 #include "knn.cuh"
+#include "vgicp_logic.cuh"
 #include "../../include/pcr_cuda.h"
 #include <utility>
 #include <vector>
@@ -47,16 +48,18 @@ struct VgicpTarget {
   DevBuf<int32_t> table;      // dense cell -> voxel id or -1
 };
 
-struct VgicpEvalParams {
-  double T0[16];
-  double Ti[16];
-  int want_hb;
-  int scan;
-  int pad[2];
-};
 struct VgicpEvalResult { double v[30]; };  // cost, H upper 21, b 6, count, pad
 
+struct VgicpProgress {  // host-mapped pinned memory
+  volatile int round;  // evaluation launch that has started
+  volatile int done;   // the registration has finished (set by the tail that ends it)
+  int pad[14];
+};
+
 struct VgicpDriver {
+  DevBuf<VgicpState> d_states;
+  PinBuf<VgicpState> h_states;
+  VgicpProgress* progress = nullptr;
   DevBuf<VgicpEvalParams> d_params;
   DevBuf<VgicpEvalResult> d_results;
   DevBuf<double> partials;

@@ -4,6 +4,7 @@
 #include "../../simpleslam_b200/csrc/dev_linalg.cuh"
 #include "../../simpleslam_b200/csrc/host_math.hpp"
 #include "../../simpleslam_b200/csrc/ndt_logic.cuh"
+#include "../../simpleslam_b200/csrc/vgicp_logic.cuh"
 #include <cstring>
 
 extern "C" {
@@ -63,5 +64,29 @@ void shim_ndt_result(const void* stv, float* final_T, int* converged, int* nr_it
   const pcr::NdtScanState& st = *static_cast<const pcr::NdtScanState*>(stv);
   for (int i = 0; i < 16; i++) final_T[i] = st.final_T[i];
   *converged = st.converged; *nr_iterations = st.nr_iterations; *n_evals = st.n_evals; *n_hess = st.n_hess; *score = st.score;
+}
+// fast_gicp LM / GN state machine (vgicp_logic.cuh), the code vgicp_eval_kernel's tail runs on the device
+size_t shim_vgicp_state_size() { return sizeof(pcr::VgicpState); }
+static pcr::VgicpCfg shim_vg_cfg(int optimizer, int max_iters, int lm_max_iters, double rot_eps, double trans_eps, double lm_init_lambda) {
+  pcr::VgicpCfg c{};
+  c.optimizer = optimizer; c.max_iters = max_iters; c.lm_max_iters = lm_max_iters;
+  c.rot_eps = rot_eps; c.trans_eps = trans_eps; c.lm_init_lambda = lm_init_lambda;
+  return c;
+}
+void shim_vgicp_start(void* st, const double* Tguess, int optimizer, int max_iters, int lm_max_iters, double rot_eps, double trans_eps, double lm_init_lambda) {
+  pcr::vgicp_logic::start(*static_cast<pcr::VgicpState*>(st), Tguess, 0, shim_vg_cfg(optimizer, max_iters, lm_max_iters, rot_eps, trans_eps, lm_init_lambda));
+}
+void shim_vgicp_on_result(void* st, const double* v29, int optimizer, int max_iters, int lm_max_iters, double rot_eps, double trans_eps, double lm_init_lambda) {
+  pcr::vgicp_logic::on_result(*static_cast<pcr::VgicpState*>(st), v29, shim_vg_cfg(optimizer, max_iters, lm_max_iters, rot_eps, trans_eps, lm_init_lambda));
+}
+void shim_vgicp_pending(const void* stv, int* pend, int* want_hb, double* T0, double* Ti) {
+  const pcr::VgicpState& st = *static_cast<const pcr::VgicpState*>(stv);
+  *pend = st.pend; *want_hb = st.next.want_hb;
+  for (int i = 0; i < 16; i++) { T0[i] = st.next.T0[i]; Ti[i] = st.next.Ti[i]; }
+}
+void shim_vgicp_result(const void* stv, double* T, int* converged, int* nr_iterations, int* n_linearize, int* n_error) {
+  const pcr::VgicpState& st = *static_cast<const pcr::VgicpState*>(stv);
+  for (int i = 0; i < 16; i++) T[i] = st.x0[i];
+  *converged = st.converged; *nr_iterations = st.nr_iterations; *n_linearize = st.n_linearize; *n_error = st.n_error;
 }
 }
