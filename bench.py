@@ -220,12 +220,13 @@ def load_peak():
 def load_traffic(key, kernel_prefix):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same workload"""
     for fn in ("r02_traffic.json", "r01_traffic.json"):
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", fn))).get(key)
-            if tr and tr["kernel"].startswith(kernel_prefix):
-                return tr["dram_bytes_per_launch"], "profiles/%s: %s (ncu --set full, one launch)" % (fn, tr["source"])
-        except Exception:
-            pass
+        for k in (key if isinstance(key, (list, tuple)) else [key]):
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", fn))).get(k)
+                if tr and tr["kernel"].startswith(kernel_prefix):
+                    return tr["dram_bytes_per_launch"], "profiles/%s[%s]: %s (ncu --set full, one launch)" % (fn, k, tr["source"])
+            except Exception:
+                pass
     return None, None
 
 
@@ -881,7 +882,7 @@ def measure_c4_job(args, method, rank, world, local_rank, dist, dev, cpu=True):
             if method == "loam":
                 qs = [scans[u][:, :3].astype(np.float64) @ guesses[u][:3, :3].T + guesses[u][:3, 3] for u in range(min(4, n_local))]
                 c_bar = float(orc.neighbourhood27(dst, np.concatenate(qs), 1.0, threads=cores))
-        roof = make_roofline(method, prof, c_bar, "c4_" + method)
+        roof = make_roofline(method, prof, c_bar, ["c4_job_" + method, "c4_" + method])
         idx_roof = measure_index_build(ctx, dev, dst, raw_map, 0.2, method) if world == 1 else None
         out = {
             "metric": "scan registrations/sec (%s)" % method.upper(), "value": value, "unit": "registrations/s", "n_gpus": world, "steps": args.steps,

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 SRC = os.path.join(ROOT, "gpurun_out")
 # workload -> captures (name, kernel); the FIRST one is the kernel bench.py reports roofline.traffic for
-CAPS = {"c2_ndt": [("ndt", "ndt_round_kernel")], "c4_ndt": [("ndt", "ndt_round_kernel")],
+CAPS = {"c4_job_ndt": [("ndt", "ndt_round_kernel")], "c2_ndt": [("ndt", "ndt_round_kernel")], "c4_ndt": [("ndt", "ndt_round_kernel")],
         "c1_loam": [("search", "loam_search_kernel"), ("fit", "loam_fit_kernel")], "c4_loam": [("search", "loam_search_kernel"), ("fit", "loam_fit_kernel")],
         "c3_vgicp": [("knn", "gicp_knn_kernel"), ("eval", "vgicp_eval_kernel")]}
 
@@ -45,7 +45,7 @@ def launches(rnd, wl):
         a[0] += 1
         a[1] += t
     tot = sum(a[1] for a in agg.values()) or 1.0
-    out = ["# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --workload %s --steps 2 --warmup 3 --no-cpu-baseline" % wl,
+    out = ["# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --workload %s --steps 2 --warmup 3 --no-cpu-baseline --no-workloads" % wl,
            "# per-launch times are cold-cache and serialised: compare SHARES with bench.py's kernel_share_of_step, not absolutes",
            "%-62s %8s %12s %10s %7s %11s  %s" % ("kernel", "launches", "total_us", "mean_us", "share", "lanes/inst", "last block x grid")]
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):

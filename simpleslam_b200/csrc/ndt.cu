@@ -348,13 +348,46 @@ __device__ __forceinline__ void ndt_fill_request_warp(NdtScanState* st, double* 
   __syncwarp();
 }
 
+constexpr int kNdtGroup = 32;  // blocks per first-level group of a request's two-level reduction
+
+// totals of n_rows rows of kNdtNV partial sums: four interleaved slices per component (coalesced: a step of the loop reads
+// four consecutive rows), combined in a fixed order. The accumulator columns in `sacc` are free when this runs.
+__device__ __forceinline__ void ndt_reduce_rows(const double* __restrict__ rows, int n_rows, double* sacc, double* s_tot, int tid) {
+  if (tid < 4 * kNdtNV) {
+    const int comp = tid % kNdtNV, slice = tid / kNdtNV;
+    const double* pb = rows + comp;
+    double t0 = 0.0, t1 = 0.0;
+    int b = slice;
+    for (; b + 4 < n_rows; b += 8) {
+      t0 += __ldcg(pb + size_t(b) * kNdtNV);
+      t1 += __ldcg(pb + size_t(b + 4) * kNdtNV);
+    }
+    if (b < n_rows) t0 += __ldcg(pb + size_t(b) * kNdtNV);
+    sacc[slice * kNdtNV + comp] = t0 + t1;
+  }
+  __syncthreads();
+  if (tid < kNdtNV) s_tot[tid] = (sacc[tid] + sacc[kNdtNV + tid]) + (sacc[2 * kNdtNV + tid] + sacc[3 * kNdtNV + tid]);
+  __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <int SEARCH, bool DOUBLE_PATH>
 __global__ void __launch_bounds__(kNdtBlock, DOUBLE_PATH ? 2 : 5)
 ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, NdtTargetView tgt, NdtScanState* __restrict__ states,
                  NdtScanOut* __restrict__ outs, int32_t* __restrict__ float_round, int32_t* __restrict__ hess_round, int n_scans, int round,
                  int step, NdtCfg cfg, double* __restrict__ partials, unsigned* __restrict__ tickets, NdtProgress* progress,
-                 NdtCounters* __restrict__ counters, int* __restrict__ round_flags, int max_bpr) {
+                 NdtCounters* __restrict__ counters, int* __restrict__ round_flags, int max_bpr, double* __restrict__ gpart,
+                 unsigned* __restrict__ gtickets) {
   constexpr int NNB = NbTraits<SEARCH>::N;
+  // programmatic dependent launch: let the next kernel of the stream be scheduled, then wait until the previous grid has
+  // completed and its writes are visible (both are no-ops for a launch without the attribute)
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // round_flags[r]: bit 0 = some scan wants a float evaluation in round r, bit 1 = a double-path Hessian. Written only by
   // tails of EARLIER kernels (or, for bit 1 of this round, by the float kernel that has completed): a launch without
   // work returns at once (most double-path launches, and the rounds queued past the end of the registration)
@@ -363,6 +396,7 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     progress->round = round;
   }
   if (step && !(round_flags[round] & (DOUBLE_PATH ? 2 : 1))) return;
+  if (cfg.trace && blockIdx.x == 0 && threadIdx.x == 0) counters->t_tail[4] = globaltimer_ns();
   __shared__ __align__(16) NdtScanState s_state;
   __shared__ double sacc[kNdtNV * kNdtBlock];
   __shared__ double s_tot[kNdtNV + 1];
@@ -540,26 +574,44 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     }
     if (lane == 0) __threadfence();  // one fence per writer warp, after all of its partial sums
     __syncthreads();
+    // ---- 4. block partials -> totals in a fixed order, by whichever block finishes last. A single scan owns the whole wave
+    // (740 partial rows, 170 KB): one block reading them all took as long as the evaluation itself, so requests with more
+    // than kNdtGroup blocks are reduced in two levels - the last block of every group of kNdtGroup consecutive blocks adds
+    // up its group's rows, the last of those adds up the group rows.
+    const bool trace = cfg.trace && tid == 0;
+    const int n_groups = (nb + kNdtGroup - 1) / kNdtGroup;
+    const double* rows = partials + size_t(req) * bpr * kNdtNV;
+    int n_rows = nb;
+    if (n_groups > 1) {
+      const int gid = sub / kNdtGroup, gsize = min(kNdtGroup, nb - gid * kNdtGroup);
+      const size_t gslot = size_t(req) * ((bpr + kNdtGroup - 1) / kNdtGroup);
+      if (tid == 0) {
+        const unsigned t = atomicAdd(gtickets + gslot + gid, 1u);
+        s_last = (t == unsigned(gsize - 1));
+      }
+      __syncthreads();
+      if (!s_last) continue;  // block-uniform
+      __threadfence();
+      ndt_reduce_rows(rows + size_t(gid) * kNdtGroup * kNdtNV, gsize, sacc, s_tot, tid);
+      if (tid < kNdtNV) {
+        gpart[(gslot + gid) * kNdtNV + tid] = s_tot[tid];
+        __threadfence();
+      }
+      if (tid == 0) gtickets[gslot + gid] = 0;
+      __syncthreads();
+      rows = gpart + gslot * kNdtNV;
+      n_rows = n_groups;
+    }
     if (tid == 0) {
-      unsigned t = atomicAdd(tickets + scan, 1u);
-      s_last = (t == unsigned(nb - 1));
+      const unsigned t = atomicAdd(tickets + scan, 1u);
+      s_last = (t == unsigned(n_rows - 1));
     }
     __syncthreads();
     if (!s_last) continue;  // block-uniform
-    // ---- 4. last block of the request: totals, then the scan's state machine
     __threadfence();
-    // four slices of the block partials per component, combined in a fixed order (a single scan owns the whole wave: 740
-    // partials — one thread per component would walk them one dependent add after the other)
-    if (tid < 4 * kNdtNV) {
-      const int comp = tid % kNdtNV, slice = tid / kNdtNV;
-      const double* pb = partials + size_t(req) * bpr * kNdtNV + comp;
-      double tsum = 0.0;
-      for (int b = slice; b < nb; b += 4) tsum += __ldcg(pb + size_t(b) * kNdtNV);
-      sacc[slice * kNdtNV + comp] = tsum;  // the accumulators are free again
-    }
-    __syncthreads();
-    if (tid < kNdtNV) s_tot[tid] = (sacc[tid] + sacc[kNdtNV + tid]) + (sacc[2 * kNdtNV + tid] + sacc[3 * kNdtNV + tid]);
-    __syncthreads();
+    if (trace) counters->t_tail[0] = globaltimer_ns();
+    ndt_reduce_rows(rows, n_rows, sacc, s_tot, tid);
+    if (trace) counters->t_tail[1] = globaltimer_ns();
     if (tid < 30) outs[scan].v[tid] = tid < kNdtNV ? s_tot[tid] : 0.0;
     if (tid == 0) {
       tickets[scan] = 0;
@@ -568,9 +620,11 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     if (step && warp == 0) {
       if (lane == 0) ndt_state_step(&s_state, s_tot, cfg);  // decides the next evaluation ...
       __syncwarp();
+      if (trace) counters->t_tail[2] = globaltimer_ns();
       ndt_fill_request_warp(&s_state, s_trig, lane);          // ... whose transform and derivative tables the warp fills in
     }
     __syncthreads();
+    if (trace) counters->t_tail[3] = globaltimer_ns();
     if (step) {
       const int nwords = sizeof(NdtScanState) / 16;
       uint4* gp = reinterpret_cast<uint4*>(states + scan);
@@ -591,38 +645,56 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
         }
       }
     }
+    if (trace) counters->t_tail[5] = globaltimer_ns();
     __syncthreads();  // s_state / s_tot are reused by the next item
   }
 }
 
-// start of a registration: one thread per scan runs ndt_logic::start (guess -> p, first request). Empty scans and an
-// empty target evaluate to all-zero sums (no block would contribute), which the state machine digests right here.
-__global__ void ndt_init_kernel(const double* __restrict__ guesses, const uint32_t* __restrict__ offs, NdtScanState* __restrict__ states,
-                                NdtScanOut* __restrict__ outs, int32_t* __restrict__ float_round, int32_t* __restrict__ hess_round, int first_scan,
-                                int count, int n_scans, int first_round, int no_target, NdtCfg cfg, NdtProgress* progress,
-                                NdtCounters* __restrict__ counters, int* __restrict__ round_flags) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= count) return;
+// start of a registration: one WARP per scan. Lane 0 runs ndt_logic::start (guess -> p, first request), the warp fills in
+// the request's transform and derivative tables exactly as the evaluation kernels' tails do (ndt_fill_request_warp).
+// Empty scans and an empty target evaluate to all-zero sums (no block would contribute), which the state machine digests
+// right here.
+constexpr int kNdtInitWarps = 4;
+__global__ void __launch_bounds__(kNdtInitWarps * 32)
+ndt_init_kernel(const double* __restrict__ guesses, const uint32_t* __restrict__ offs, NdtScanState* __restrict__ states,
+                NdtScanOut* __restrict__ outs, int32_t* __restrict__ float_round, int32_t* __restrict__ hess_round, int first_scan,
+                int count, int n_scans, int first_round, int no_target, NdtCfg cfg, NdtProgress* progress,
+                NdtCounters* __restrict__ counters, int* __restrict__ round_flags) {
+  __shared__ __align__(16) NdtScanState s_st[kNdtInitWarps];
+  __shared__ double s_trig[kNdtInitWarps][12];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.x * kNdtInitWarps + warp;
+  if (k >= count) return;  // warp-uniform
   const int s = first_scan + k;
-  NdtScanState st;
-  ndt_logic::start(st, guesses + size_t(s) * 16, s);
-  hess_round[s] = -1;
-  if (no_target || offs[s + 1] == offs[s]) {
-    double zeros[kNdtNV];
-    for (int q = 0; q < kNdtNV; q++) zeros[q] = 0.0;
-    while (st.pend != NDT_PEND_NONE) ndt_logic::on_result(st, zeros, cfg);
+  NdtScanState* st = &s_st[warp];
+  if (lane == 0) {
+    ndt_logic::start(*st, guesses + size_t(s) * 16, s);
+    hess_round[s] = -1;
+    if (no_target || offs[s + 1] == offs[s]) {
+      double zeros[kNdtNV];
+      for (int q = 0; q < kNdtNV; q++) zeros[q] = 0.0;
+      while (st->pend != NDT_PEND_NONE) ndt_logic::on_result(*st, zeros, cfg);
+    }
   }
-  ndt_logic::fill_request(st);
-  states[s] = st;
-  if (st.pend == NDT_PEND_NONE) {
-    float_round[s] = -1;
+  __syncwarp();
+  ndt_fill_request_warp(st, s_trig[warp], lane);
+  {
+    const int nwords = sizeof(NdtScanState) / 16;
+    uint4* gp = reinterpret_cast<uint4*>(states + s);
+    const uint4* sp4 = reinterpret_cast<const uint4*>(st);
+    for (int q = lane; q < nwords; q += 32) gp[q] = sp4[q];
+  }
+  if (st->pend == NDT_PEND_NONE) {
     NdtScanOut* o = outs + s;
-    for (int q = 0; q < 16; q++) o->final_T[q] = st.final_T[q];
-    o->converged = st.converged; o->nr_iterations = st.nr_iterations; o->n_evals = st.n_evals; o->n_hess = st.n_hess;
-    o->n_pairs = st.n_pairs; o->score = st.score;
-    const int f = atomicAdd(&counters->finished, 1) + 1;
-    if (f == n_scans && progress) { __threadfence_system(); progress->all_done = 1; }
-  } else {
+    if (lane < 16) o->final_T[lane] = st->final_T[lane];
+    if (lane == 0) {
+      float_round[s] = -1;
+      o->converged = st->converged; o->nr_iterations = st->nr_iterations; o->n_evals = st->n_evals; o->n_hess = st->n_hess;
+      o->n_pairs = st->n_pairs; o->score = st->score;
+      const int f = atomicAdd(&counters->finished, 1) + 1;
+      if (f == n_scans && progress) { __threadfence_system(); progress->all_done = 1; }
+    }
+  } else if (lane == 0) {
     float_round[s] = first_round;  // joins the batch in the next round to be launched
     atomicOr(round_flags + first_round, 1);
   }
@@ -641,12 +713,18 @@ void NdtDriver::ensure_progress() {
 void NdtDriver::prepare(size_t n_scans, int grid_blocks, cudaStream_t s) {
   ensure_progress();
   states.ensure(n_scans); outs.ensure(n_scans); stamps.ensure(2 * n_scans);
-  partials.ensure((size_t(7) * size_t(std::max(grid_blocks, 1)) + 2 * n_scans + 64) * kNdtNV);  // items <= 6 * grid + n_active (+ slack)
+  // rows: items <= 6 * grid + n_active (+ slack); behind them the group rows of the two-level reductions (a request has
+  // groups only when it is cut into more than kNdtGroup items: at most items / kNdtGroup + one per such request of them)
+  const size_t item_rows = size_t(7) * size_t(std::max(grid_blocks, 1)) + 2 * n_scans + 64;
+  const size_t group_rows = size_t(std::max(grid_blocks, 1)) + 64;
+  partials.ensure((item_rows + group_rows) * kNdtNV);
+  gpart_ = partials.p + item_rows * kNdtNV;
   counters.ensure(1);
-  if (tickets.cap < n_scans) {
-    tickets.ensure(n_scans);
+  if (tickets.cap < n_scans + group_rows) {  // all zero between kernels: the last block to arrive resets its ticket
+    tickets.ensure(n_scans + group_rows);
     PCR_CUDA_CHECK(cudaMemsetAsync(tickets.p, 0, tickets.cap * sizeof(unsigned), s));
   }
+  gtickets_ = tickets.p + n_scans;
   PCR_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, sizeof(NdtCounters), s));
   round_flags.ensure(size_t(max_rounds_cap) + 2);
   PCR_CUDA_CHECK(cudaMemsetAsync(round_flags.p, 0, (size_t(max_rounds_cap) + 2) * sizeof(int), s));
@@ -665,14 +743,30 @@ static NdtTargetView make_view(const NdtTarget& tgt) {
   return v;
 }
 
+// Round kernels are launched with programmatic stream serialisation: the next kernel of the stream may be scheduled while
+// this one drains (every block releases its dependents at once and waits for the complete previous grid — griddepcontrol —
+// before it reads anything), which takes the launch latency out of the chain float kernel -> double kernel -> next round.
 template <int SEARCH>
 static void launch_round_t(bool dbl, int grid, cudaStream_t s, const float4* src, const uint32_t* offs, const NdtTargetView& v, NdtScanState* states,
                            NdtScanOut* outs, int32_t* fr, int32_t* hr, int n, int round, int step, const NdtCfg& cfg, double* partials,
-                           unsigned* tickets, NdtProgress* prog, NdtCounters* cnt, int* flags, int max_bpr) {
-  if (dbl)  // 218 registers: two blocks per SM, one resident wave
-    ndt_round_kernel<SEARCH, true><<<std::min(grid, kNumSMs * 2), kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt, flags, max_bpr);
+                           unsigned* tickets, NdtProgress* prog, NdtCounters* cnt, int* flags, int max_bpr, double* gpart, unsigned* gtickets) {
+  // Measured (profiles/README.md): a single scan / a batch of 8 gain 3-7 %, the 1024-scan job loses 2 % -> small batches only.
+  static const int pdl_env = [] { const char* e = std::getenv("PCR_NDT_PDL"); return e ? (std::atoi(e) != 0 ? 1 : 0) : -1; }();
+  const bool pdl = pdl_env >= 0 ? pdl_env != 0 : n < 64;
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(unsigned(dbl ? std::min(grid, kNumSMs * 2) : grid));  // double path: 212 registers, two blocks per SM, one resident wave
+  lc.blockDim = dim3(kNdtBlock);
+  lc.dynamicSmemBytes = 0;
+  lc.stream = s;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = &attr;
+  lc.numAttrs = pdl ? 1 : 0;
+  if (dbl)
+    PCR_CUDA_CHECK(cudaLaunchKernelEx(&lc, ndt_round_kernel<SEARCH, true>, src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt, flags, max_bpr, gpart, gtickets));
   else
-    ndt_round_kernel<SEARCH, false><<<grid, kNdtBlock, 0, s>>>(src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt, flags, max_bpr);
+    PCR_CUDA_CHECK(cudaLaunchKernelEx(&lc, ndt_round_kernel<SEARCH, false>, src, offs, v, states, outs, fr, hr, n, round, step, cfg, partials, tickets, prog, cnt, flags, max_bpr, gpart, gtickets));
 }
 
 void NdtDriver::launch_round(const float4* src, const NdtTarget& tgt, int search, int n, int round, int step, const NdtCfg& cfg, int grid_blocks,
@@ -686,10 +780,10 @@ void NdtDriver::launch_round(const float4* src, const NdtTarget& tgt, int search
     if (part == 0 ? !float_kernel : !double_kernel) continue;
     const bool dbl = part == 1;
     switch (search) {
-      case PCR_NDT_DIRECT1: launch_round_t<PCR_NDT_DIRECT1>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_); break;
-      case PCR_NDT_DIRECT26: launch_round_t<PCR_NDT_DIRECT26>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_); break;
-      case PCR_NDT_KDTREE: launch_round_t<PCR_NDT_KDTREE>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_); break;
-      default: launch_round_t<PCR_NDT_DIRECT7>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_); break;
+      case PCR_NDT_DIRECT1: launch_round_t<PCR_NDT_DIRECT1>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_, gpart_, gtickets_); break;
+      case PCR_NDT_DIRECT26: launch_round_t<PCR_NDT_DIRECT26>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_, gpart_, gtickets_); break;
+      case PCR_NDT_KDTREE: launch_round_t<PCR_NDT_KDTREE>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_, gpart_, gtickets_); break;
+      default: launch_round_t<PCR_NDT_DIRECT7>(dbl, grid_blocks, s, src, offsets.p, v, states.p, outs.p, fr, hr, n, round, step, cfg, partials.p, tickets.p, dprog, counters.p, round_flags.p, max_bpr_, gpart_, gtickets_); break;
     }
     launches++;
   }
@@ -747,6 +841,8 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
   cfg.step_size = prm.ndt_step_size;
   cfg.trans_eps = prm.ndt_trans_eps;
   cfg.max_iters = prm.ndt_max_iters;
+  static const int tail_trace = [] { const char* v = std::getenv("PCR_NDT_TAIL_TRACE"); return v ? std::atoi(v) : 0; }();
+  cfg.trace = tail_trace;
   const int no_target = (tgt.overflow || tgt.nleaves == 0) ? 1 : 0;
   static const int lookahead = [] { const char* v = std::getenv("PCR_NDT_LOOKAHEAD"); return v ? std::max(1, std::atoi(v)) : 3; }();
   // every outer iteration costs at most 1 + kMaxStepIterations float evaluations (+ 1 double-path Hessian in the same round);
@@ -778,7 +874,7 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
       const size_t a = arrivals ? arrivals->first[k] : 0, b = arrivals ? arrivals->first[k + 1] : n;
       if (arrivals) PCR_CUDA_CHECK(cudaStreamWaitEvent(s, arrivals->event(k), 0));
       if (b > a)
-        ndt_init_kernel<<<unsigned((b - a + 127) / 128), 128, 0, s>>>(guesses.p, offsets.p, states.p, outs.p, stamps.p, stamps.p + n, int(a), int(b - a),
+        ndt_init_kernel<<<unsigned((b - a + kNdtInitWarps - 1) / kNdtInitWarps), kNdtInitWarps * 32, 0, s>>>(guesses.p, offsets.p, states.p, outs.p, stamps.p, stamps.p + n, int(a), int(b - a),
                                                                   int(n), r, no_target, cfg, dprog, counters.p, round_flags.p);
       admitted = b;
       launches++;
@@ -821,6 +917,12 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
     PCR_CUDA_CHECK(cudaStreamSynchronize(s));
     PCR_CUDA_CHECK(cudaGetLastError());
     if (hc->finished != int(n)) throw CudaError("NDT: the evaluation rounds ended before every scan finished");
+    if (cfg.trace) {  // the LAST request tail that ran: ns from its kernel's start
+      const unsigned long long* t = hc->t_tail;
+      std::fprintf(stderr, "[pcr ndt tail] kernel start -> last block %.1f us, totals +%.1f, state step +%.1f, request filled +%.1f, state stored +%.1f\n",
+                   1e-3 * double((long long)(t[0] - t[4])), 1e-3 * double((long long)(t[1] - t[0])), 1e-3 * double((long long)(t[2] - t[1])),
+                   1e-3 * double((long long)(t[3] - t[2])), 1e-3 * double((long long)(t[5] - t[3])));
+    }
     if (profile) {
       float ms = 0.f;
       PCR_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));

@@ -53,6 +53,7 @@ struct NdtCounters {  // device
   int finished;
   int work_launches;      // kernel launches that had at least one request
   long long point_evals;  // source points pushed through the evaluation kernels
+  unsigned long long t_tail[6];  // NdtCfg::trace: %globaltimer at [4] kernel start, [0] last block found, [1] totals, [2] state step, [3] request filled, [5] state stored
 };
 
 // Scans may JOIN a running batch: a group of scans becomes eligible when its points have arrived on the device (an upload
@@ -77,6 +78,8 @@ struct NdtDriver {
   DevBuf<NdtCounters> counters;
   DevBuf<int> round_flags;  // per round: which kinds of evaluation are wanted (lets idle launches return at once)
   static constexpr int max_rounds_cap = 4096;
+  double* gpart_ = nullptr;      // group rows of the two-level reduction (inside `partials`)
+  unsigned* gtickets_ = nullptr;  // their tickets (inside `tickets`)
   int max_bpr_ = 1;         // blocks a single scan can use at most: ceil(points / block)
   PinBuf<NdtScanOut> h_outs;
   PinBuf<NdtScanState> h_state;

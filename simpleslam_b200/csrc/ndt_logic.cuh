@@ -24,7 +24,7 @@ struct NdtEvalParams {  // per scan, per evaluation
 struct NdtCfg {  // the tunables the control flow reads (pcr_params)
   double step_size, trans_eps;
   int max_iters;
-  int pad;
+  int trace;  // PCR_NDT_TAIL_TRACE=1: the tail of a request stamps %globaltimer into NdtCounters::t_tail (single-scan diagnostics)
 };
 
 enum { NDT_PEND_NONE = 0, NDT_PEND_FLOAT = 1, NDT_PEND_DOUBLE = 2 };
