@@ -113,10 +113,24 @@ static LoamParams loam_params(const pcr_params& p) {
   return lp;
 }
 
+// the caller's current device is restored when the call returns (a host with its own CUDA work on another GPU)
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    PCR_CUDA_CHECK(cudaSetDevice(dev));
+  }
+  ~DeviceScope() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+
 #define PCR_API_BEGIN(c)                                   \
   if (!(c)) return PCR_ERR_INVALID;                        \
   try {                                                    \
-    PCR_CUDA_CHECK(cudaSetDevice((c)->device));
+    DeviceScope pcr_device_scope((c)->device);
 #define PCR_API_END(c)                                     \
   }                                                        \
   catch (const CudaError& e) {                             \
@@ -188,7 +202,7 @@ extern "C" int pcr_create(const pcr_params* p, pcr_ctx** out) {
   c->prm = *p;
   c->device = p->device;
   try {
-    PCR_CUDA_CHECK(cudaSetDevice(c->device));
+    DeviceScope scope(c->device);
     PCR_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     PCR_CUDA_CHECK(cudaEventCreate(&c->ev_a));
     PCR_CUDA_CHECK(cudaEventCreate(&c->ev_b));
@@ -203,6 +217,8 @@ extern "C" int pcr_create(const pcr_params* p, pcr_ctx** out) {
 
 extern "C" void pcr_destroy(pcr_ctx* c) {
   if (!c) return;
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
   cudaSetDevice(c->device);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   for (cudaEvent_t e : c->ev_up) cudaEventDestroy(e);
@@ -210,6 +226,7 @@ extern "C" void pcr_destroy(pcr_ctx* c) {
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
   delete c;
+  if (prev >= 0) cudaSetDevice(prev);
 }
 
 extern "C" const char* pcr_last_error(const pcr_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }

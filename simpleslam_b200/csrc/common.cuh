@@ -1,5 +1,6 @@
 // Shared device/host utilities for the PCR CUDA library (sm_100a).
 #pragma once
+#include <exception>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -116,7 +117,16 @@ struct DevBuf {
     return p;
   }
   void release() {
-    if (p) DevPool::release(p, bytes_, dev_);
+    if (p) {
+      if (std::uncaught_exceptions() > 0) {  // unwinding: queued work may still touch the buffer; the pool hands it to anyone
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != dev_) cudaSetDevice(dev_);
+        cudaDeviceSynchronize();
+        if (cur >= 0 && cur != dev_) cudaSetDevice(cur);
+      }
+      DevPool::release(p, bytes_, dev_);
+    }
     p = nullptr;
     cap = 0;
   }

@@ -69,3 +69,23 @@ def test_multi_equals_single_context(method, case_fn):
         # a shard of 2-3 scans partitions the wave differently from the 9-scan batch: equal to rounding
         assert ca == cb and np.allclose(a, b, rtol=0, atol=1e-6 if method == capi.PCR_NDT else 1e-9)
     m.close()
+
+
+@pytest.mark.gpu
+def test_api_calls_leave_the_callers_current_device_alone():
+    """A host with CUDA work of its own on another GPU: every entry point switches to the context's device and back."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    case = data.ndt_case()
+    torch.cuda.set_device(0)
+    ctx = capi.Context(capi.PCR_NDT, device=1)
+    assert torch.cuda.current_device() == 0
+    ctx.set_target(case["dst"])
+    T, conv = ctx.align(case["src"], case["T_guess"])
+    assert torch.cuda.current_device() == 0 and conv
+    ref = capi.Context(capi.PCR_NDT, device=0)
+    ref.set_target(case["dst"])
+    T0, _ = ref.align(case["src"], case["T_guess"])
+    assert np.array_equal(T, T0)
+    del ctx
+    assert torch.cuda.current_device() == 0
