@@ -88,10 +88,14 @@ int build_morton_grid(const float4* pts, size_t n, MortonGrid& grid, BBoxWork& b
   PCR_CUDA_CHECK(cudaMemsetAsync(grid.tables.p, 0, size_t(kKnnLevels) * cap * sizeof(uint4), s));
   const unsigned blocks = unsigned((n + 255) / 256);
   morton_code_kernel<<<blocks, 256, 0, s>>>(pts, n, mn[0], mn[1], mn[2], grid.inv_h0, grid.dim0[0], grid.dim0[1], grid.dim0[2], grid.c0.p, grid.v0.p);
+  // only the bits the extent uses take part in the sort: a 200 m cloud at 1/32 m needs 13 bits per axis = 5 radix passes, not 8
+  int axis_bits = 1;
+  while ((1ll << axis_bits) < (long long)m) axis_bits++;
+  const int end_bit = std::min(63, 3 * axis_bits);
   size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, grid.c0.p, grid.c1.p, grid.v0.p, grid.v1.p, int(n), 0, 63, s);
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, grid.c0.p, grid.c1.p, grid.v0.p, grid.v1.p, int(n), 0, end_bit, s);
   grid.tmp.ensure(bytes);
-  PCR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(grid.tmp.p, bytes, grid.c0.p, grid.c1.p, grid.v0.p, grid.v1.p, int(n), 0, 63, s));
+  PCR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(grid.tmp.p, bytes, grid.c0.p, grid.c1.p, grid.v0.p, grid.v1.p, int(n), 0, end_bit, s));
   morton_table_kernel<<<blocks, 256, 0, s>>>(pts, grid.c1.p, grid.v1.p, n, grid.pts.p, grid.tables.p, cap);
   PCR_CUDA_CHECK(cudaGetLastError());
   grid.built = true;
