@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["api.cu", "voxel.cu", "knn.cu", "loam.cu", "ndt.cu", "vgicp.cu", "scancontext.cu"]
 HEADERS = ["common.cuh", "voxel.cuh", "loam.cuh", "ndt.cuh", "vgicp.cuh", "knn.cuh", "scancontext.cuh", "dev_linalg.cuh", "host_math.hpp", "ndt_logic.cuh", "vgicp_logic.cuh", "../../include/pcr_cuda.h"]
-LIB = os.path.join(CSRC, "libpcr_cuda.so")
+LIB = os.environ.get("PCR_LIB_OUT") or os.path.join(CSRC, "libpcr_cuda.so")  # PCR_LIB_OUT + PCR_NVCC_EXTRA: tuning variants
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Wno-deprecated-declarations", "-Xcompiler", "-Wno-deprecated-declarations"]
 
@@ -33,8 +33,8 @@ def build(force=False, verbose=False):
     host_cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else None
     objs, procs = [], []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-ccbin", host_cxx] if host_cxx else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(CSRC, src.replace(".cu", ".o")) if LIB.endswith("libpcr_cuda.so") else LIB + "." + src.replace(".cu", ".o")
+        cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("PCR_NVCC_EXTRA", "").split() + (["-ccbin", host_cxx] if host_cxx else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

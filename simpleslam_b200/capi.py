@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpcr_cuda.so")
+LIB_PATH = (os.environ.get("PCR_LIB") or "").strip() or os.path.join(_HERE, "csrc", "libpcr_cuda.so")  # PCR_LIB: a tuning variant built by build.py
 _LIB = None
 
 PCR_LOAM, PCR_NDT, PCR_VGICP = 0, 1, 2

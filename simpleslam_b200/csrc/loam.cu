@@ -531,6 +531,7 @@ __device__ __noinline__ void exact_search_one(const GridView& grid, float qf0, f
   for (int k = 0; k < 5; k++) wj[k] = best[k].j;
 }
 
+template <bool PREFETCH>
 __global__ void __launch_bounds__(kLoamBlock, 4)
 loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, GridView grid, LoamParams prm,
                    const LoamState* __restrict__ states, double slack, int max_ring, float4* __restrict__ nb_out, int2* __restrict__ cnt_out,
@@ -615,10 +616,16 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
         }
         return false;
       };
-      auto scan = [&](int lo, int hi, float row2) {
-        if (row2 > thr) return;  // pruned by what was found since the row was chosen
+      // PREFETCH: once the first candidates of a row have been looked at, the table entries of the next row have
+      // arrived; its first points are requested into L1 / L2 so that the next scan does not start with a DRAM miss.
+      auto scan = [&](int lo, int hi, float row2, bool pf, int pf_lo, int pf_hi) {
+        if (row2 > thr) {  // pruned by what was found since the row was chosen
+          if (PREFETCH && pf && pf_hi > pf_lo) asm volatile("prefetch.global.L1 [%0];" ::"l"(grid.pts + pf_lo));
+          return;
+        }
         ncand += hi - lo;
         nrows++;
+        bool first = true;
 #pragma unroll 1
         for (int j = lo; j < hi; j += 4) {  // four independent float4 loads in flight
           const int rem = hi - j;
@@ -628,6 +635,8 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
           const float4 m2 = rem > 2 ? __ldg(grid.pts + j + 2) : far;
           const float4 m3 = rem > 3 ? __ldg(grid.pts + j + 3) : far;
           consider(m0, j); consider(m1, j + 1); consider(m2, j + 2); consider(m3, j + 3);
+          if (PREFETCH && first && pf && pf_hi > pf_lo) asm volatile("prefetch.global.L1 [%0];" ::"l"(grid.pts + pf_lo));
+          first = false;
         }
       };
       int loA = 0, hiA = 0, loB = 0, hiB = 0;
@@ -636,10 +645,10 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
 #pragma unroll 1
       while (haveA) {
         const bool haveB = next_row(loB, hiB, r2B);
-        scan(loA, hiA, r2A);
+        scan(loA, hiA, r2A, haveB, loB, hiB);
         if (!haveB) break;
         haveA = next_row(loA, hiA, r2A);
-        scan(loB, hiB, r2B);
+        scan(loB, hiB, r2B, haveA, loA, hiA);
       }
       // a 6th candidate within 1e-6 (relative) of the 5th: the FP32 metric cannot tell which of them the reference keeps
       if (bj[4] >= 0 && !(f_out > bf[4] * 1.000001f)) {
@@ -960,6 +969,7 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
   max_blocks = std::max(1, std::min(max_blocks, int(size_t(kNumSMs) * 2 / n_scans)));  // all scans' blocks resident in one wave
   // large batches (one lane per query, full tiles): search and fit as two kernels per iteration ("Batch path" above)
   const bool split = lpq == 1 && tile == 32 && env_int("PCR_LOAM_SPLIT", 1) != 0;
+  const bool search_prefetch = env_int("PCR_LOAM_PREFETCH", 0) != 0;
   // the fit kernel: one query per thread, one partial per warp
   const int fit_blocks = std::max(1, int((max_pts + kLoamBlock - 1) / kLoamBlock));
   const int max_warps = fit_blocks * kLoamWarps;
@@ -989,7 +999,8 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     const dim3 fgrid(static_cast<unsigned>(fit_blocks), static_cast<unsigned>(n_scans));
     for (int it = 0; it < prm.max_iters; it++) {
       if (split) {
-        loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
+        if (search_prefetch) loam_search_kernel<true><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
+        else loam_search_kernel<false><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
         loam_fit_kernel<false><<<fgrid, kLoamBlock, 0, s>>>(q, offsets.p, nb_buf.p, cnt_buf.p, total_q, prm, states.p, partials.p, max_warps, logs.p, 1,
                                                             nullptr, nullptr, perm);
         launches += 2;
@@ -1059,7 +1070,7 @@ int LoamDriver::linearize(const float4* src, size_t ns, const CellGrid& grid, co
       const dim3 sgrid(unsigned((ns + search_pb - 1) / search_pb), 1);
       const int fit_blocks = std::max(1, int((ns + kLoamBlock - 1) / kLoamBlock));
       partials.ensure(size_t(fit_blocks) * kLoamWarps * kNV);
-      loam_search_kernel<<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, ns);
+      loam_search_kernel<false><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, ns);
       loam_fit_kernel<true><<<dim3(fit_blocks, 1), kLoamBlock, 0, s>>>(q, offsets.p, nb_buf.p, cnt_buf.p, ns, prm, states.p, partials.p, fit_blocks * kLoamWarps,
                                                                        logs.p, 0, dbg_knn.p, dbg_status.p, perm);
       last_split = true;

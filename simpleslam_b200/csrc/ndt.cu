@@ -348,6 +348,9 @@ __device__ __forceinline__ void ndt_fill_request_warp(NdtScanState* st, double* 
   __syncwarp();
 }
 
+#ifndef PCR_NDT_FLOAT_BLOCKS
+#define PCR_NDT_FLOAT_BLOCKS 5  // resident blocks per SM of the float-path kernel (96 registers); 6 = 80 registers, measured slower
+#endif
 constexpr int kNdtGroup = 32;  // blocks per first-level group of a request's two-level reduction
 
 // totals of n_rows rows of kNdtNV partial sums: four interleaved slices per component (coalesced: a step of the loop reads
@@ -377,7 +380,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 
 template <int SEARCH, bool DOUBLE_PATH>
-__global__ void __launch_bounds__(kNdtBlock, DOUBLE_PATH ? 2 : 5)
+__global__ void __launch_bounds__(kNdtBlock, DOUBLE_PATH ? 2 : PCR_NDT_FLOAT_BLOCKS)
 ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, NdtTargetView tgt, NdtScanState* __restrict__ states,
                  NdtScanOut* __restrict__ outs, int32_t* __restrict__ float_round, int32_t* __restrict__ hess_round, int n_scans, int round,
                  int step, NdtCfg cfg, double* __restrict__ partials, unsigned* __restrict__ tickets, NdtProgress* progress,
@@ -790,9 +793,9 @@ void NdtDriver::launch_round(const float4* src, const NdtTarget& tgt, int search
 }
 
 static int wave_blocks(size_t n_scans, size_t max_pts) {
-  // one resident wave (5 blocks of 128 threads per SM), never more than one block per 128 points
+  // one resident wave (PCR_NDT_FLOAT_BLOCKS blocks of 128 threads per SM), never more than one block per 128 points
   const size_t full = (max_pts + kNdtBlock - 1) / kNdtBlock;
-  return int(std::max<size_t>(1, std::min<size_t>(size_t(kNumSMs) * 5, full * n_scans)));
+  return int(std::max<size_t>(1, std::min<size_t>(size_t(kNumSMs) * PCR_NDT_FLOAT_BLOCKS, full * n_scans)));
 }
 
 void NdtDriver::evaluate_one(const float4* src, size_t ns, const NdtTarget& tgt, int search, const NdtEvalParams& ep, NdtEvalResult& out,
