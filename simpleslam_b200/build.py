@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["api.cu", "voxel.cu", "knn.cu", "loam.cu", "ndt.cu", "vgicp.cu", "scancontext.cu"]
-HEADERS = ["common.cuh", "voxel.cuh", "loam.cuh", "ndt.cuh", "vgicp.cuh", "knn.cuh", "scancontext.cuh", "dev_linalg.cuh", "host_math.hpp", "ndt_logic.cuh", "vgicp_logic.cuh", "../../include/pcr_cuda.h"]
+HEADERS = ["common.cuh", "voxel.cuh", "loam.cuh", "ndt.cuh", "vgicp.cuh", "knn.cuh", "scancontext.cuh", "dev_linalg.cuh", "host_math.hpp", "ndt_logic.cuh", "vgicp_logic.cuh", "hostpack.hpp", "../../include/pcr_cuda.h"]
 LIB = os.environ.get("PCR_LIB_OUT") or os.path.join(CSRC, "libpcr_cuda.so")  # PCR_LIB_OUT + PCR_NVCC_EXTRA: tuning variants
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Wno-deprecated-declarations", "-Xcompiler", "-Wno-deprecated-declarations"]

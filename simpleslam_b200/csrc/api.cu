@@ -2,6 +2,7 @@
 // failures to an error code + pcr_last_error() text (SURVEY.md §8b "Errors").
 #include "../../include/pcr_cuda.h"
 #include "common.cuh"
+#include "hostpack.hpp"
 #include "voxel.cuh"
 #include "loam.cuh"
 #include "ndt.cuh"
@@ -71,6 +72,12 @@ struct pcr_ctx {
   cudaStream_t copy_stream = nullptr;
   DevBuf<unsigned char> raw_chunk[2];
   std::vector<cudaEvent_t> ev_up;
+
+  // uploads from pageable host memory: `cores` host threads pack into pinned staging, chunk by chunk (hostpack.hpp)
+  std::unique_ptr<HostPacker> packer;
+  PinBuf<float> pack_stage[2];
+  cudaEvent_t ev_pack[2] = {nullptr, nullptr};
+  size_t host_packed_bytes = 0;  // diagnostics: bytes that took this path in the last call
 
   KnnProfile knn_prof;  // VGICP k-NN kernel timing while profiling is on (target build + source covariances)
 
@@ -222,6 +229,7 @@ extern "C" void pcr_destroy(pcr_ctx* c) {
   cudaSetDevice(c->device);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   for (cudaEvent_t e : c->ev_up) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_pack) if (e) cudaEventDestroy(e);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -256,12 +264,57 @@ extern "C" int pcr_get_stats(const pcr_ctx* c, pcr_stats* s) {
 }
 
 // ---- uploads -------------------------------------------------------------------------------------------------------
+static bool is_pageable_host(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+constexpr size_t kPackChunkPts = size_t(1) << 20;  // 16 MB of float4 per staging buffer
+
+static bool use_host_pack(const pcr_ctx* c, const void* host, size_t bytes) {
+  const char* e = std::getenv("PCR_HOST_PACK");  // read on every call: a test / tuning knob
+  const int force = e ? (std::atoi(e) != 0 ? 1 : 0) : -1;
+  return force == 1 || (force < 0 && c->prm.cores > 0 && bytes >= (size_t(1) << 20) && is_pageable_host(host));
+}
+
+// host AoS records -> float4 records at `out` (device), ordered on stream s. Pageable sources of some size are packed by the
+// context's host threads into pinned staging and cross PCIe as 16-byte records while the next chunk is packed; everything
+// else is copied as it is and packed by pack_kernel. PCR_HOST_PACK=0 / 1 forces the choice (tests, A/B).
+static void upload_host_cloud(pcr_ctx* c, const void* host, size_t n, size_t stride, DevBuf<unsigned char>& raw, float4* out, cudaStream_t s) {
+  if (n == 0) return;
+  if (!use_host_pack(c, host, n * stride)) {
+    raw.ensure(n * stride);
+    PCR_CUDA_CHECK(cudaMemcpyAsync(raw.p, host, n * stride, cudaMemcpyHostToDevice, s));
+    pack_points(raw.p, n, stride, out, s);
+    return;
+  }
+  if (!c->packer) c->packer.reset(new HostPacker(c->prm.cores));
+  const size_t chunk = std::min(n, kPackChunkPts);
+  for (int b = 0; b < 2; b++) {
+    if (!c->ev_pack[b]) PCR_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_pack[b], cudaEventDisableTiming));
+    if (c->pack_stage[b].cap < chunk * 4) {
+      PCR_CUDA_CHECK(cudaEventSynchronize(c->ev_pack[b]));  // a copy of an earlier call may still read the buffer
+      c->pack_stage[b].ensure(kPackChunkPts * 4);
+    }
+  }
+  const unsigned char* bytes = static_cast<const unsigned char*>(host);
+  size_t k = 0;
+  for (size_t p0 = 0; p0 < n; p0 += kPackChunkPts, k++) {
+    const size_t cnt = std::min(kPackChunkPts, n - p0);
+    const int b = int(k & 1);
+    PCR_CUDA_CHECK(cudaEventSynchronize(c->ev_pack[b]));  // the copy that last read this staging buffer has completed
+    c->packer->pack(bytes + p0 * stride, cnt, stride, c->pack_stage[b].p);
+    PCR_CUDA_CHECK(cudaMemcpyAsync(out + p0, c->pack_stage[b].p, cnt * sizeof(float4), cudaMemcpyHostToDevice, s));
+    PCR_CUDA_CHECK(cudaEventRecord(c->ev_pack[b], s));
+  }
+  c->host_packed_bytes += n * stride;
+}
+
 static const float4* upload_points(pcr_ctx* c, const void* host, size_t n, size_t stride, DevBuf<unsigned char>& raw, DevBuf<float4>& out) {
   out.ensure(n + 1);
   if (n == 0) return out.p;
-  raw.ensure(n * stride);
-  PCR_CUDA_CHECK(cudaMemcpyAsync(raw.p, host, n * stride, cudaMemcpyHostToDevice, c->stream));
-  pack_points(raw.p, n, stride, out.p, c->stream);
+  upload_host_cloud(c, host, n, stride, raw, out.p, c->stream);
   return out.p;
 }
 static const float4* adopt_points(pcr_ctx* c, const void* dev, size_t n, size_t stride, DevBuf<float4>& out) {
@@ -476,8 +529,6 @@ extern "C" int pcr_batch_align(pcr_ctx* c, const void* src, const size_t* offset
   for (size_t i = 1; i <= n_scans; i++)
     if (i == n_scans || (offsets[i] - offsets[cut.back()]) * stride >= chunk_bytes) cut.push_back(i);
   const size_t nc = cut.size() - 1;
-  size_t max_bytes = 0;
-  for (size_t k = 0; k < nc; k++) max_bytes = std::max(max_bytes, (offsets[cut[k + 1]] - offsets[cut[k]]) * stride);
   if (!c->copy_stream) PCR_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   while (c->ev_up.size() < nc) {
     cudaEvent_t e;
@@ -485,15 +536,17 @@ extern "C" int pcr_batch_align(pcr_ctx* c, const void* src, const size_t* offset
     c->ev_up.push_back(e);
   }
   c->src.ensure(n + 1);
-  c->raw_chunk[0].ensure(max_bytes);
-  c->raw_chunk[1].ensure(max_bytes);
+  if (!use_host_pack(c, base, chunk_bytes)) {  // raw copies of two chunks in flight; sized here, not on the uploader thread
+    size_t max_bytes = 0;
+    for (size_t k = 0; k < nc; k++) max_bytes = std::max(max_bytes, (offsets[cut[k + 1]] - offsets[cut[k]]) * stride);
+    c->raw_chunk[0].ensure(max_bytes);
+    c->raw_chunk[1].ensure(max_bytes);
+  }
   PCR_CUDA_CHECK(cudaStreamSynchronize(c->stream));  // nothing of an earlier call still reads c->src
   auto upload = [&](size_t k) {
     const size_t p0 = offsets[cut[k]] - offsets[0], pn = offsets[cut[k + 1]] - offsets[cut[k]];
-    if (pn) {
-      PCR_CUDA_CHECK(cudaMemcpyAsync(c->raw_chunk[k & 1].p, base + p0 * stride, pn * stride, cudaMemcpyHostToDevice, c->copy_stream));
-      pack_points(c->raw_chunk[k & 1].p, pn, stride, c->src.p + p0, c->copy_stream);  // the copy stream is in order: buffer k & 1 is free again afterwards
-    }
+    if (pn)  // the copy stream is in order: staging buffer k & 1 is free again afterwards
+      upload_host_cloud(c, base + p0 * stride, pn, stride, c->raw_chunk[k & 1], c->src.p + p0, c->copy_stream);
     PCR_CUDA_CHECK(cudaEventRecord(c->ev_up[k], c->copy_stream));
   };
   // the uploads run on their own host thread: a copy from pageable memory blocks its caller while the driver stages it, and

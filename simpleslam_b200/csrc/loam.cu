@@ -969,7 +969,8 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
   max_blocks = std::max(1, std::min(max_blocks, int(size_t(kNumSMs) * 2 / n_scans)));  // all scans' blocks resident in one wave
   // large batches (one lane per query, full tiles): search and fit as two kernels per iteration ("Batch path" above)
   const bool split = lpq == 1 && tile == 32 && env_int("PCR_LOAM_SPLIT", 1) != 0;
-  const bool search_prefetch = env_int("PCR_LOAM_PREFETCH", 0) != 0;
+  // L1 prefetch of the next row's first points: +1..2.5 % when the map lives in DRAM (18.6 M points), -1 % when it fits in L2
+  const bool search_prefetch = env_int("PCR_LOAM_PREFETCH", grid.n > (size_t(4) << 20) ? 1 : 0) != 0;
   // the fit kernel: one query per thread, one partial per warp
   const int fit_blocks = std::max(1, int((max_pts + kLoamBlock - 1) / kLoamBlock));
   const int max_warps = fit_blocks * kLoamWarps;

@@ -39,19 +39,44 @@ def broadcast_target(ctx, dist, rank, device, src=0):
     return n, dt
 
 
+_GATHER_BUFFERS = {}
+
+
 def gather_poses(dist, world, local_T, local_conv, n_total, device):
-    """all-gather of the per-scan results (16 doubles + converged flag) of contiguous shards -> arrays of length n_total"""
+    """all-gather of the per-scan results (16 doubles + converged flag) of contiguous shards -> arrays of length n_total.
+    One host->device copy, one all_gather_into_tensor, one device->host copy per call; the buffers are kept between calls
+    (at 8 ranks the job step is a few milliseconds: a copy per rank and fresh allocations were a fifth of it)."""
     counts = [shard(n_total, r, world)[1] - shard(n_total, r, world)[0] for r in range(world)]
     mx = max(counts) if counts else 0
-    buf = torch.zeros((mx, 17), dtype=torch.float64, device=device)
+    if n_total == 0 or mx == 0:
+        return np.zeros((0, 4, 4)), np.zeros(0, bool)
+    key = (world, mx, str(device))
+    bufs = _GATHER_BUFFERS.get(key)
+    if bufs is None:
+        pin = device != "cpu" and str(device) != "cpu" and torch.cuda.is_available()
+        h_in = torch.zeros((mx, 17), dtype=torch.float64, pin_memory=pin)
+        h_out = torch.zeros((world * mx, 17), dtype=torch.float64, pin_memory=pin)
+        bufs = (h_in, h_out, torch.zeros((mx, 17), dtype=torch.float64, device=device), torch.zeros((world * mx, 17), dtype=torch.float64, device=device))
+        _GATHER_BUFFERS[key] = bufs
+    h_in, h_out, d_in, d_out = bufs
     k = len(local_T)
+    hv = h_in.numpy()
     if k:
-        buf[:k, :16] = torch.as_tensor(np.asarray(local_T, dtype=np.float64).reshape(k, 16), device=device)
-        buf[:k, 16] = torch.as_tensor(np.asarray(local_conv, dtype=np.float64), device=device)
-    outs = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(outs, buf)
-    T = np.concatenate([o[:c, :16].cpu().numpy().reshape(c, 4, 4) for o, c in zip(outs, counts)]) if n_total else np.zeros((0, 4, 4))
-    conv = np.concatenate([o[:c, 16].cpu().numpy() for o, c in zip(outs, counts)]) > 0.5 if n_total else np.zeros(0, bool)
+        hv[:k, :16] = np.asarray(local_T, dtype=np.float64).reshape(k, 16)
+        hv[:k, 16] = np.asarray(local_conv, dtype=np.float64)
+    hv[k:] = 0.0
+    d_in.copy_(h_in, non_blocking=True)
+    if hasattr(dist, "all_gather_into_tensor") and d_in.is_cuda:
+        dist.all_gather_into_tensor(d_out, d_in)
+    else:  # gloo (CPU tests): list form
+        outs = list(d_out.view(world, mx, 17).unbind(0))
+        dist.all_gather(outs, d_in)
+    h_out.copy_(d_out, non_blocking=True)
+    if d_out.is_cuda:
+        torch.cuda.current_stream().synchronize()
+    allv = h_out.numpy().reshape(world, mx, 17)
+    T = np.concatenate([allv[r, :c, :16].reshape(c, 4, 4) for r, c in enumerate(counts)])
+    conv = np.concatenate([allv[r, :c, 16] for r, c in enumerate(counts)]) > 0.5
     return T, conv
 
 

@@ -5,6 +5,7 @@
 #include "../../simpleslam_b200/csrc/host_math.hpp"
 #include "../../simpleslam_b200/csrc/ndt_logic.cuh"
 #include "../../simpleslam_b200/csrc/vgicp_logic.cuh"
+#include "../../simpleslam_b200/csrc/hostpack.hpp"
 #include <cstring>
 
 extern "C" {
@@ -88,5 +89,10 @@ void shim_vgicp_result(const void* stv, double* T, int* converged, int* nr_itera
   const pcr::VgicpState& st = *static_cast<const pcr::VgicpState*>(stv);
   for (int i = 0; i < 16; i++) T[i] = st.x0[i];
   *converged = st.converged; *nr_iterations = st.nr_iterations; *n_linearize = st.n_linearize; *n_error = st.n_error;
+}
+// host-side record packing of pageable uploads (hostpack.hpp): `repeat` calls on one pool
+void shim_host_pack(const unsigned char* src, size_t n, size_t stride, int threads, int repeat, float* out) {
+  pcr::HostPacker pk(threads);
+  for (int r = 0; r < repeat; r++) pk.pack(src, n, stride, out);
 }
 }

@@ -162,3 +162,29 @@ def test_corrupt_or_foreign_index_blobs_are_rejected(method, case_fn, tmp_path):
     assert np.array_equal(Ta, Tb)
     for x in (a, b, other, d):
         x.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["ndt", "loam"])
+def test_host_packed_upload_equals_plain_upload(method, monkeypatch):
+    """Clouds that come from pageable memory are packed to float4 by the context's host threads (hostpack.hpp) instead of
+    being copied raw and packed on the device: same bits on the device, same poses; all record layouts."""
+    case = data.ndt_case() if method == "ndt" else data.loam_case()
+    mid = capi.PCR_NDT if method == "ndt" else capi.PCR_LOAM
+    out = {}
+    for force in ("0", "1"):
+        monkeypatch.setenv("PCR_HOST_PACK", force)
+        ctx = capi.Context(mid)
+        ctx.set_target(case["dst"])
+        out[force] = ctx.align(case["src"], case["T_guess"])
+        # record layouts other than PointXYZI: xyz + padding (16 B), xyz + intensity at float 4 (20 B), bare xyz (12 B)
+        xyz = np.ascontiguousarray(case["src"][:, :3])
+        for width in (4, 5, 3):
+            rec = np.zeros((len(xyz), width), np.float32)
+            rec[:, :3] = xyz
+            T, conv = ctx.align(rec, case["T_guess"])
+            assert np.array_equal(T, out[force][0]) and conv == out[force][1], (force, width)
+        ds = ctx.voxel_downsample(case["dst"], 0.5)
+        out[force] += (ds,)
+    assert np.array_equal(out["0"][0], out["1"][0]) and out["0"][1] == out["1"][1]
+    assert np.array_equal(out["0"][2], out["1"][2])

@@ -129,3 +129,19 @@ def test_ndt_pose_euler_and_angle_tables(shim):
         assert np.allclose(jf, jd.astype(np.float32)) and hd.shape == (15, 3)
         # float-path quirk of the reference: row 6 (d1) of h_ang has +sy in the float table, -sy in the double one (:361, :383)
         assert np.isclose(hf[6, 2], -hd[6, 2].astype(np.float32)) or abs(hd[6, 2]) < 1e-7
+
+
+def test_host_packer_matches_the_device_pack_layout(shim):
+    """hostpack.hpp: `cores` host threads turn AoS records into (x, y, z, intensity | 0) float4 records — the host twin of
+    pack_kernel — for every record layout the C ABI accepts, any thread count, ragged sizes, repeated use of one pool."""
+    rng = np.random.RandomState(0)
+    for width, n in ((8, 100003), (8, 5), (4, 70001), (5, 33333), (3, 4097), (6, 12345)):
+        rec = rng.randn(n, width).astype(np.float32)
+        want = np.zeros((n, 4), np.float32)
+        want[:, :3] = rec[:, :3]
+        if width == 8 or width >= 5:
+            want[:, 3] = rec[:, 4]
+        for threads in (1, 3, 8):
+            out = np.full((n, 4), np.nan, np.float32)
+            shim.shim_host_pack(_p(rec), ctypes.c_size_t(n), ctypes.c_size_t(width * 4), threads, 3, _p(out))
+            assert np.array_equal(out, want), (width, n, threads)
