@@ -435,7 +435,9 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
 // the current bound, candidates are read four float4 at a time. (Measured and rejected, profiles/README.md: issuing all
 // rows' table entries up front and walking a per-lane list of non-empty rows from shared memory — fewer instructions,
 // better lane utilisation, but 1.5x slower: the extra table sectors of rows the bound would have pruned cost more than
-// the saved latency; warm-starting the bound from the previous iteration's winners — no change.)
+// the saved latency; warm-starting the bound from the previous iteration's winners — no change; a select-only top-5 update
+// — 27 % more instructions, lanes per instruction 14 -> 15, 6 % slower; one flattened (row switch | four candidates) loop
+// instead of the nested row / chunk loops — 24..47 % more instructions, 2..12 % slower.)
 // Selection runs on the FP32 metric f (|f - e| <= 3e-7 e against the exact FP64 metric e of the reference, both taken on
 // the same float coordinates): a lane keeps its five smallest (f, position) pairs and the smallest f that was looked at but
 // is NOT among them (f_out). Candidates and rows are pruned against thr = 1.00001 * min(gate, current 5th f), so whatever
@@ -1022,6 +1024,31 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
   PCR_CUDA_CHECK(cudaStreamSynchronize(s));
   PCR_CUDA_CHECK(cudaGetLastError());
   if (profile) PCR_CUDA_CHECK(cudaEventElapsedTime(&hot_ms, ev0, ev1));
+  if (split && env_int("PCR_LOAM_HIST", 0)) {
+    // diagnostics of the lane divergence in loam_search_kernel: rows / candidates per query of the LAST iteration, and how
+    // much of a warp's lock-step work its lanes really need (sum over the 32 queries / 32 x the largest)
+    std::vector<int2> hc(total_q);
+    PCR_CUDA_CHECK(cudaMemcpy(hc.data(), cnt_buf.p, total_q * sizeof(int2), cudaMemcpyDeviceToHost));
+    long long hist_r[27] = {0}, hist_c[12] = {0};
+    double sum_r = 0, max_r = 0, sum_c = 0, max_c = 0, sum_ch = 0, max_ch = 0;
+    for (size_t w = 0; w + 32 <= total_q; w += 32) {
+      int mr = 0, mc = 0, mch = 0;
+      for (int l = 0; l < 32; l++) {
+        const int c = hc[w + l].x, r = hc[w + l].y, ch = (c + 3) / 4 + r;  // four candidates per step + one step per row
+        hist_r[std::min(r, 26)]++;
+        hist_c[std::min(c / 16, 11)]++;
+        sum_r += r; sum_c += c; sum_ch += ch;
+        mr = std::max(mr, r); mc = std::max(mc, c); mch = std::max(mch, ch);
+      }
+      max_r += 32.0 * mr; max_c += 32.0 * mc; max_ch += 32.0 * mch;
+    }
+    std::fprintf(stderr, "[pcr loam hist] queries %zu | rows/query:", total_q);
+    for (int r = 0; r < 27; r++) if (hist_r[r]) std::fprintf(stderr, " %d:%.1f%%", r, 100.0 * double(hist_r[r]) / double(total_q));
+    std::fprintf(stderr, " | candidates/query (x16):");
+    for (int c = 0; c < 12; c++) if (hist_c[c]) std::fprintf(stderr, " %d:%.1f%%", c * 16, 100.0 * double(hist_c[c]) / double(total_q));
+    std::fprintf(stderr, " | warp lock-step efficiency: rows %.2f candidates %.2f steps (rows + candidates / 4) %.2f\n", sum_r / std::max(max_r, 1.0),
+                 sum_c / std::max(max_c, 1.0), sum_ch / std::max(max_ch, 1.0));
+  }
   for (size_t i = 0; i < n_scans; i++) {
     for (int q = 0; q < 16; q++) T[i * 16 + q] = hs[i].T[q];
     if (converged) converged[i] = hs[i].converged;
