@@ -144,6 +144,12 @@ int pcr_voxel_downsample(pcr_ctx* c, const void* pts, size_t n, size_t stride, f
 int pcr_voxel_downsample_device(pcr_ctx* c, const void* dev_pts, size_t n, size_t stride, float leaf, void* dev_out, size_t cap,
                                 size_t* m);
 
+/* One frame of frontend::LidarOdometry::generateOdom (frontend/src/LidarOdometry.cpp:170-184): mVoxelGrid.filter(scan) followed by
+ * mPcr->scan2Map(downsampled, submap, pose) against the resident target (pcr_set_target / pcr_submap_build). Same result as
+ * pcr_voxel_downsample + pcr_align, without moving the downsampled scan to the host and back. m (nullable): points left. */
+int pcr_downsample_align(pcr_ctx* c, const void* scan, size_t n, size_t stride, float leaf, double T[16], int32_t* converged, size_t* m);
+
+
 /* Submap assembly on the device. Replaces the body of MapManager::updateMap (frontend/src/MapManager.cpp:177-192) and of
  * LoopClosureManager::loopFindNearKeyframes (backend/src/LoopClosureManager.cpp:40-60): every keyframe cloud i is
  * transformed by poses[i] (cast to float, pcp::transformPointCloud, common/pcp/pcp.hpp:38-62), the clouds are

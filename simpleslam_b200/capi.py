@@ -19,7 +19,7 @@ PCR_LSQ_LM, PCR_LSQ_GN = 0, 1
 SYMBOLS = [
     "pcr_default_params", "pcr_create", "pcr_destroy", "pcr_last_error", "pcr_vgicp_init_for_lc", "pcr_set_profiling",
     "pcr_set_target", "pcr_set_target_device", "pcr_align", "pcr_align_device", "pcr_scan2map", "pcr_batch_align",
-    "pcr_batch_align_device", "pcr_fitness", "pcr_get_stats", "pcr_voxel_downsample", "pcr_voxel_downsample_device",
+    "pcr_batch_align_device", "pcr_fitness", "pcr_get_stats", "pcr_voxel_downsample", "pcr_voxel_downsample_device", "pcr_downsample_align",
     "pcr_target_blob_size", "pcr_target_export", "pcr_target_import", "pcr_debug_voxel", "pcr_loam_linearize",
     "pcr_loam_get_logs", "pcr_ndt_num_leaves", "pcr_ndt_get_leaves", "pcr_ndt_derivatives", "pcr_ndt_hessian",
     "pcr_gicp_covariances", "pcr_vgicp_num_voxels", "pcr_vgicp_get_voxels", "pcr_vgicp_evaluate",
@@ -321,6 +321,17 @@ class Context:
         self._ds_n = n
         self._ds_m = m.value
         return out[:m.value].copy()
+
+    def downsample_align(self, scan, leaf, T):
+        """one frame of LidarOdometry::generateOdom: voxel filter + scan2Map against the resident target, the downsampled
+        scan never leaves the device. Returns (pose, converged, points left)."""
+        a, n, st = _cloud(scan)
+        Tb = _T_in(T)
+        conv = ctypes.c_int32(0)
+        m = ctypes.c_size_t(0)
+        self._check(lib().pcr_downsample_align(self._h, _vp(a), ctypes.c_size_t(n), ctypes.c_size_t(st), ctypes.c_float(leaf), _vp(Tb),
+                                               ctypes.byref(conv), ctypes.byref(m)))
+        return _T_out(Tb), bool(conv.value), m.value
 
     def voxel_downsample_device(self, dev_in, n, stride, leaf, dev_out, cap):
         m = ctypes.c_size_t(0)

@@ -9,6 +9,7 @@
 #pragma once
 #include <types/basic.hpp>
 #include <pcr_cuda.h>
+#include <cstdio>
 
 #include <cmath>
 #include <cstring>
@@ -191,12 +192,12 @@ class LidarOdometry {
     }
     last_conv_ = true;
     if (!map_->isSubmapEmpty()) {
-      ds_.resize(scan->size() * 32);
-      size_t m = 0;
-      if (pcr_voxel_downsample(ctx_, scan->points.data(), scan->size(), sizeof(pt_t), grid_, ds_.data(), scan->size(), &m) != PCR_OK)
-        throw std::runtime_error(std::string("pcr_voxel_downsample: ") + pcr_last_error(ctx_));
+      // mVoxelGrid.filter (:170-171) + mPcr->scan2Map (:184): one call, the downsampled scan stays on the device
       int32_t conv = 0;
-      if (pcr_align(ctx_, ds_.data(), m, 32, init.matrix().data(), &conv) != PCR_OK) conv = 0;  // scan2Map failure is not fatal (:184-199)
+      if (pcr_downsample_align(ctx_, scan->points.data(), scan->size(), sizeof(pt_t), grid_, init.matrix().data(), &conv, nullptr) != PCR_OK) {
+        std::fprintf(stderr, "[PCR] %s\n", pcr_last_error(ctx_));
+        conv = 0;  // scan2Map failure is not fatal (:184-199)
+      }
       last_conv_ = conv != 0;
     }
     pose_t mob;
@@ -234,7 +235,6 @@ class LidarOdometry {
   bool odom2map_init_{false};
   bool last_conv_{true};
   double last_pos_[3] = {0, 0, 0};
-  std::vector<unsigned char> ds_;
 };
 
 }  // namespace frontend

@@ -697,6 +697,26 @@ extern "C" int pcr_voxel_downsample_device(pcr_ctx* c, const void* dev_pts, size
   PCR_API_END(c)
 }
 
+// One frame of LidarOdometry::generateOdom (LidarOdometry.cpp:170-184): mVoxelGrid.filter(scan) -> mPcr->scan2Map(ds, submap,
+// pose) against the resident target. The downsampled scan stays on the device (the two-call form downloads it and uploads it
+// again); its records go through the same 32-byte layout and pack step, so the registration sees the same bits.
+extern "C" int pcr_downsample_align(pcr_ctx* c, const void* scan, size_t n, size_t stride, float leaf, double T[16], int32_t* converged,
+                                    size_t* m_out) {
+  PCR_API_BEGIN(c)
+  if ((n && !scan) || !T || !(leaf > 0.f) || stride < 12 || stride % 4) return fail(c, PCR_ERR_INVALID, "bad arguments");
+  if (!c->has_target) return fail(c, PCR_ERR_NO_TARGET, "no target set");
+  const float4* d = upload_points(c, scan, n, stride, c->raw_src, c->ds_in);
+  c->ds_out.ensure(std::max<size_t>(n, 1) * 32);
+  size_t m = 0;
+  int rc = downsample_packed(c, d, n, leaf, c->ds_out.p, n, &m);
+  if (rc) return rc;
+  if (m_out) *m_out = m;
+  const float4* ds = adopt_points(c, c->ds_out.p, m, 32, c->src);
+  size_t offs[2] = {0, m};
+  return align_packed(c, ds, offs, 1, T, converged);
+  PCR_API_END(c)
+}
+
 // ---- submap assembly (MapManager::updateMap / loopFindNearKeyframes) ------------------------------------------------
 struct SubmapPart {
   const float4* src;

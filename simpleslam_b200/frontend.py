@@ -171,8 +171,9 @@ class LidarOdometry:
                     init_pose = self.global_odom[cidx][1].copy()
         conv = True
         if not self.map.isSubmapEmpty():
-            ds = self.ctx.voxel_downsample(scan, self.grid_size)       # mVoxelGrid.filter (:170-171)
-            init_pose, conv = self.ctx.align(ds, init_pose)            # mPcr->scan2Map against the resident submap (:184)
+            # mVoxelGrid.filter (:170-171) + mPcr->scan2Map against the resident submap (:184) in one call: the downsampled
+            # scan stays on the device (same result as voxel_downsample + align, tests/test_gpu_frontend.py)
+            init_pose, conv, _ = self.ctx.downsample_align(scan, self.grid_size, init_pose)
         self.converged.append(bool(conv))
         init_pose = six_dof_to_mobile(init_pose)                       # :211
         self.map.setCurPose(init_pose)

@@ -162,3 +162,24 @@ def test_loop_closure_batch_equals_serial(seq):
         assert g["converged"] == r["converged"] and g["accepted"] == r["accepted"] and g["map_points"] == r["map_points"]
         assert np.array_equal(g["T"], r["T"]) and g["fitness"] == r["fitness"]
     assert any(g["accepted"] for g in got) and not all(g["accepted"] for g in got)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["loam", "ndt", "vgicp"])
+def test_downsample_align_equals_the_two_calls(method):
+    """pcr_downsample_align (one frame of generateOdom: voxel filter + scan2Map, the downsampled scan stays on the device)
+    gives bit for bit the pose of pcr_voxel_downsample followed by pcr_align, and the same number of points."""
+    case = {"loam": data.loam_case, "ndt": data.ndt_case, "vgicp": data.vgicp_case}[method]()
+    mid = {"loam": capi.PCR_LOAM, "ndt": capi.PCR_NDT, "vgicp": capi.PCR_VGICP}[method]
+    ctx = capi.Context(mid)
+    ctx.set_target(case["dst"])
+    for leaf in (0.2, 0.5):
+        ds = ctx.voxel_downsample(case["src"], leaf)
+        T2, c2 = ctx.align(ds, case["T_guess"])
+        T1, c1, m = ctx.downsample_align(case["src"], leaf, case["T_guess"])
+        assert m == len(ds) and c1 == c2
+        assert np.array_equal(T1, T2)
+    # empty scan: nothing to register, the guess comes back unconverged like pcr_align of an empty cloud
+    T0, c0 = ctx.align(np.zeros((0, 8), np.float32), case["T_guess"])
+    T1, c1, m = ctx.downsample_align(np.zeros((0, 8), np.float32), 0.5, case["T_guess"])
+    assert m == 0 and c1 == c0 and np.array_equal(T0, T1)
