@@ -1166,7 +1166,7 @@ extern "C" int pcr_trim_device_cache(size_t* freed_bytes) {
   const size_t before = DevPool::cached_bytes();
   cudaDeviceSynchronize();
   DevPool::trim();
-  if (freed_bytes) *freed_bytes = before;
+  if (freed_bytes) *freed_bytes = before - DevPool::cached_bytes();  // buffers of a slab with a sibling in use stay parked
   return PCR_OK;
 }
 

@@ -39,6 +39,12 @@ class DevPool {
     while (c < bytes) c <<= 1;
     return c;
   }
+  // Small size classes are carved out of slabs: a miss for a class of at most 4 MiB allocates 16 MiB worth of buffers of that
+  // class with ONE cudaMalloc (2..16 of them) and parks the others. A frontend that caches one device copy per keyframe
+  // (pcr_submap_build) otherwise paid a 1-3 ms cudaMalloc on every other keyframe (PCR_TRACE=1, profiles/README.md).
+  static constexpr size_t kSlabMaxClass = size_t(4) << 20;
+  static constexpr size_t kSlabBytes = size_t(16) << 20;
+
   static void* alloc(size_t bytes, size_t& got, int& dev) {
     got = size_class(bytes);
     dev = 0;
@@ -46,22 +52,42 @@ class DevPool {
     {
       std::lock_guard<std::mutex> lk(mu());
       auto& lst = free_list()[std::make_pair(dev, got)];
-      if (!lst.empty()) { void* p = lst.back(); lst.pop_back(); return p; }
+      if (!lst.empty()) {
+        void* p = lst.back();
+        lst.pop_back();
+        auto it = child_slab().find(p);
+        if (it != child_slab().end()) slabs()[it->second].n_free--;
+        return p;
+      }
     }
+    const size_t k = got <= kSlabMaxClass ? std::min<size_t>(16, std::max<size_t>(2, kSlabBytes / got)) : 1;
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, got);
+    cudaError_t e = cudaMalloc(&p, got * k);
     if (e == cudaErrorMemoryAllocation) {  // out of memory: give the parked buffers back to the driver and retry once
       cudaGetLastError();
       trim();
-      e = cudaMalloc(&p, got);
+      e = cudaMalloc(&p, got * k);
     }
-    if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc(") + std::to_string(got) + " bytes) failed: " + cudaGetErrorString(e));
+    if (e != cudaSuccess) throw CudaError(std::string("cudaMalloc(") + std::to_string(got * k) + " bytes) failed: " + cudaGetErrorString(e));
+    if (k > 1) {
+      std::lock_guard<std::mutex> lk(mu());
+      const int id = int(slabs().size());
+      slabs().push_back(Slab{p, int(k), int(k) - 1, true});
+      auto& lst = free_list()[std::make_pair(dev, got)];
+      for (size_t c = 0; c < k; c++) {
+        void* child = static_cast<unsigned char*>(p) + c * got;
+        child_slab()[child] = id;
+        if (c) lst.push_back(child);
+      }
+    }
     return p;
   }
   // the caller guarantees that no work touching p is still in flight; dev = the device the allocation came from
   static void release(void* p, size_t got, int dev) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(mu());
+    auto it = child_slab().find(p);
+    if (it != child_slab().end()) slabs()[it->second].n_free++;
     free_list()[std::make_pair(dev, got)].push_back(p);
   }
   // bytes parked in the cache (all devices)
@@ -71,19 +97,32 @@ class DevPool {
     for (auto& kv : free_list()) t += kv.first.second * kv.second.size();
     return t;
   }
+  // hands parked buffers back to the driver; a slab goes back once all of its buffers are parked
   static void trim() {
     std::lock_guard<std::mutex> lk(mu());
     int cur = 0;
     const bool have = cudaGetDevice(&cur) == cudaSuccess;
     for (auto& kv : free_list()) {
-      if (!kv.second.empty()) cudaSetDevice(kv.first.first);
-      for (void* p : kv.second) cudaFree(p);
-      kv.second.clear();
+      if (kv.second.empty()) continue;
+      cudaSetDevice(kv.first.first);
+      std::vector<void*> keep;
+      for (void* p : kv.second) {
+        auto it = child_slab().find(p);
+        if (it == child_slab().end()) { cudaFree(p); continue; }
+        Slab& sl = slabs()[it->second];
+        if (sl.n_free < sl.n_children) { keep.push_back(p); continue; }  // a sibling is still in use
+        if (sl.live) { cudaFree(sl.base); sl.live = false; }
+        child_slab().erase(it);
+      }
+      kv.second.swap(keep);
     }
     if (have) cudaSetDevice(cur);
   }
 
  private:
+  struct Slab { void* base; int n_children; int n_free; bool live; };
+  static std::vector<Slab>& slabs() { static auto* v = new std::vector<Slab>(); return *v; }
+  static std::map<void*, int>& child_slab() { static auto* m = new std::map<void*, int>(); return *m; }
   static std::mutex& mu() { static std::mutex m; return m; }
   static std::map<std::pair<int, size_t>, std::vector<void*>>& free_list() {
     static auto* m = new std::map<std::pair<int, size_t>, std::vector<void*>>();  // leaked on purpose: outlives the CUDA context teardown

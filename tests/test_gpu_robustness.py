@@ -188,3 +188,25 @@ def test_host_packed_upload_equals_plain_upload(method, monkeypatch):
         out[force] += (ds,)
     assert np.array_equal(out["0"][0], out["1"][0]) and out["0"][1] == out["1"][1]
     assert np.array_equal(out["0"][2], out["1"][2])
+
+
+@pytest.mark.gpu
+def test_trim_device_cache_hands_buffers_back_and_the_library_keeps_working():
+    """pcr_trim_device_cache: buffers parked by destroyed contexts go back to the driver — whole slabs of small buffers only
+    once every buffer of the slab is parked — and later calls allocate again with the same results."""
+    case = data.loam_case()
+    res = []
+    for rep in range(2):
+        ctx = capi.Context(capi.PCR_LOAM)
+        keep = capi.Context(capi.PCR_LOAM)          # holds buffers of the same slabs while the other context goes away
+        keep.set_target(case["dst"][::7])
+        ctx.set_target(case["dst"])
+        res.append(ctx.align(case["src"], case["T_guess"])[0])
+        ctx.voxel_downsample(case["src"], 0.5)
+        ctx.close()
+        freed = capi.trim_device_cache()
+        assert freed > 0
+        assert np.array_equal(keep.align(case["src"], case["T_guess"])[0], keep.align(case["src"], case["T_guess"])[0])
+        keep.close()
+        capi.trim_device_cache()
+    assert np.array_equal(res[0], res[1])
