@@ -437,7 +437,8 @@ loam_iter_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
 // better lane utilisation, but 1.5x slower: the extra table sectors of rows the bound would have pruned cost more than
 // the saved latency; warm-starting the bound from the previous iteration's winners — no change; a select-only top-5 update
 // — 27 % more instructions, lanes per instruction 14 -> 15, 6 % slower; one flattened (row switch | four candidates) loop
-// instead of the nested row / chunk loops — 24..47 % more instructions, 2..12 % slower.)
+// instead of the nested row / chunk loops — 24..47 % more instructions, 2..12 % slower. STAGE (PCR_LOAM_STAGE=1) keeps the
+// cp.async double buffering of a lane's candidates selectable: parity-green, 13 % more instructions, 1..6 % slower.)
 // Selection runs on the FP32 metric f (|f - e| <= 3e-7 e against the exact FP64 metric e of the reference, both taken on
 // the same float coordinates): a lane keeps its five smallest (f, position) pairs and the smallest f that was looked at but
 // is NOT among them (f_out). Candidates and rows are pruned against thr = 1.00001 * min(gate, current 5th f), so whatever
@@ -533,7 +534,17 @@ __device__ __noinline__ void exact_search_one(const GridView& grid, float qf0, f
   for (int k = 0; k < 5; k++) wj[k] = best[k].j;
 }
 
-template <bool PREFETCH>
+// cp.async (LDGSTS) staging of a lane's candidates in a private shared-memory slot: the next four candidates of a row are
+// copied while the current four are examined, at no register cost (the register version of the same double buffering
+// needs 16 more registers and loses a resident block).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(unsigned(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool PREFETCH, bool STAGE>
 __global__ void __launch_bounds__(kLoamBlock, 4)
 loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ offs, GridView grid, LoamParams prm,
                    const LoamState* __restrict__ states, double slack, int max_ring, float4* __restrict__ nb_out, int2* __restrict__ cnt_out,
@@ -543,6 +554,7 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
   const LoamState* st = states + scan;
   if (st->done) return;
   __shared__ double sT[16];
+  __shared__ float4 s_stage[STAGE ? 2 * 4 * kLoamBlock : 1];  // [buffer][slot][thread]: conflict-free 16-byte accesses
   if (threadIdx.x < 16) sT[threadIdx.x] = st->T[threadIdx.x];
   __syncthreads();
   const int tid = threadIdx.x;
@@ -628,6 +640,31 @@ loam_search_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ 
         ncand += hi - lo;
         nrows++;
         bool first = true;
+        if (STAGE) {
+          auto issue = [&](int buf, int j, int rem) {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+              if (u < rem) cp_async16(&s_stage[(buf * 4 + u) * kLoamBlock + tid], grid.pts + j + u);
+            cp_async_commit();
+          };
+          int buf = 0;
+          issue(0, lo, hi - lo);
+#pragma unroll 1
+          for (int j = lo; j < hi; j += 4) {
+            const int rem = hi - j;
+            if (rem > 4) { issue(buf ^ 1, j + 4, rem - 4); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+            const float4 far = make_float4(INFINITY, 0.f, 0.f, 0.f);
+            const float4 m0 = s_stage[(buf * 4 + 0) * kLoamBlock + tid];
+            const float4 m1 = rem > 1 ? s_stage[(buf * 4 + 1) * kLoamBlock + tid] : far;
+            const float4 m2 = rem > 2 ? s_stage[(buf * 4 + 2) * kLoamBlock + tid] : far;
+            const float4 m3 = rem > 3 ? s_stage[(buf * 4 + 3) * kLoamBlock + tid] : far;
+            consider(m0, j); consider(m1, j + 1); consider(m2, j + 2); consider(m3, j + 3);
+            if (PREFETCH && first && pf && pf_hi > pf_lo) asm volatile("prefetch.global.L1 [%0];" ::"l"(grid.pts + pf_lo));
+            first = false;
+            buf ^= 1;
+          }
+          return;
+        }
 #pragma unroll 1
         for (int j = lo; j < hi; j += 4) {  // four independent float4 loads in flight
           const int rem = hi - j;
@@ -973,6 +1010,7 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
   const bool split = lpq == 1 && tile == 32 && env_int("PCR_LOAM_SPLIT", 1) != 0;
   // L1 prefetch of the next row's first points: +1..2.5 % when the map lives in DRAM (18.6 M points), -1 % when it fits in L2
   const bool search_prefetch = env_int("PCR_LOAM_PREFETCH", grid.n > (size_t(4) << 20) ? 1 : 0) != 0;
+  const bool search_stage = env_int("PCR_LOAM_STAGE", 0) != 0;
   // the fit kernel: one query per thread, one partial per warp
   const int fit_blocks = std::max(1, int((max_pts + kLoamBlock - 1) / kLoamBlock));
   const int max_warps = fit_blocks * kLoamWarps;
@@ -1002,8 +1040,10 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     const dim3 fgrid(static_cast<unsigned>(fit_blocks), static_cast<unsigned>(n_scans));
     for (int it = 0; it < prm.max_iters; it++) {
       if (split) {
-        if (search_prefetch) loam_search_kernel<true><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
-        else loam_search_kernel<false><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
+        if (search_stage && search_prefetch) loam_search_kernel<true, true><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
+        else if (search_stage) loam_search_kernel<false, true><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
+        else if (search_prefetch) loam_search_kernel<true, false><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
+        else loam_search_kernel<false, false><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
         loam_fit_kernel<false><<<fgrid, kLoamBlock, 0, s>>>(q, offsets.p, nb_buf.p, cnt_buf.p, total_q, prm, states.p, partials.p, max_warps, logs.p, 1,
                                                             nullptr, nullptr, perm);
         launches += 2;
@@ -1098,7 +1138,7 @@ int LoamDriver::linearize(const float4* src, size_t ns, const CellGrid& grid, co
       const dim3 sgrid(unsigned((ns + search_pb - 1) / search_pb), 1);
       const int fit_blocks = std::max(1, int((ns + kLoamBlock - 1) / kLoamBlock));
       partials.ensure(size_t(fit_blocks) * kLoamWarps * kNV);
-      loam_search_kernel<false><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, ns);
+      loam_search_kernel<false, false><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, ns);
       loam_fit_kernel<true><<<dim3(fit_blocks, 1), kLoamBlock, 0, s>>>(q, offsets.p, nb_buf.p, cnt_buf.p, ns, prm, states.p, partials.p, fit_blocks * kLoamWarps,
                                                                        logs.p, 0, dbg_knn.p, dbg_status.p, perm);
       last_split = true;
