@@ -966,6 +966,14 @@ LoamDriver::~LoamDriver() {
 
 static GridView make_view(const CellGrid& grid) { return view_of(grid); }
 
+static void launch_search(bool prefetch, bool stage, dim3 g, cudaStream_t s, const float4* q, const uint32_t* offs, const GridView& view, const LoamParams& prm,
+                          const LoamState* states, double slack, int max_ring, float4* nb, int2* cnt, size_t stride) {
+  if (stage && prefetch) loam_search_kernel<true, true><<<g, kLoamBlock, 0, s>>>(q, offs, view, prm, states, slack, max_ring, nb, cnt, stride);
+  else if (stage) loam_search_kernel<false, true><<<g, kLoamBlock, 0, s>>>(q, offs, view, prm, states, slack, max_ring, nb, cnt, stride);
+  else if (prefetch) loam_search_kernel<true, false><<<g, kLoamBlock, 0, s>>>(q, offs, view, prm, states, slack, max_ring, nb, cnt, stride);
+  else loam_search_kernel<false, false><<<g, kLoamBlock, 0, s>>>(q, offs, view, prm, states, slack, max_ring, nb, cnt, stride);
+}
+
 const float4* LoamDriver::sort_queries(const float4* src, const uint32_t* d_offs, size_t n_scans, size_t total_q, size_t max_pts, const uint32_t** perm,
                                        cudaStream_t s) {
   q_keys0.ensure(total_q); q_keys1.ensure(total_q); q_vals0.ensure(total_q); q_vals1.ensure(total_q); q_sorted.ensure(total_q);
@@ -1040,10 +1048,7 @@ int LoamDriver::align(const float4* src, const size_t* offs, size_t n_scans, con
     const dim3 fgrid(static_cast<unsigned>(fit_blocks), static_cast<unsigned>(n_scans));
     for (int it = 0; it < prm.max_iters; it++) {
       if (split) {
-        if (search_stage && search_prefetch) loam_search_kernel<true, true><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
-        else if (search_stage) loam_search_kernel<false, true><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
-        else if (search_prefetch) loam_search_kernel<true, false><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
-        else loam_search_kernel<false, false><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
+        launch_search(search_prefetch, search_stage, sgrid, s, q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, total_q);
         loam_fit_kernel<false><<<fgrid, kLoamBlock, 0, s>>>(q, offsets.p, nb_buf.p, cnt_buf.p, total_q, prm, states.p, partials.p, max_warps, logs.p, 1,
                                                             nullptr, nullptr, perm);
         launches += 2;
@@ -1138,7 +1143,8 @@ int LoamDriver::linearize(const float4* src, size_t ns, const CellGrid& grid, co
       const dim3 sgrid(unsigned((ns + search_pb - 1) / search_pb), 1);
       const int fit_blocks = std::max(1, int((ns + kLoamBlock - 1) / kLoamBlock));
       partials.ensure(size_t(fit_blocks) * kLoamWarps * kNV);
-      loam_search_kernel<false, false><<<sgrid, kLoamBlock, 0, s>>>(q, offsets.p, view, prm, states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, ns);
+      launch_search(env_int("PCR_LOAM_PREFETCH", grid.n > (size_t(4) << 20) ? 1 : 0) != 0, env_int("PCR_LOAM_STAGE", 0) != 0, sgrid, s, q, offsets.p, view, prm,
+                    states.p, slack, grid.max_ring, nb_buf.p, cnt_buf.p, ns);
       loam_fit_kernel<true><<<dim3(fit_blocks, 1), kLoamBlock, 0, s>>>(q, offsets.p, nb_buf.p, cnt_buf.p, ns, prm, states.p, partials.p, fit_blocks * kLoamWarps,
                                                                        logs.p, 0, dbg_knn.p, dbg_status.p, perm);
       last_split = true;

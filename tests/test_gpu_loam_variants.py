@@ -16,12 +16,13 @@ TOL_REL, TOL_T, TOL_R = 1e-6, 1e-4, 1e-4
 # (lanes per query, tile, split) -> environment
 VARIANTS = {
     "lpq1_split": dict(PCR_LOAM_LPQ="1", PCR_LOAM_TILE="32", PCR_LOAM_SPLIT="1"),   # the benchmarked batch path
+    "lpq1_split_staged": dict(PCR_LOAM_LPQ="1", PCR_LOAM_TILE="32", PCR_LOAM_SPLIT="1", PCR_LOAM_STAGE="1", PCR_LOAM_PREFETCH="1"),  # cp.async staging + L1 prefetch
     "lpq1_fused": dict(PCR_LOAM_LPQ="1", PCR_LOAM_TILE="32", PCR_LOAM_SPLIT="0"),
     "lpq2": dict(PCR_LOAM_LPQ="2", PCR_LOAM_TILE="32"),
     "lpq4": dict(PCR_LOAM_LPQ="4", PCR_LOAM_TILE="16"),
     "lpq8": dict(PCR_LOAM_LPQ="8", PCR_LOAM_TILE="4"),
 }
-KNOBS = ("PCR_LOAM_LPQ", "PCR_LOAM_TILE", "PCR_LOAM_SPLIT")
+KNOBS = ("PCR_LOAM_LPQ", "PCR_LOAM_TILE", "PCR_LOAM_SPLIT", "PCR_LOAM_STAGE", "PCR_LOAM_PREFETCH")
 
 
 @pytest.fixture
