@@ -346,12 +346,28 @@ vgicp_eval_kernel(const float4* __restrict__ src, const double* __restrict__ src
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // totals in a fixed order: four interleaved slices of the block rows per component (a step of the loop reads four
+  // consecutive rows, coalesced), two accumulators each — one thread per component walking all ~590 rows was a quarter of
+  // the kernel's 37 us
+  static_assert(4 * kVgNV <= kVgBlock, "four slices per component");
+  if (threadIdx.x < 4 * kVgNV) {
+    const int comp = threadIdx.x % kVgNV, slice = threadIdx.x / kVgNV;
+    const double* pb = partials + size_t(req) * max_blocks * kVgNV + comp;
+    double t0 = 0.0, t1 = 0.0;
+    int b = slice;
+    for (; b + 4 < nb; b += 8) {
+      t0 += __ldcg(pb + size_t(b) * kVgNV);
+      t1 += __ldcg(pb + size_t(b + 4) * kVgNV);
+    }
+    if (b < nb) t0 += __ldcg(pb + size_t(b) * kVgNV);
+    sred[slice * kVgNV + comp] = t0 + t1;
+  }
+  __syncthreads();
   if (threadIdx.x < kVgNV) {
-    const double* base = partials + size_t(req) * max_blocks * kVgNV + threadIdx.x;
-    double tsum = 0.0;
-    for (int b = 0; b < nb; b++) tsum += __ldcg(base + size_t(b) * kVgNV);
-    results[req].v[threadIdx.x] = tsum;
-    s_tot[threadIdx.x] = tsum;
+    const int c = threadIdx.x;
+    const double tsum = (sred[c] + sred[kVgNV + c]) + (sred[2 * kVgNV + c] + sred[3 * kVgNV + c]);
+    results[req].v[c] = tsum;
+    s_tot[c] = tsum;
   }
   __syncthreads();
   if (threadIdx.x == 0) tickets[req] = 0;
