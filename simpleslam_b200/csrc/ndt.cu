@@ -454,6 +454,7 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     }
   }
   const int n_items = n_active * bpr;
+  if (cfg.trace && blockIdx.x == 0 && tid == 0) counters->t_tail[6] = globaltimer_ns();
   const GridSpec& g = tgt.g;
   SmemAcc acc{sacc + tid};
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -569,6 +570,7 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
 
     // ---- 3. fixed-order block reduction straight out of shared memory: warp w owns components w, w+4, ...
     __syncthreads();
+    if (cfg.trace && blockIdx.x == 0 && tid == 0 && item == int(blockIdx.x)) counters->t_tail[7] = globaltimer_ns();
     for (int k = warp; k < kNdtNV; k += kNdtBlock / 32) {
       const double* col = sacc + k * kNdtBlock;
       double v = ((col[lane] + col[lane + 32]) + col[lane + 64]) + col[lane + 96];
@@ -577,6 +579,7 @@ ndt_round_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ of
     }
     if (lane == 0) __threadfence();  // one fence per writer warp, after all of its partial sums
     __syncthreads();
+    if (cfg.trace && blockIdx.x == 0 && tid == 0 && item == int(blockIdx.x)) counters->t_tail[8] = globaltimer_ns();
     // ---- 4. block partials -> totals in a fixed order, by whichever block finishes last. A single scan owns the whole wave
     // (740 partial rows, 170 KB): one block reading them all took as long as the evaluation itself, so requests with more
     // than kNdtGroup blocks are reduced in two levels - the last block of every group of kNdtGroup consecutive blocks adds
@@ -922,9 +925,11 @@ int NdtDriver::align(const float4* src, const size_t* offs, size_t n_scans, cons
     if (hc->finished != int(n)) throw CudaError("NDT: the evaluation rounds ended before every scan finished");
     if (cfg.trace) {  // the LAST request tail that ran: ns from its kernel's start
       const unsigned long long* t = hc->t_tail;
-      std::fprintf(stderr, "[pcr ndt tail] kernel start -> last block %.1f us, totals +%.1f, state step +%.1f, request filled +%.1f, state stored +%.1f\n",
+      std::fprintf(stderr, "[pcr ndt tail] kernel start -> last block %.1f us, totals +%.1f, state step +%.1f, request filled +%.1f, state stored +%.1f"
+                   " | block 0: request list +%.1f, its points +%.1f, partial row written +%.1f\n",
                    1e-3 * double((long long)(t[0] - t[4])), 1e-3 * double((long long)(t[1] - t[0])), 1e-3 * double((long long)(t[2] - t[1])),
-                   1e-3 * double((long long)(t[3] - t[2])), 1e-3 * double((long long)(t[5] - t[3])));
+                   1e-3 * double((long long)(t[3] - t[2])), 1e-3 * double((long long)(t[5] - t[3])), 1e-3 * double((long long)(t[6] - t[4])),
+                   1e-3 * double((long long)(t[7] - t[6])), 1e-3 * double((long long)(t[8] - t[7])));
     }
     if (profile) {
       float ms = 0.f;

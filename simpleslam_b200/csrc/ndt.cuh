@@ -53,7 +53,8 @@ struct NdtCounters {  // device
   int finished;
   int work_launches;      // kernel launches that had at least one request
   long long point_evals;  // source points pushed through the evaluation kernels
-  unsigned long long t_tail[6];  // NdtCfg::trace: %globaltimer at [4] kernel start, [0] last block found, [1] totals, [2] state step, [3] request filled, [5] state stored
+  unsigned long long t_tail[10];  // NdtCfg::trace: %globaltimer at [4] kernel start, [0] last block found, [1] totals, [2] state step, [3] request filled,
+                                  // [5] state stored; block 0 of the launch: [6] request list ready, [7] first item's points done, [8] its partial row written
 };
 
 // Scans may JOIN a running batch: a group of scans becomes eligible when its points have arrived on the device (an upload
