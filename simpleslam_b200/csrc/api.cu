@@ -275,7 +275,8 @@ constexpr size_t kPackChunkPts = size_t(1) << 20;  // 16 MB of float4 per stagin
 static bool use_host_pack(const pcr_ctx* c, const void* host, size_t bytes) {
   const char* e = std::getenv("PCR_HOST_PACK");  // read on every call: a test / tuning knob
   const int force = e ? (std::atoi(e) != 0 ? 1 : 0) : -1;
-  return force == 1 || (force < 0 && c->prm.cores > 0 && bytes >= (size_t(1) << 20) && is_pageable_host(host));
+  static const size_t min_bytes = [] { const char* m = std::getenv("PCR_HOST_PACK_MIN_KB"); return size_t(m ? std::max(1, std::atoi(m)) : 1024) << 10; }();
+  return force == 1 || (force < 0 && c->prm.cores > 0 && bytes >= min_bytes && is_pageable_host(host));
 }
 
 // host AoS records -> float4 records at `out` (device), ordered on stream s. Pageable sources of some size are packed by the
