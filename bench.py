@@ -206,6 +206,17 @@ def pose_err(Ta, Tb):
     return dt, float(2.0 * np.arcsin(min(1.0, f / (2.0 * np.sqrt(2.0)))))
 
 
+def host_threads(world):
+    """`cores` of the registers bench.py creates: the host threads that pack uploads (hostpack.hpp). The reference's shipped
+    value is 4; like the reference arm, which runs on every host core, the GPU arm may use the cores of the box: three
+    quarters of this rank's share, at most 12, at least the shipped 4 (PCR_BENCH_CORES overrides)."""
+    env = os.environ.get("PCR_BENCH_CORES")
+    if env:
+        return max(0, int(env))
+    share = (os.cpu_count() or 4) // max(1, world)
+    return int(max(4, min(12, (3 * share) // 4)))
+
+
 HOT_KERNEL = {"ndt": "ndt_round_kernel", "loam": "loam_search_kernel + loam_iter_kernel<fit> (one Gauss-Newton iteration)", "vgicp": "vgicp_eval_kernel"}
 
 
@@ -528,7 +539,8 @@ def measure_replicas(args, name, rank, world, local_rank, dist, dev, cpu=True):
                  "c4_ndt": capi.PCR_NDT}[name]
     static_map = name.startswith("c4")  # loc.cpp mode: the map is registered once, e2e = batches of host scans
     gn = name == "c3_vgicp_gn"
-    ctx = capi.Context(method_id, device=local_rank, **(dict(vgicp_optimizer=capi.PCR_LSQ_GN, vgicp_max_iters=20) if gn else {}))
+    n_host_threads = host_threads(world)
+    ctx = capi.Context(method_id, device=local_rank, cores=n_host_threads, **(dict(vgicp_optimizer=capi.PCR_LSQ_GN, vgicp_max_iters=20) if gn else {}))
     ds = lambda pts, leaf: ctx.voxel_downsample(pts, leaf)  # noqa: E731
     B = args.batch if args.batch > 0 else {"c2_ndt": 8, "c1_loam": 64, "c3_vgicp": 1, "c3_vgicp_gn": 1, "c4_loam": 128, "c4_ndt": 16}[name]
     n_steps_all = args.steps + args.warmup
@@ -725,6 +737,7 @@ def measure_replicas(args, name, rank, world, local_rank, dist, dev, cpu=True):
             "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / e2e_steps,
                     "what": "pcr_scan2map(src, dst, pose), ONE scan per call, pinned host buffers: target upload + index build + scan upload + align",
+                    "host_threads": n_host_threads, "host_threads_note": "pcr_params.cores of the register: host threads that pack uploads to 16-byte records (from 8 up also pinned sources)",
                     "pageable_ms_per_step": (1e3 * float(np.mean(e2e_pageable_t))) if e2e_pageable_t else None,
                     "pageable_value": (world / float(np.mean(e2e_pageable_t))) if e2e_pageable_t else None,
                     "static_map_ms_per_step": (1e3 * float(np.mean(e2e_cached_t))) if e2e_cached_t else None},
@@ -745,7 +758,8 @@ def measure_c4_job(args, method, rank, world, local_rank, dist, dev, cpu=True):
     import torch
     from simpleslam_b200 import capi, multigpu, workloads
     method_id = capi.PCR_NDT if method == "ndt" else capi.PCR_LOAM
-    ctx = capi.Context(method_id, device=local_rank)
+    n_host_threads = host_threads(world)
+    ctx = capi.Context(method_id, device=local_rank, cores=n_host_threads)
     ds = lambda pts, leaf: ctx.voxel_downsample(pts, leaf)  # noqa: E731
     n_job = args.job_scans
     lo, hi = multigpu.shard(n_job, rank, world)
@@ -904,6 +918,7 @@ def measure_c4_job(args, method, rank, world, local_rank, dist, dev, cpu=True):
             "e2e": {"value": e2e_value, "unit": "registrations/s", "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(n_job * (16 * 8 + 4)),
                     "ms_per_step": 1e3 * t_e2e / e2e_steps, "steps": e2e_steps,
                     "what": "pcr_batch_align of every rank's shard from PINNED host memory (scan upload + align + pose read-back) + the gather, per step",
+                    "host_threads": n_host_threads, "host_threads_note": "pcr_params.cores of the register: host threads that pack uploads to 16-byte records (from 8 up also pinned sources); the shipped default 4 gives plain DMA of the 32-byte records",
                     "pageable_ms_per_step": 1e3 * t_pg / 2, "pageable_value": 2 * n_job / t_pg},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpub, "parity": par,
             "setup": setup, "wall_s_timed_region": wall, "map_kernels": idx_roof,

@@ -47,7 +47,8 @@ typedef struct pcr_params {
   int32_t method;            /* PCR_LOAM | PCR_NDT | PCR_VGICP */
   int32_t device;            /* CUDA device ordinal */
   int32_t cores;             /* the reference's `cores` (PointCloudRegister.hpp:30-31): host threads that pack clouds uploaded from
-                                pageable memory into pinned staging; 0 = plain cudaMemcpy. Never used for arithmetic. */
+                                pageable memory into pinned staging (from 8 threads up also clouds in pinned memory: half the PCIe bytes);
+                                0 = plain cudaMemcpy. Never used for arithmetic. */
   /* LOAM (PCR/include/PCR/LoamRegister.hpp:30-40) */
   int32_t loam_max_iters;    /* 8 */
   float loam_max_knn_d2;     /* 1.0  (compared with a SQUARED distance, LoamRegister.cpp:59) */

@@ -17,7 +17,7 @@ for mb in (4, 64, 512):
     print(mb, "MB pageable", attr(a), "pinned", attr(p), attr(p))
 from simpleslam_b200 import capi
 import bench
-ctx = capi.Context(capi.PCR_NDT)
+ctx = capi.Context(capi.PCR_NDT, cores=int(os.environ.get("PCR_BENCH_CORES", "4")))
 wl = bench.build_workload("c2_ndt", lambda p, l: ctx.voxel_downsample(p, l), 2, 0)
 s, d, Tg, _ = bench.step_inputs(wl, 0)
 pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()

@@ -264,19 +264,29 @@ extern "C" int pcr_get_stats(const pcr_ctx* c, pcr_stats* s) {
 }
 
 // ---- uploads -------------------------------------------------------------------------------------------------------
-static bool is_pageable_host(const void* p) {
+// 0 = ordinary pageable host memory, 1 = pinned / registered host memory, 2 = anything else (device, managed)
+static int host_memory_kind(const void* p) {
   cudaPointerAttributes a{};
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
-  return a.type == cudaMemoryTypeUnregistered;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (a.type == cudaMemoryTypeUnregistered) return 0;
+  return a.type == cudaMemoryTypeHost ? 1 : 2;
 }
 
 constexpr size_t kPackChunkPts = size_t(1) << 20;  // 16 MB of float4 per staging buffer
+constexpr int kPackPinnedCores = 8;                // host threads from which packing beats the plain DMA of pinned 32-byte records
+constexpr size_t kPackPinnedBytes = size_t(256) << 20;  // a 67 MB map gains nothing (1.58 vs 1.50 ms): only batches that stream for tens of ms
 
+// Pageable sources are always packed by the host threads (the driver's own staging copy is single-threaded). Pinned
+// sources cross PCIe at ~50 GB/s as they are; packing them first halves the bytes but needs >= 8 threads to keep up
+// (measured on the 1024-scan job, 4.26 GB: plain DMA 85 ms, packed with 4 / 8 / 12 threads 115 / 82 / 76 ms).
 static bool use_host_pack(const pcr_ctx* c, const void* host, size_t bytes) {
   const char* e = std::getenv("PCR_HOST_PACK");  // read on every call: a test / tuning knob
   const int force = e ? (std::atoi(e) != 0 ? 1 : 0) : -1;
   static const size_t min_bytes = [] { const char* m = std::getenv("PCR_HOST_PACK_MIN_KB"); return size_t(m ? std::max(1, std::atoi(m)) : 1024) << 10; }();
-  return force == 1 || (force < 0 && c->prm.cores > 0 && bytes >= min_bytes && is_pageable_host(host));
+  if (force >= 0) return force == 1;
+  if (c->prm.cores <= 0 || bytes < min_bytes) return false;
+  const int kind = host_memory_kind(host);
+  return kind == 0 || (kind == 1 && c->prm.cores >= kPackPinnedCores && bytes >= kPackPinnedBytes);
 }
 
 // host AoS records -> float4 records at `out` (device), ordered on stream s. Pageable sources of some size are packed by the

@@ -1,9 +1,11 @@
-// Host side of an upload from PAGEABLE memory (what a pcl::PointCloud is): `cores` host threads — the reference's `cores`
+// Host side of an upload from host memory — always for PAGEABLE sources (what a pcl::PointCloud is), for pinned sources when
+// the register was given at least 8 `cores`: `cores` host threads — the reference's `cores`
 // setting (PCR/include/PCR/PointCloudRegister.hpp:30-31, config/params.json:5), which there sizes the OpenMP teams of the
 // registration itself — turn the caller's AoS records (pcl::PointXYZI: 32 bytes) into the 16-byte float4 records the
 // kernels read, into pinned staging memory, chunk by chunk; each chunk crosses PCIe while the next one is packed. A plain
 // cudaMemcpyAsync from pageable memory is staged by the driver on one thread (~11 GB/s measured) and moves the 16 bytes of
-// padding / ring / time of every record as well. Pinned or device sources never come here.
+// padding / ring / time of every record as well; a pinned source crosses PCIe at ~50 GB/s as it is, which 8 or more packing
+// threads beat by halving the bytes (api.cu: use_host_pack). Device sources never come here.
 #pragma once
 #include <condition_variable>
 #include <cstdint>
