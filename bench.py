@@ -208,13 +208,16 @@ def pose_err(Ta, Tb):
 
 def host_threads(world):
     """`cores` of the registers bench.py creates: the host threads that pack uploads (hostpack.hpp). The reference's shipped
-    value is 4; like the reference arm, which runs on every host core, the GPU arm may use the cores of the box: three
-    quarters of this rank's share, at most 12, at least the shipped 4 (PCR_BENCH_CORES overrides)."""
+    value is 4. One rank: like the reference arm, which runs on every host core, the GPU arm may use the cores of the box —
+    three quarters of them, at most 12 (from 8 up pinned batches are packed too: job e2e 12.0 k -> 13.5 k). Several ranks on
+    one host: the shipped 4 — the host's memory bandwidth is the bound there and packing pinned batches costs it twice the
+    traffic of a plain DMA (measured at N = 2: 22.4 k plain, 17.5 k packed). PCR_BENCH_CORES overrides."""
     env = os.environ.get("PCR_BENCH_CORES")
     if env:
         return max(0, int(env))
-    share = (os.cpu_count() or 4) // max(1, world)
-    return int(max(4, min(12, (3 * share) // 4)))
+    if world > 1:
+        return 4
+    return int(max(4, min(12, (3 * (os.cpu_count() or 4)) // 4)))
 
 
 HOT_KERNEL = {"ndt": "ndt_round_kernel", "loam": "loam_search_kernel + loam_iter_kernel<fit> (one Gauss-Newton iteration)", "vgicp": "vgicp_eval_kernel"}
