@@ -182,6 +182,13 @@ int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes);
 typedef void (*pcr_log_fn)(int32_t level, const char* message, void* user);
 void pcr_set_logger(pcr_log_fn cb, void* user);
 
+/* Page-lock a host buffer the caller keeps handing to the library (cudaHostRegister, portable): clouds in registered
+ * memory cross PCIe by plain DMA at full rate instead of being staged. Worth it for memory that is uploaded many times
+ * or is large (the static map of loc.cpp, a batch of scans); registering costs about a millisecond per 10 MB. The
+ * adaptor's target-cache mode can do it for `dst` (CudaRegister::enableTargetCache(true, true)). */
+int pcr_host_register(const void* p, size_t bytes);
+int pcr_host_unregister(const void* p);
+
 /* Device allocations released by contexts are parked in a process-wide, mutex-protected cache (cudaMalloc / cudaFree cost
  * milliseconds inside host-driven loops). A long-running caller can hand the parked buffers back to the driver at a quiet
  * moment: *freed_bytes (nullable) = bytes returned. Buffers owned by live contexts are not touched. */

@@ -19,7 +19,7 @@ PCR_LSQ_LM, PCR_LSQ_GN = 0, 1
 SYMBOLS = [
     "pcr_default_params", "pcr_create", "pcr_destroy", "pcr_last_error", "pcr_vgicp_init_for_lc", "pcr_set_profiling",
     "pcr_set_target", "pcr_set_target_device", "pcr_align", "pcr_align_device", "pcr_scan2map", "pcr_batch_align",
-    "pcr_batch_align_device", "pcr_fitness", "pcr_get_stats", "pcr_voxel_downsample", "pcr_voxel_downsample_device", "pcr_downsample_align",
+    "pcr_batch_align_device", "pcr_fitness", "pcr_get_stats", "pcr_voxel_downsample", "pcr_voxel_downsample_device", "pcr_downsample_align", "pcr_host_register", "pcr_host_unregister",
     "pcr_target_blob_size", "pcr_target_export", "pcr_target_import", "pcr_debug_voxel", "pcr_loam_linearize",
     "pcr_loam_get_logs", "pcr_ndt_num_leaves", "pcr_ndt_get_leaves", "pcr_ndt_derivatives", "pcr_ndt_hessian",
     "pcr_gicp_covariances", "pcr_vgicp_num_voxels", "pcr_vgicp_get_voxels", "pcr_vgicp_evaluate",
@@ -156,6 +156,17 @@ def set_logger(fn):
     cb = LOG_FN(lambda level, msg, user: fn(int(level), msg.decode(errors="replace")))
     _log_keepalive = cb   # the C side keeps the pointer
     lib().pcr_set_logger(cb, None)
+
+
+def host_register(a):
+    """page-lock a numpy array the caller keeps handing to the library (pcr_host_register)"""
+    rc = lib().pcr_host_register(ctypes.c_void_p(a.ctypes.data), ctypes.c_size_t(a.nbytes))
+    if rc != 0:
+        raise PcrError(rc, "pcr_host_register failed")
+
+
+def host_unregister(a):
+    lib().pcr_host_unregister(ctypes.c_void_p(a.ctypes.data))
 
 
 def trim_device_cache():

@@ -46,6 +46,8 @@ class CudaRegister : public PointCloudRegister {
   // optional static-map cache (the reference's VGICP caches by pointer identity, fast_vgicp_impl.hpp:57; loc.cpp feeds the
   // same submap pointer on every call). Off by default = reference semantics of LOAM / NDT: index rebuilt on every call.
   bool cache_target_{false};
+  bool pin_target_{false};              // page-lock the cached target's points (pcr_host_register) for its upload
+  const void* pinned_points_{nullptr};
   const void* cached_ptr_{nullptr};
   size_t cached_size_{0};
   unsigned long cached_generation_{0}, generation_{0};
@@ -66,12 +68,21 @@ class CudaRegister : public PointCloudRegister {
   }
 
  public:
-  ~CudaRegister() override { if (ctx_) pcr_destroy(ctx_); }
+  ~CudaRegister() override {
+    unpin();
+    if (ctx_) pcr_destroy(ctx_);
+  }
   CudaRegister(const CudaRegister&) = delete;
   CudaRegister& operator=(const CudaRegister&) = delete;
 
-  // localisation mode: keep the index of an unchanged target (same pointer, size and generation)
-  void enableTargetCache(bool on) { cache_target_ = on; cached_ptr_ = nullptr; }
+  // localisation mode: keep the index of an unchanged target (same pointer, size and generation). pin_target: page-lock the
+  // target's points before they are uploaded (a static map is large and, with bumpTargetGeneration, uploaded again and again)
+  void enableTargetCache(bool on, bool pin_target = false) {
+    cache_target_ = on;
+    pin_target_ = on && pin_target;
+    cached_ptr_ = nullptr;
+    if (!pin_target_) unpin();
+  }
   void bumpTargetGeneration() { ++generation_; }
 
   bool scan2Map(const PC_cPtr& src, const PC_cPtr& dst, pose_t& res) override {
@@ -80,6 +91,10 @@ class CudaRegister : public PointCloudRegister {
     int rc;
     const bool hit = cache_target_ && cached_ptr_ == dst.get() && cached_size_ == dst->size() && cached_generation_ == generation_;
     if (!hit) {
+      if (pin_target_ && pinned_points_ != dst->points.data()) {
+        unpin();
+        if (dst->size() && pcr_host_register(dst->points.data(), dst->size() * sizeof(pt_t)) == PCR_OK) pinned_points_ = dst->points.data();
+      }
       rc = pcr_set_target(ctx_, dst->points.data(), dst->size(), sizeof(pt_t));
       if (rc != PCR_OK) return fail("set_target");
       cached_ptr_ = dst.get(); cached_size_ = dst->size(); cached_generation_ = generation_;
@@ -92,6 +107,12 @@ class CudaRegister : public PointCloudRegister {
   }
 
   bool stats(pcr_stats& s) const { return pcr_get_stats(ctx_, &s) == PCR_OK; }
+
+ protected:
+  void unpin() {
+    if (pinned_points_) pcr_host_unregister(pinned_points_);
+    pinned_points_ = nullptr;
+  }
 
  private:
   bool fail(const char* what) {

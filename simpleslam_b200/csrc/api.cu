@@ -1173,6 +1173,25 @@ extern "C" int pcr_target_import(pcr_ctx* c, const void* dev_blob, size_t bytes)
   PCR_API_END(c)
 }
 
+extern "C" int pcr_host_register(const void* p, size_t bytes) {
+  if (!p || bytes == 0) return PCR_ERR_INVALID;
+  const cudaError_t e = cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return PCR_OK; }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    pcr_log(3, std::string("cudaHostRegister failed: ") + cudaGetErrorString(e));
+    return PCR_ERR_CUDA;
+  }
+  return PCR_OK;
+}
+
+extern "C" int pcr_host_unregister(const void* p) {
+  if (!p) return PCR_ERR_INVALID;
+  const cudaError_t e = cudaHostUnregister(const_cast<void*>(p));
+  if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorHostMemoryNotRegistered ? PCR_OK : PCR_ERR_CUDA; }
+  return PCR_OK;
+}
+
 extern "C" int pcr_trim_device_cache(size_t* freed_bytes) {
   const size_t before = DevPool::cached_bytes();
   cudaDeviceSynchronize();

@@ -68,6 +68,22 @@ int main(int argc, char** argv) {
     std::printf("%-5s converged=%d  t_err=%.4f m  yaw_err=%.5f rad  fitness=%.5f\n", names[k], int(conv), et, eyaw, reg->getFitnessScore());
     const double tol_t = (k == 1) ? 0.15 : 0.03, tol_r = (k == 1) ? 0.02 : 0.004;  // NDT stops at its 0.1 step epsilon
     if (!(et < tol_t) || !(std::fabs(eyaw) < tol_r)) bad++;
+    // localisation mode: target cached by (pointer, size, generation) and its points page-locked for the upload; the second
+    // call reuses the index, a bumped generation rebuilds it — same pose every time
+    auto* cr = dynamic_cast<PCR::CudaRegister*>(reg.get());
+    if (cr) {
+      cr->enableTargetCache(true, true);
+      pose_t p1, p2, p3;
+      const bool c1 = reg->scan2Map(src, dst, p1), c2 = reg->scan2Map(src, dst, p2);
+      cr->bumpTargetGeneration();
+      const bool c3 = reg->scan2Map(src, dst, p3);
+      bool same = c1 == conv && c2 == conv && c3 == conv;
+      for (int q = 0; q < 16; q++) same = same && p1.matrix().data()[q] == pose.matrix().data()[q] && p2.matrix().data()[q] == p1.matrix().data()[q] &&
+                                         p3.matrix().data()[q] == p1.matrix().data()[q];
+      std::printf("%-5s target cache + pinned target: %s\n", names[k], same ? "same pose" : "MISMATCH");
+      if (!same) bad++;
+      cr->enableTargetCache(false);
+    }
   }
   return bad ? 1 : 0;
 }

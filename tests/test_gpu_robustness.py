@@ -210,3 +210,23 @@ def test_trim_device_cache_hands_buffers_back_and_the_library_keeps_working():
         keep.close()
         capi.trim_device_cache()
     assert np.array_equal(res[0], res[1])
+
+
+@pytest.mark.gpu
+def test_registered_host_memory_gives_the_same_results():
+    """pcr_host_register / pcr_host_unregister: a page-locked map takes the plain-DMA upload path; same index, same pose.
+    Registering twice and unregistering memory that is not registered are not errors."""
+    case = data.ndt_case()
+    dst = np.array(case["dst"], copy=True)
+    ctx = capi.Context(capi.PCR_NDT)
+    ctx.set_target(dst)
+    T0, c0 = ctx.align(case["src"], case["T_guess"])
+    capi.host_register(dst)
+    capi.host_register(dst)
+    try:
+        ctx.set_target(dst)
+        T1, c1 = ctx.align(case["src"], case["T_guess"])
+    finally:
+        capi.host_unregister(dst)
+        capi.host_unregister(dst)
+    assert c0 == c1 and np.array_equal(T0, T1)
