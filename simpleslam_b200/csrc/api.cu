@@ -292,9 +292,11 @@ static bool use_host_pack(const pcr_ctx* c, const void* host, size_t bytes) {
 // host AoS records -> float4 records at `out` (device), ordered on stream s. Pageable sources of some size are packed by the
 // context's host threads into pinned staging and cross PCIe as 16-byte records while the next chunk is packed; everything
 // else is copied as it is and packed by pack_kernel. PCR_HOST_PACK=0 / 1 forces the choice (tests, A/B).
-static void upload_host_cloud(pcr_ctx* c, const void* host, size_t n, size_t stride, DevBuf<unsigned char>& raw, float4* out, cudaStream_t s) {
+// pack_mode: -1 = decide here from the size and kind of the source, 0 / 1 = the caller decided for a whole batch of chunks.
+static void upload_host_cloud(pcr_ctx* c, const void* host, size_t n, size_t stride, DevBuf<unsigned char>& raw, float4* out, cudaStream_t s,
+                              int pack_mode = -1) {
   if (n == 0) return;
-  if (!use_host_pack(c, host, n * stride)) {
+  if (!(pack_mode < 0 ? use_host_pack(c, host, n * stride) : pack_mode != 0)) {
     raw.ensure(n * stride);
     PCR_CUDA_CHECK(cudaMemcpyAsync(raw.p, host, n * stride, cudaMemcpyHostToDevice, s));
     pack_points(raw.p, n, stride, out, s);
@@ -547,7 +549,8 @@ extern "C" int pcr_batch_align(pcr_ctx* c, const void* src, const size_t* offset
     c->ev_up.push_back(e);
   }
   c->src.ensure(n + 1);
-  if (!use_host_pack(c, base, chunk_bytes)) {  // raw copies of two chunks in flight; sized here, not on the uploader thread
+  const bool pack = use_host_pack(c, base, n * stride);  // one decision for the whole batch: every chunk takes the same path
+  if (!pack) {  // raw copies of two chunks in flight; sized here, not on the uploader thread
     size_t max_bytes = 0;
     for (size_t k = 0; k < nc; k++) max_bytes = std::max(max_bytes, (offsets[cut[k + 1]] - offsets[cut[k]]) * stride);
     c->raw_chunk[0].ensure(max_bytes);
@@ -557,7 +560,7 @@ extern "C" int pcr_batch_align(pcr_ctx* c, const void* src, const size_t* offset
   auto upload = [&](size_t k) {
     const size_t p0 = offsets[cut[k]] - offsets[0], pn = offsets[cut[k + 1]] - offsets[cut[k]];
     if (pn)  // the copy stream is in order: staging buffer k & 1 is free again afterwards
-      upload_host_cloud(c, base + p0 * stride, pn, stride, c->raw_chunk[k & 1], c->src.p + p0, c->copy_stream);
+      upload_host_cloud(c, base + p0 * stride, pn, stride, c->raw_chunk[k & 1], c->src.p + p0, c->copy_stream, pack ? 1 : 0);
     PCR_CUDA_CHECK(cudaEventRecord(c->ev_up[k], c->copy_stream));
   };
   // the uploads run on their own host thread: a copy from pageable memory blocks its caller while the driver stages it, and
